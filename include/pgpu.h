@@ -1,0 +1,144 @@
+/*
+ * pgpu.h -- C ABI of libpaillier_b200.so, the B200 batch engine behind the
+ * hot path of sachaservan/paillier (modular exponentiation mod n^2, n^3, p^2, q^2).
+ *
+ * The reference has no FFI of its own for this path: its boundary is the
+ * gmp.Int method set of github.com/ncw/gmp (one cgo call per big-integer
+ * operation).  Each entry point below replaces N such call sequences by one
+ * batched call; the reference call sites are cited per function.
+ *
+ * Data layout: every big integer crosses the boundary as a fixed-width record
+ * of little-endian 32-bit limbs (little-endian bytes on the host).  Record
+ * widths are per key and reported by pgpu_ctx_widths():
+ *   n-width   : plaintexts m, randomness r, CRT outputs          (W_N  bytes)
+ *   n2-width  : level-1 ciphertexts, partial decryptions, ZKP a,b (W_N2 = 2*W_N bytes)
+ *   n3-width  : level-2 ciphertexts                               (W_N3 bytes, 0 if unsupported)
+ * Record i of a batch starts at byte i*width.  Key material is passed as
+ * big-endian magnitude bytes exactly as gmp.Int.Bytes() returns it.
+ *
+ * Ownership: the caller owns every buffer; the library keeps no host pointer
+ * after a call returns.  Calls block until the result is in the output buffer.
+ * A context is bound to one device and must be used by one thread at a time.
+ * All functions return PGPU_OK (0) or an error code; pgpu_last_error() gives
+ * the message.  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with PGPU_ERR_CUDA.
+ */
+#ifndef PGPU_H
+#define PGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgpu_ctx pgpu_ctx;
+
+enum {
+    PGPU_OK = 0,
+    PGPU_ERR_ARG = 1,            /* bad argument (null pointer, width mismatch, even modulus ...) */
+    PGPU_ERR_CUDA = 2,           /* CUDA runtime error or no device */
+    PGPU_ERR_NCCL = 3,
+    PGPU_ERR_STATE = 4,          /* key material for this call was not loaded into the context */
+    PGPU_ERR_NOT_INVERTIBLE = 5, /* ModInverse of a non-unit (undefined in the reference) */
+    PGPU_ERR_THRESHOLD = 6,      /* "Threshold not meet" / duplicate share ids, thresholdkey.go:77-89 */
+    PGPU_ERR_UNSUPPORTED = 7     /* key size outside the built kernel shapes */
+};
+
+/* modulus selectors for the generic entry points */
+enum { PGPU_MOD_N = 0, PGPU_MOD_N2 = 1, PGPU_MOD_N3 = 2 };
+
+int pgpu_version(void);
+int pgpu_device_count(int* count);
+/* message of the last failing call on this thread (ctx may be NULL) */
+const char* pgpu_last_error(const pgpu_ctx* ctx);
+
+/* ---- key state -------------------------------------------------------- */
+
+/* PublicKey{N} (paillier.go:46-56); g = n+1 is implied (paillier.go:147).
+ * Precomputes n^2, n^3 (GetN2/GetN3, paillier.go:72-90) and Montgomery constants. */
+int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_len);
+int pgpu_ctx_destroy(pgpu_ctx* ctx);
+/* record widths in bytes (any pointer may be NULL) */
+int pgpu_ctx_widths(const pgpu_ctx* ctx, size_t* w_n, size_t* w_n2, size_t* w_n3);
+/* run subsequent *_dev calls on this cudaStream_t (default: a stream owned by the context) */
+int pgpu_ctx_set_stream(pgpu_ctx* ctx, void* cuda_stream);
+
+/* SecretKey (paillier.go:59-62).  The reference keeps only Lambda = (p-1)(q-1)
+ * (paillier.go:152,172-176); pgpu_ctx_set_secret_lambda recovers p, q from
+ * (n, lambda).  Either call enables CRT decryption over p^2, q^2. */
+int pgpu_ctx_set_secret_pq(pgpu_ctx* ctx, const uint8_t* p_be, size_t p_len, const uint8_t* q_be, size_t q_len);
+int pgpu_ctx_set_secret_lambda(pgpu_ctx* ctx, const uint8_t* lambda_be, size_t lambda_len);
+
+/* ThresholdSecretKey / ThresholdPublicKey (thresholdkey.go:26-46).
+ * share may be NULL for a verifier/combiner-only context.  vkeys = l
+ * verification keys v_i as n2-width records (may be NULL). */
+int pgpu_ctx_set_threshold(pgpu_ctx* ctx, int total_servers, int threshold, int id,
+                           const uint8_t* share_be, size_t share_len,
+                           const uint8_t* v_be, size_t v_len,
+                           const void* vkeys_n2w);
+
+/* ---- batch entry points, host buffers ---------------------------------- */
+
+/* PublicKey.EncryptWithR (paillier.go:185-187,206-218), level 1:
+ * c[i] = (1 + m[i]*n) * r[i]^n mod n^2.   m, r: n-width; c: n2-width. */
+int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c);
+
+/* SecretKey.Decrypt (paillier.go:292-303), level 1, computed with CRT over
+ * p^2 and q^2.   c: n2-width; m: n-width. */
+int pgpu_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* m);
+
+/* PublicKey.ConstMult (operations.go:58-64): out[i] = c[i]^k[i] mod n^2 with
+ * k an unsigned record of k_bytes bytes (multiple of 4).  k = 0 yields 1. */
+int pgpu_const_mult(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out);
+
+/* PublicKey.Add over a whole batch (operations.go:11-29): out = prod c[i] mod n^2. */
+int pgpu_add_reduce(pgpu_ctx* ctx, size_t count, const void* c, void* out);
+/* PublicKey.Add(a[i], b[i]) element-wise: out[i] = a[i]*b[i] mod n^2. */
+int pgpu_add_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out);
+/* Encrypted dot product: out = prod c[i]^k[i] mod n^2 (ConstMult + Add fused). */
+int pgpu_dot_u64(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out);
+
+/* ThresholdSecretKey.PartialDecrypt (thresholdkey.go:192-201):
+ * out[i] = c[i]^(2*delta*share) mod n^2, delta = l!.   c, out: n2-width. */
+int pgpu_partial_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* out);
+
+/* Generic batched gmp.Int.Exp (mpz_powm) / Mul+Mod against one of the key's
+ * moduli; records are the modulus' width.  exp: per-item unsigned records of
+ * exp_bytes bytes.  These back ConstMult, the ZKP and DDLEQ entry points. */
+int pgpu_modexp(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const void* exp, size_t exp_bytes, void* out);
+int pgpu_modexp_shared(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const uint8_t* exp_be, size_t exp_len, void* out);
+int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const void* b, void* out);
+
+/* ---- same operations on device-resident buffers ------------------------ */
+/* Pointers are device pointers on the context's device; work is enqueued on
+ * the context's stream and NOT synchronised (the caller owns ordering). */
+int pgpu_encrypt_with_r_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c);
+int pgpu_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* m);
+int pgpu_partial_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out);
+int pgpu_const_mult_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out);
+int pgpu_add_reduce_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out);
+int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out);
+
+/* ---- introspection used by bench.py ------------------------------------ */
+/* number of kernels this context has launched so far */
+int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches);
+/* Montgomery multiplications per item of the compiled programs
+ * (what = 0 encrypt, 1 decrypt (both CRT halves), 2 partial decrypt): squarings and multiplies */
+int pgpu_ctx_program_cost(const pgpu_ctx* ctx, int what, uint32_t* limbs, uint32_t* n_sqr, uint32_t* n_mul);
+/* device time of the last call's kernels in milliseconds (host-buffer and *_dev
+ * calls record CUDA events around their launches when timing is enabled) */
+int pgpu_ctx_enable_timing(pgpu_ctx* ctx, int on);
+int pgpu_ctx_last_kernel_ms(pgpu_ctx* ctx, float* ms);
+
+/* host big-integer self test hook (tests/test_host_bignum.py): op 0 mul, 1 divmod-q,
+ * 2 mod, 3 modinv, 4 modexp, 5 isqrt.  Operands and result are big-endian bytes;
+ * *out_len holds the capacity on entry and the length on return. */
+int pgpu_selftest_bn(int op, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len,
+                     const uint8_t* m, size_t m_len, uint8_t* out, size_t* out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGPU_H */

@@ -1,0 +1,105 @@
+"""ctypes front-end of oracle/gmp_ref.c (libgmp restatement of the reference's call sequences).
+
+TEST INFRASTRUCTURE / CPU BASELINE ONLY -- see the header of gmp_ref.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libgmpref.so")
+
+
+def build() -> str:
+    src = os.path.join(_HERE, "gmp_ref.c")
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _be(x: int) -> bytes:
+    return x.to_bytes((x.bit_length() + 7) // 8, "big")
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+def cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def encrypt_with_r(n: int, m, r, w_n: int, threads: int = 0) -> np.ndarray:
+    m, r = _u8(m), _u8(r)
+    count = m.size // w_n
+    out = np.zeros(count * 2 * w_n, dtype=np.uint8)
+    nb = _be(n)
+    lib().ref_encrypt_with_r(nb, C.c_size_t(len(nb)), C.c_size_t(count), _p(m), _p(r), C.c_size_t(w_n), _p(out),
+                             C.c_size_t(2 * w_n), threads or cores())
+    return out
+
+
+def decrypt(n: int, lam: int, c, w_n: int, threads: int = 0) -> np.ndarray:
+    c = _u8(c)
+    count = c.size // (2 * w_n)
+    out = np.zeros(count * w_n, dtype=np.uint8)
+    nb, lb = _be(n), _be(lam)
+    lib().ref_decrypt(nb, C.c_size_t(len(nb)), lb, C.c_size_t(len(lb)), C.c_size_t(count), _p(c), C.c_size_t(2 * w_n),
+                      _p(out), C.c_size_t(w_n), threads or cores())
+    return out
+
+
+def partial_decrypt(n: int, share: int, l: int, c, w_n2: int, threads: int = 0) -> np.ndarray:
+    c = _u8(c)
+    count = c.size // w_n2
+    out = np.zeros(count * w_n2, dtype=np.uint8)
+    nb, sb = _be(n), _be(share)
+    lib().ref_partial_decrypt(nb, C.c_size_t(len(nb)), sb, C.c_size_t(len(sb)), l, C.c_size_t(count), _p(c), _p(out),
+                              C.c_size_t(w_n2), threads or cores())
+    return out
+
+
+def modexp(mod: int, base, width: int, exp, exp_bytes: int, threads: int = 0) -> np.ndarray:
+    base, exp = _u8(base), _u8(exp)
+    count = base.size // width
+    out = np.zeros(count * width, dtype=np.uint8)
+    mb = _be(mod)
+    lib().ref_modexp(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(base), C.c_size_t(width), _p(exp),
+                     C.c_size_t(exp_bytes), _p(out), threads or cores())
+    return out
+
+
+def modmul(mod: int, a, b, width: int, threads: int = 0) -> np.ndarray:
+    a, b = _u8(a), _u8(b)
+    count = a.size // width
+    out = np.zeros(count * width, dtype=np.uint8)
+    mb = _be(mod)
+    lib().ref_modmul(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(a), _p(b), C.c_size_t(width), _p(out), threads or cores())
+    return out
+
+
+def add_reduce(mod: int, c, width: int, threads: int = 0) -> np.ndarray:
+    c = _u8(c)
+    count = c.size // width
+    out = np.zeros(width, dtype=np.uint8)
+    mb = _be(mod)
+    lib().ref_add_reduce(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(c), C.c_size_t(width), _p(out), threads or cores())
+    return out

@@ -1,0 +1,189 @@
+// Light per-item epilogues and reductions around powm_vm.  They are <1 % of a
+// batch's multiply work, so they use plain one-thread-per-item limb loops
+// (the CRT recombination) or the warp-cooperative multiplier on a tree (the
+// Add reduction).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "mont.cuh"
+#include "aux.h"
+
+namespace pgpu {
+
+// ---------------------------------------------------------------------------
+// one-thread helpers on little-endian limb arrays of h limbs (h <= CRT_MAXH)
+// ---------------------------------------------------------------------------
+// r = a * b * 2^(-32h) mod n   (CIOS, n odd, a < 2^(32h), b < n)
+__device__ void st_mont(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* n, uint32_t np0, int h) {
+    uint32_t t[CRT_MAXH + 2];
+    for (int i = 0; i < h + 2; ++i) t[i] = 0;
+    for (int i = 0; i < h; ++i) {
+        uint64_t c = 0;
+        const uint32_t bi = b[i];
+        for (int j = 0; j < h; ++j) {
+            c += (uint64_t)a[j] * bi + t[j];
+            t[j] = (uint32_t)c; c >>= 32;
+        }
+        c += t[h]; t[h] = (uint32_t)c; t[h + 1] = (uint32_t)(c >> 32);
+        const uint32_t q = t[0] * np0;
+        c = ((uint64_t)n[0] * q + t[0]) >> 32;
+        for (int j = 1; j < h; ++j) {
+            c += (uint64_t)n[j] * q + t[j];
+            t[j - 1] = (uint32_t)c; c >>= 32;
+        }
+        c += t[h]; t[h - 1] = (uint32_t)c;
+        t[h] = t[h + 1] + (uint32_t)(c >> 32);
+    }
+    // conditional subtraction
+    bool ge = t[h] != 0;
+    if (!ge) {
+        ge = true;
+        for (int j = h - 1; j >= 0; --j) {
+            if (t[j] != n[j]) { ge = t[j] > n[j]; break; }
+        }
+    }
+    if (ge) {
+        int64_t bw = 0;
+        for (int j = 0; j < h; ++j) {
+            int64_t d = (int64_t)t[j] - n[j] - bw;
+            bw = d < 0; t[j] = (uint32_t)d;
+        }
+    }
+    for (int j = 0; j < h; ++j) r[j] = t[j];
+}
+
+// Paillier's L over one prime: k = (x - 1) / p for x = 1 (mod p), x < p^2,
+// as an exact division: k = (x - 1) * p^-1 mod 2^(32h)   (paillier.go:437-440)
+__device__ void st_L(uint32_t* k, const uint32_t* x, const uint32_t* pinv, int h) {
+    uint32_t y[CRT_MAXH];
+    int64_t bw = 1;
+    for (int j = 0; j < h; ++j) {
+        int64_t d = (int64_t)x[j] - bw;
+        bw = d < 0; y[j] = (uint32_t)d;
+    }
+    for (int j = 0; j < h; ++j) k[j] = 0;
+    for (int i = 0; i < h; ++i) {
+        uint64_t c = 0;
+        const uint32_t yi = y[i];
+        for (int j = 0; i + j < h; ++j) {
+            c += (uint64_t)yi * pinv[j] + k[i + j];
+            k[i + j] = (uint32_t)c; c >>= 32;
+        }
+    }
+}
+
+// m = CRT(m_p, m_q) with m_p = L_p(x_p) * h_p mod p, m_q = L_q(x_q) * h_q mod q
+// where x_p = c^(p-1) mod p^2, x_q = c^(q-1) mod q^2.  Equal to the reference's
+// L(c^lambda mod n^2) * lambda^-1 mod n (paillier.go:292-303) for every valid ciphertext.
+__global__ void crt_combine_kernel(CrtParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_items) return;
+    const int h = P.h;
+    const uint32_t* K = P.consts;
+    const uint32_t* p = K + 0 * h;  const uint32_t* q = K + 1 * h;
+    const uint32_t* pinv = K + 2 * h; const uint32_t* qinv = K + 3 * h;
+    const uint32_t* hpM = K + 4 * h; const uint32_t* hqM = K + 5 * h;
+    const uint32_t* cqM = K + 6 * h;
+    uint32_t mp[CRT_MAXH], mq[CRT_MAXH], a[CRT_MAXH], b[CRT_MAXH];
+    st_L(a, P.xp + (size_t)i * P.x_stride, pinv, h);
+    st_mont(mp, a, hpM, p, P.np0_p, h);
+    st_L(a, P.xq + (size_t)i * P.x_stride, qinv, h);
+    st_mont(mq, a, hqM, q, P.np0_q, h);
+    // t = (m_p - m_q) * q^-1 mod p
+    st_mont(a, mp, cqM, p, P.np0_p, h);
+    st_mont(b, mq, cqM, p, P.np0_p, h);
+    int64_t bw = 0;
+    for (int j = 0; j < h; ++j) {
+        int64_t d = (int64_t)a[j] - b[j] - bw;
+        bw = d < 0; a[j] = (uint32_t)d;
+    }
+    if (bw) {
+        uint64_t c = 0;
+        for (int j = 0; j < h; ++j) { c += (uint64_t)a[j] + p[j]; a[j] = (uint32_t)c; c >>= 32; }
+    }
+    // m = m_q + q * t
+    uint32_t r[2 * CRT_MAXH];
+    for (int j = 0; j < 2 * h; ++j) r[j] = j < h ? mq[j] : 0;
+    for (int ii = 0; ii < h; ++ii) {
+        uint64_t c = 0;
+        const uint32_t ti = a[ii];
+        for (int j = 0; j < h; ++j) {
+            c += (uint64_t)ti * q[j] + r[ii + j];
+            r[ii + j] = (uint32_t)c; c >>= 32;
+        }
+        for (int j = ii + h; c != 0 && j < 2 * h; ++j) {
+            c += r[j]; r[j] = (uint32_t)c; c >>= 32;
+        }
+    }
+    uint32_t* out = P.out + (size_t)i * P.out_stride;
+    for (uint32_t j = 0; j < P.out_limbs; ++j) out[j] = j < (uint32_t)(2 * h) ? r[j] : 0;
+}
+
+cudaError_t crt_combine_launch(const CrtParams& P, cudaStream_t stream) {
+    if (P.n_items == 0) return cudaSuccess;
+    const int threads = 64;
+    crt_combine_kernel<<<(P.n_items + threads - 1) / threads, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// PublicKey.Add over a batch (operations.go:11-29): one running Montgomery
+// product per group, then a shared-memory tree across the block's groups.
+// Missing items are padded with the plain integer 1, so every block performs
+// exactly GPB*rounds - 1 multiplications and the power of R^-1 picked up on the
+// way is known to the host, which folds the correction into a final multiply.
+// ---------------------------------------------------------------------------
+template <int TPI, int L>
+__global__ void __launch_bounds__(128) prod_reduce_kernel(ProdParams P) {
+    constexpr int S = TPI * L;
+    constexpr int GPB = 128 / TPI;
+    __shared__ uint32_t sm[GPB * S];
+    Mont<TPI, L> M;
+    M.init(P.mod, P.np0);
+    const int g = threadIdx.x / TPI, t = threadIdx.x & (TPI - 1);
+    const uint32_t G = gridDim.x * GPB, group = blockIdx.x * GPB + g;
+    const uint32_t rounds = P.n_items == 0 ? 1 : (P.n_items + G - 1) / G;
+    uint32_t acc[L], y[L];
+    for (uint32_t rd = 0; rd < rounds; ++rd) {
+        const uint32_t idx = rd * G + group;
+        if (idx < P.n_items) {
+            const uint32_t* p = P.in + (size_t)idx * S + t * L;
+#pragma unroll
+            for (int k = 0; k < L; ++k) y[k] = __ldg(p + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) y[k] = (t == 0 && k == 0) ? 1u : 0u;
+        }
+        if (rd == 0) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) acc[k] = y[k];
+        } else {
+            M.mul(acc, acc, y);
+        }
+    }
+    for (int stride = GPB / 2; stride >= 1; stride >>= 1) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) sm[g * S + t * L + k] = acc[k];
+        __syncthreads();
+        const int partner = (g + stride) % GPB;
+#pragma unroll
+        for (int k = 0; k < L; ++k) y[k] = sm[partner * S + t * L + k];
+        __syncthreads();
+        M.mul(acc, acc, y);
+    }
+    if (g == 0) {
+        uint32_t* o = P.partial + (size_t)blockIdx.x * S + t * L;
+#pragma unroll
+        for (int k = 0; k < L; ++k) o[k] = acc[k];
+    }
+}
+
+#define PGPU_PROD_SHAPES(X) X(4, 8) X(4, 16) X(8, 12) X(8, 16) X(8, 24)
+
+cudaError_t prod_reduce_launch(int tpi, int limbs, const ProdParams& P, int blocks, cudaStream_t stream) {
+#define X(T, LL) if (tpi == T && limbs == LL) { prod_reduce_kernel<T, LL><<<blocks, 128, 0, stream>>>(P); return cudaGetLastError(); }
+    PGPU_PROD_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pgpu

@@ -1,0 +1,965 @@
+// C ABI of libpaillier_b200.so (include/pgpu.h): key contexts, the host-side
+// compiler from reference functions to powm_vm micro-programs, and the batch
+// entry points.  No CPU arithmetic happens on a batch item here: the host only
+// derives per-key constants and programs once and then launches kernels.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pgpu.h"
+#include "aux.h"
+#include "bn_host.hpp"
+#include "launch.h"
+#include "vm.h"
+
+using namespace pgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(pgpu_ctx* ctx, int code, const std::string& msg);
+
+// ------------------------------------------------------------------ shapes
+struct Shape { int S, tpi, L; };
+
+// smallest built shape holding `limbs` limbs; override with PGPU_SHAPE_<S>="tpi,L"
+bool pick_shape(size_t limbs, Shape& out) {
+    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 8, 12}, {128, 8, 16}, {192, 8, 24}};
+    for (const Shape& s : defaults) {
+        if ((size_t)s.S >= limbs) {
+            out = s;
+            char name[32];
+            snprintf(name, sizeof name, "PGPU_SHAPE_%d", s.S);
+            if (const char* e = getenv(name)) {
+                int t = 0, l = 0;
+                if (sscanf(e, "%d,%d", &t, &l) == 2 && t * l == s.S && vm_occupancy(t, l) > 0) { out.tpi = t; out.L = l; }
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+// kconst slots shared by every modulus
+enum : uint32_t { K_R2 = 0, K_R1 = 1, K_ONE = 2, K_R3 = 3, K_NR2 = 4, K_FIX = 5, K_USER0 = 6, K_SLOTS = 16 };
+
+struct Program {
+    std::vector<uint32_t> ops;
+    uint32_t* d_ops = nullptr;
+    uint32_t n_sqr = 0, n_mul = 0, tbl_entries = 0;
+    void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); }
+    void use_slot(uint32_t s) { tbl_entries = std::max(tbl_entries, s + 1); }
+};
+
+struct ModCtx {
+    bool ready = false;
+    Shape sh{};
+    BigU N, R1, R2, R3;
+    uint32_t np0 = 0;
+    uint32_t* d_mod = nullptr;
+    uint32_t* d_kconst = nullptr;   // K_SLOTS records of S limbs
+    int blocks_per_sm = 0;
+};
+
+}  // namespace
+
+struct pgpu_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    BigU n, n2, n3;
+    size_t wn = 0;         // limbs of an n-width record
+    ModCtx m_n, m_n2, m_n3, m_p2, m_q2;
+
+    // secret key
+    bool has_secret = false;
+    BigU p, q;
+    uint32_t* d_crt = nullptr;
+    uint32_t crt_np0_p = 0, crt_np0_q = 0;
+    int crt_h = 0;
+
+    // threshold key
+    bool has_threshold = false, has_share = false;
+    int tk_l = 0, tk_w = 0, tk_id = 0;
+    BigU tk_share, tk_v, tk_delta;
+    std::vector<BigU> tk_vi;
+
+    Program prog_enc, prog_dec_p, prog_dec_q, prog_pdec;
+    std::map<std::string, Program> prog_cache;
+
+    // scratch
+    uint32_t* d_table = nullptr; size_t table_limbs = 0;
+    void* d_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
+
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+namespace {
+
+int fail(pgpu_ctx* ctx, int code, const std::string& msg) {
+    g_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(ctx, PGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v) {
+    CU(ctx, cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PGPU_OK;
+}
+
+int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v) {
+    return upload(ctx, m.d_kconst + (size_t)slot * m.sh.S, v.limbs(m.sh.S));
+}
+
+int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
+    if (!N.is_odd()) return fail(ctx, PGPU_ERR_ARG, "modulus must be odd");
+    if (!pick_shape(N.v.size(), m.sh)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus wider than the built kernel shapes");
+    m.N = N;
+    const BigU R = BigU::pow2(32 * (size_t)m.sh.S);
+    m.R1 = R % N;
+    m.R2 = (m.R1 * m.R1) % N;
+    m.R3 = (m.R2 * m.R1) % N;
+    m.np0 = mont_np0(N.v[0]);
+    CU(ctx, cudaMalloc(&m.d_mod, (size_t)m.sh.S * 4));
+    CU(ctx, cudaMalloc(&m.d_kconst, (size_t)K_SLOTS * m.sh.S * 4));
+    CU(ctx, cudaMemsetAsync(m.d_kconst, 0, (size_t)K_SLOTS * m.sh.S * 4, ctx->stream));
+    int rc;
+    if ((rc = upload(ctx, m.d_mod, N.limbs(m.sh.S)))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R2, m.R2))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R1, m.R1))) return rc;
+    if ((rc = set_kconst(ctx, m, K_ONE, BigU(1)))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R3, m.R3))) return rc;
+    m.blocks_per_sm = vm_occupancy(m.sh.tpi, m.sh.L);
+    if (m.blocks_per_sm <= 0) return fail(ctx, PGPU_ERR_CUDA, "powm_vm occupancy query failed for shape");
+    m.ready = true;
+    return PGPU_OK;
+}
+
+void modctx_free(ModCtx& m) {
+    if (m.d_mod) cudaFree(m.d_mod);
+    if (m.d_kconst) cudaFree(m.d_kconst);
+    m = ModCtx();
+}
+
+// ------------------------------------------------------- program compiler
+int choose_window(size_t bits) {
+    int best = 1; double best_cost = 1e300;
+    for (int w = 1; w <= 7; ++w) {
+        double cost = (w == 1 ? 0.0 : (double)(1u << (w - 1))) + (double)bits / (w + 1);
+        if (cost < best_cost) { best_cost = cost; best = w; }
+    }
+    return best;
+}
+
+// x holds the base in Montgomery form; afterwards x = base^e (Montgomery form).
+// Sliding window over the shared exponent e: odd powers in T[tb .. tb+2^(w-1)),
+// base^2 in T[tb+2^(w-1)].   gmp semantics: e = 0 gives 1.
+void emit_pow_shared(Program& P, const BigU& e, uint32_t tb) {
+    const size_t bits = e.bitlen();
+    if (bits == 0) { P.emit(OP_LDC, K_R1); return; }
+    const int w = choose_window(bits);
+    const uint32_t nodd = 1u << (w - 1);
+    P.emit(OP_STT, tb); P.use_slot(tb);
+    if (w > 1) {
+        const uint32_t sq = tb + nodd;
+        P.emit(OP_SQR, 1); P.n_sqr += 1;
+        P.emit(OP_STT, sq); P.use_slot(sq);
+        for (uint32_t i = 1; i < nodd; ++i) {   // x = T[i-1] * base^2
+            if (i == 1) P.emit(OP_LDT, tb);
+            P.emit(OP_MULT, sq); P.n_mul += 1;
+            P.emit(OP_STT, tb + i);
+        }
+    }
+    bool first = true;
+    uint32_t pending = 0;
+    long i = (long)bits - 1;
+    while (i >= 0) {
+        if (!e.bit(i)) { ++pending; --i; continue; }
+        long j = std::max<long>(i - w + 1, 0);
+        while (!e.bit(j)) ++j;
+        uint32_t val = 0;
+        for (long k = i; k >= j; --k) val = (val << 1) | (e.bit(k) ? 1u : 0u);
+        const uint32_t len = (uint32_t)(i - j + 1), idx = tb + (val >> 1);
+        if (first) {
+            P.emit(OP_LDT, idx);
+            first = false;
+        } else {
+            uint32_t nsq = pending + len;
+            if (nsq > 0xfff) { P.emit(OP_SQR, nsq - len); nsq = len; }
+            P.emit(OP_SQMT, nsq | (idx << 12));
+            P.n_sqr += pending + len; P.n_mul += 1;
+        }
+        pending = 0;
+        i = j - 1;
+    }
+    if (pending) { P.emit(OP_SQR, pending); P.n_sqr += pending; }
+}
+
+// per-item exponents of exp_bits bits (OP_WIN): full table T[tb .. tb+2^w), fixed window
+void emit_pow_items(Program& P, size_t exp_bits, uint32_t tb) {
+    int w = 1;
+    { double best = 1e300; for (int c = 1; c <= 6; ++c) { double cost = (double)(1u << c) + (double)exp_bits / c; if (cost < best) { best = cost; w = c; } } }
+    const uint32_t n = 1u << w;
+    // T[tb+1] = base, T[tb] = 1, T[tb+i] = T[tb+i-1] * base
+    P.emit(OP_STT, tb + 1);
+    for (uint32_t i = 2; i < n; ++i) { P.emit(OP_MULT, tb + 1); P.n_mul += 1; P.emit(OP_STT, tb + i); }
+    P.emit(OP_LDC, K_R1); P.emit(OP_STT, tb);
+    P.use_slot(tb + n - 1);
+    const size_t nwin = (exp_bits + w - 1) / w;
+    for (size_t k = nwin; k-- > 0;) {
+        // x starts at 1, so the first squarings are of 1; keep the program uniform
+        P.emit(OP_WIN, (uint32_t)(k * w) | ((uint32_t)w << 20) | (tb << 24));
+        P.n_sqr += w; P.n_mul += 1;
+    }
+}
+
+int program_upload(pgpu_ctx* ctx, Program& P) {
+    P.ops.push_back(vm_op(OP_END, 0));
+    if (P.d_ops) cudaFree(P.d_ops);
+    CU(ctx, cudaMalloc(&P.d_ops, P.ops.size() * 4));
+    return upload(ctx, P.d_ops, P.ops);
+}
+
+void program_free(Program& P) { if (P.d_ops) cudaFree(P.d_ops); P = Program(); }
+
+// ------------------------------------------------------------- launching
+struct IoDesc { const uint32_t* ptr; uint32_t stride, limbs; };
+
+int ensure_table(pgpu_ctx* ctx, size_t limbs) {
+    if (limbs <= ctx->table_limbs) return PGPU_OK;
+    if (ctx->d_table) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_limbs = 0; }
+    CU(ctx, cudaMalloc(&ctx->d_table, limbs * 4));
+    ctx->table_limbs = limbs;
+    return PGPU_OK;
+}
+
+int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
+           const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
+           const uint32_t* exp = nullptr, uint32_t exp_stride = 0) {
+    if (count == 0) return PGPU_OK;
+    if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
+    const int gpb = VM_BLOCK_THREADS / m.sh.tpi;
+    const size_t max_blocks = (size_t)ctx->sms * m.blocks_per_sm;
+    const size_t want = (count + gpb - 1) / gpb;
+    const int blocks = (int)std::min(max_blocks, want);
+    VmParams P{};
+    P.prog = prog.d_ops;
+    P.n_items = (uint32_t)count;
+    P.mod = m.d_mod; P.np0 = m.np0; P.kconst = m.d_kconst;
+    for (int i = 0; i < n_in; ++i) { P.in[i] = ins[i].ptr; P.in_stride[i] = ins[i].stride; P.in_limbs[i] = ins[i].limbs; }
+    P.out[0] = out; P.out_stride[0] = out_stride; P.out_limbs[0] = out_limbs;
+    P.exp = exp; P.exp_stride = exp_stride;
+    P.n_groups = (uint32_t)blocks * gpb;
+    int rc = ensure_table(ctx, (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S);
+    if (rc) return rc;
+    P.table = ctx->d_table;
+    CU(ctx, vm_launch(m.sh.tpi, m.sh.L, P, blocks, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->stage_bytes[slot] < bytes) {
+        if (ctx->d_stage[slot]) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_stage[slot]); ctx->d_stage[slot] = nullptr; ctx->stage_bytes[slot] = 0; }
+        CU(ctx, cudaMalloc(&ctx->d_stage[slot], std::max<size_t>(bytes, 256)));
+        ctx->stage_bytes[slot] = std::max<size_t>(bytes, 256);
+    }
+    *out = ctx->d_stage[slot];
+    return PGPU_OK;
+}
+
+struct TimedScope {
+    pgpu_ctx* c;
+    explicit TimedScope(pgpu_ctx* ctx) : c(ctx) { if (c->timing) { cudaEventRecord(c->ev0, c->stream); } }
+    ~TimedScope() { if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->ev_valid = true; } }
+};
+
+ModCtx* select_mod(pgpu_ctx* ctx, int modsel) {
+    switch (modsel) {
+        case PGPU_MOD_N: return ctx->m_n.ready ? &ctx->m_n : nullptr;
+        case PGPU_MOD_N2: return ctx->m_n2.ready ? &ctx->m_n2 : nullptr;
+        case PGPU_MOD_N3: return ctx->m_n3.ready ? &ctx->m_n3 : nullptr;
+    }
+    return nullptr;
+}
+
+// ---------------------------------------------------- compiled key programs
+// EncryptWithR, level 1 (paillier.go:206-218) with the g = n+1 shortcut:
+// c = (1 + m*n) * r^n mod n^2.   in0 = r, in1 = m.
+int build_encrypt(pgpu_ctx* ctx) {
+    Program& P = ctx->prog_enc;
+    program_free(P);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;           // r -> Montgomery form
+    emit_pow_shared(P, ctx->n, 0);              // r^n
+    const uint32_t RES = P.tbl_entries;         // next free table slot
+    P.emit(OP_STT, RES); P.use_slot(RES);
+    P.emit(OP_LDI, 1);
+    P.emit(OP_MULC, K_NR2); P.n_mul++;          // m*n (Montgomery form), exact since m*n < n^2
+    P.emit(OP_ADDC, K_R1);                      // + 1
+    P.emit(OP_MULT, RES); P.n_mul++;
+    P.emit(OP_MULC, K_ONE); P.n_mul++;          // out of Montgomery form
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+// One CRT half of Decrypt: x = c^(p-1) mod p^2.  in0 = low half of c, in1 = high half
+// (c = lo + hi*R with R = 2^(32*S) of the p^2 shape).
+int build_decrypt_half(pgpu_ctx* ctx, Program& P, const BigU& pm1) {
+    program_free(P);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;           // lo*R
+    P.emit(OP_STT, 0); P.use_slot(0);
+    P.emit(OP_LDI, 1);
+    P.emit(OP_MULC, K_R3); P.n_mul++;           // hi*R*R
+    P.emit(OP_ADDT, 0);                         // (c mod p^2) in Montgomery form
+    emit_pow_shared(P, pm1, 0);
+    P.emit(OP_MULC, K_ONE); P.n_mul++;
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+// PartialDecrypt (thresholdkey.go:192-201): c^(2*delta*share) mod n^2
+int build_pdec(pgpu_ctx* ctx) {
+    Program& P = ctx->prog_pdec;
+    program_free(P);
+    const BigU e = ctx->tk_share * (BigU(2) * ctx->tk_delta);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;
+    emit_pow_shared(P, e, 0);
+    P.emit(OP_MULC, K_ONE); P.n_mul++;
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+int setup_crt(pgpu_ctx* ctx) {
+    const BigU &p = ctx->p, &q = ctx->q;
+    int rc;
+    modctx_free(ctx->m_p2); modctx_free(ctx->m_q2);
+    if ((rc = modctx_init(ctx, ctx->m_p2, p * p))) return rc;
+    if ((rc = modctx_init(ctx, ctx->m_q2, q * q))) return rc;
+    if (ctx->m_p2.sh.S != ctx->m_q2.sh.S) return fail(ctx, PGPU_ERR_UNSUPPORTED, "p and q of different width");
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec_p, p - BigU(1)))) return rc;
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec_q, q - BigU(1)))) return rc;
+    const int h = ctx->m_p2.sh.S / 2;
+    if (h > CRT_MAXH || p.v.size() > (size_t)h || q.v.size() > (size_t)h) return fail(ctx, PGPU_ERR_UNSUPPORTED, "prime factors too wide for the CRT recombination");
+    ctx->crt_h = h;
+    const BigU Rh = BigU::pow2(32 * (size_t)h);
+    BigU pinv, qinv, qinv_p, hp, hq, t;
+    if (!BigU::modinv(p, Rh, pinv) || !BigU::modinv(q, Rh, qinv)) return fail(ctx, PGPU_ERR_ARG, "p, q must be odd");
+    if (!BigU::modinv(q % p, p, qinv_p)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
+    // h_p = L_p(g^(p-1) mod p^2)^-1 mod p with g = n+1: g^(p-1) = 1 + (p-1)*n mod p^2
+    const BigU p2 = p * p, q2 = q * q;
+    BigU gp = (BigU(1) + (p - BigU(1)) * ctx->n) % p2, gq = (BigU(1) + (q - BigU(1)) * ctx->n) % q2;
+    BigU lp = ((gp - BigU(1)) / p) % p, lq = ((gq - BigU(1)) / q) % q;
+    if (!BigU::modinv(lp, p, hp) || !BigU::modinv(lq, q, hq)) return fail(ctx, PGPU_ERR_ARG, "invalid key: L(g^(p-1)) not invertible");
+    std::vector<uint32_t> K;
+    auto push = [&](const BigU& x) { auto l = x.limbs(h); K.insert(K.end(), l.begin(), l.end()); };
+    push(p); push(q); push(pinv); push(qinv);
+    push((hp * Rh) % p); push((hq * Rh) % q); push((qinv_p * Rh) % p);
+    if (ctx->d_crt) cudaFree(ctx->d_crt);
+    CU(ctx, cudaMalloc(&ctx->d_crt, K.size() * 4));
+    if ((rc = upload(ctx, ctx->d_crt, K))) return rc;
+    ctx->crt_np0_p = mont_np0(p.v[0]); ctx->crt_np0_q = mont_np0(q.v[0]);
+    ctx->has_secret = true;
+    return PGPU_OK;
+}
+
+// ------------------------------------------------------- device-side ops
+int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    const ModCtx& M = ctx->m_n2;
+    IoDesc ins[2] = {{r, (uint32_t)ctx->wn, (uint32_t)ctx->wn}, {m, (uint32_t)ctx->wn, (uint32_t)ctx->wn}};
+    return run_vm(ctx, M, ctx->prog_enc, count, ins, 2, c, M.sh.S, M.sh.S);
+}
+
+int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "Decrypt: no secret key loaded");
+    const ModCtx &P2 = ctx->m_p2, &Q2 = ctx->m_q2;
+    const uint32_t S2 = ctx->m_n2.sh.S, Sp = P2.sh.S;
+    // c (S2 limbs) = lo (Sp limbs) + hi * 2^(32*Sp); S2 <= 2*Sp
+    const uint32_t hi_limbs = S2 > Sp ? S2 - Sp : 0;
+    void *xp, *xq; int rc;
+    if ((rc = stage(ctx, 4, count * Sp * 4, &xp))) return rc;
+    if ((rc = stage(ctx, 5, count * Sp * 4, &xq))) return rc;
+    IoDesc ins[2] = {{c, S2, std::min(S2, Sp)}, {c + Sp, S2, hi_limbs}};
+    if ((rc = run_vm(ctx, P2, ctx->prog_dec_p, count, ins, 2, (uint32_t*)xp, Sp, Sp))) return rc;
+    if ((rc = run_vm(ctx, Q2, ctx->prog_dec_q, count, ins, 2, (uint32_t*)xq, Sp, Sp))) return rc;
+    CrtParams C{};
+    C.n_items = (uint32_t)count; C.h = ctx->crt_h; C.consts = ctx->d_crt;
+    C.np0_p = ctx->crt_np0_p; C.np0_q = ctx->crt_np0_q;
+    C.xp = (const uint32_t*)xp; C.xq = (const uint32_t*)xq; C.x_stride = Sp;
+    C.out = m; C.out_stride = (uint32_t)ctx->wn; C.out_limbs = (uint32_t)ctx->wn;
+    CU(ctx, crt_combine_launch(C, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out) {
+    if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecrypt: no threshold share loaded");
+    const ModCtx& M = ctx->m_n2;
+    IoDesc ins[1] = {{c, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, ctx->prog_pdec, count, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+Program* cached_program(pgpu_ctx* ctx, const std::string& key) {
+    auto it = ctx->prog_cache.find(key);
+    return it == ctx->prog_cache.end() ? nullptr : &it->second;
+}
+
+// out[i] = base[i]^exp[i] mod M, exp records of exp_limbs limbs
+int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out) {
+    const std::string key = "powi:" + std::to_string(M.sh.S) + ":" + std::to_string(exp_limbs);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        emit_pow_items(np, (size_t)exp_limbs * 32, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{base, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S, exp, exp_limbs);
+}
+
+int modexp_shared_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const BigU& e, uint32_t* out) {
+    const std::string key = "pows:" + std::to_string(M.sh.S) + ":" + e.hex();
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        emit_pow_shared(np, e, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        if (ctx->prog_cache.size() > 64) { for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops); ctx->prog_cache.clear(); }
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{base, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+int modmul_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    const std::string key = "mul:" + std::to_string(M.sh.S);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_MULI, 1); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[2] = {{a, (uint32_t)M.sh.S, (uint32_t)M.sh.S}, {b, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, count, ins, 2, out, M.sh.S, M.sh.S);
+}
+
+// out = prod in[i] mod M (Add over a batch)
+int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_t* out) {
+    const int gpb = 128 / M.sh.tpi;
+    const size_t max_blocks = (size_t)ctx->sms * 4;
+    size_t b1 = std::min(max_blocks, (count + gpb - 1) / gpb);
+    if (b1 == 0) b1 = 1;
+    void* part; int rc;
+    if ((rc = stage(ctx, 3, (b1 + 1) * M.sh.S * 4, &part))) return rc;
+    uint32_t* partial = (uint32_t*)part;
+    auto rounds = [&](size_t n, size_t blocks) { size_t G = blocks * gpb; return n == 0 ? (size_t)1 : (n + G - 1) / G; };
+    // stage 1: b1 blocks -> b1 partials, each carrying R^-(gpb*rounds1 - 1)
+    ProdParams P1{in, (uint32_t)count, M.d_mod, M.np0, partial};
+    CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P1, (int)b1, ctx->stream));
+    ctx->launches++;
+    uint64_t T = (uint64_t)b1 * (gpb * rounds(count, b1) - 1);
+    uint32_t* last = partial;
+    if (b1 > 1) {
+        uint32_t* fin = partial + b1 * M.sh.S;
+        ProdParams P2{partial, (uint32_t)b1, M.d_mod, M.np0, fin};
+        CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P2, 1, ctx->stream));
+        ctx->launches++;
+        T += gpb * rounds(b1, 1) - 1;
+        last = fin;
+    }
+    // final correction: times R^(T+1), one more Montgomery multiply
+    const BigU fix = BigU::modexp(M.R1, BigU(T + 1), M.N);
+    if ((rc = set_kconst(ctx, M, K_FIX, fix))) return rc;
+    const std::string key = "fix:" + std::to_string(M.sh.S);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_FIX); np.n_mul++;
+        np.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{last, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, 1, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+// -------------------------------------------------- host-buffer wrappers
+struct HostIo {
+    pgpu_ctx* ctx;
+    int rc = PGPU_OK;
+    explicit HostIo(pgpu_ctx* c) : ctx(c) {}
+    uint32_t* in(int slot, const void* host, size_t bytes) {
+        void* d = nullptr;
+        if (rc) return nullptr;
+        if ((rc = stage(ctx, slot, bytes, &d))) return nullptr;
+        cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, PGPU_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); return nullptr; }
+        return (uint32_t*)d;
+    }
+    uint32_t* out(int slot, size_t bytes) {
+        void* d = nullptr;
+        if (rc) return nullptr;
+        if ((rc = stage(ctx, slot, bytes, &d))) return nullptr;
+        return (uint32_t*)d;
+    }
+    int finish(void* host, const uint32_t* dev, size_t bytes) {
+        if (rc) return rc;
+        cudaError_t e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+        return PGPU_OK;
+    }
+};
+
+#define REQUIRE(ctx, cond, msg) do { if (!(cond)) return fail(ctx, PGPU_ERR_ARG, msg); } while (0)
+#define GUARD_BEGIN try {
+#define GUARD_END(ctx) } catch (const std::exception& ex) { return fail(ctx, PGPU_ERR_ARG, ex.what()); }
+
+int set_device(pgpu_ctx* ctx) { CU(ctx, cudaSetDevice(ctx->device)); return PGPU_OK; }
+
+}  // namespace
+
+// =========================================================== extern "C" API
+#pragma GCC visibility push(default)
+extern "C" {
+
+int pgpu_version(void) { return 1; }
+
+int pgpu_device_count(int* count) {
+    if (!count) return fail(nullptr, PGPU_ERR_ARG, "null pointer");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return fail(nullptr, PGPU_ERR_CUDA, cudaGetErrorString(e)); }
+    return PGPU_OK;
+}
+
+const char* pgpu_last_error(const pgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_len) {
+    GUARD_BEGIN
+    REQUIRE(nullptr, out && n_be && n_len > 0, "pgpu_ctx_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PGPU_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0"));
+    REQUIRE(nullptr, device >= 0 && device < ndev, "pgpu_ctx_create: bad device index");
+    pgpu_ctx* ctx = new pgpu_ctx();
+    ctx->device = device;
+    int rc = PGPU_OK;
+    auto bail = [&](int code) { std::string m = ctx->err; pgpu_ctx_destroy(ctx); g_err = m; return code; };
+    if ((rc = set_device(ctx))) return bail(rc);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(ctx, PGPU_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    ctx->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ctx, PGPU_ERR_CUDA, "cudaStreamCreate failed"));
+    ctx->stream = ctx->own_stream;
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    ctx->n = BigU::from_be(n_be, n_len);
+    if (!ctx->n.is_odd() || ctx->n.bitlen() < 4) return bail(fail(ctx, PGPU_ERR_ARG, "n must be an odd integer >= 9"));
+    ctx->n2 = ctx->n * ctx->n;
+    ctx->n3 = ctx->n2 * ctx->n;
+    if ((rc = modctx_init(ctx, ctx->m_n2, ctx->n2))) return bail(rc);
+    ctx->wn = ctx->m_n2.sh.S / 2;
+    if (ctx->n.v.size() > ctx->wn) return bail(fail(ctx, PGPU_ERR_UNSUPPORTED, "n does not fit half an n^2 record"));
+    if ((rc = modctx_init(ctx, ctx->m_n, ctx->n))) return bail(rc);
+    {   // level 2 is optional: n^3 may exceed the built shapes
+        Shape s3;
+        if (pick_shape(ctx->n3.v.size(), s3)) { if ((rc = modctx_init(ctx, ctx->m_n3, ctx->n3))) return bail(rc); }
+    }
+    // n * R^2 mod n^2 for the g = n+1 shortcut
+    if ((rc = set_kconst(ctx, ctx->m_n2, K_NR2, (ctx->n * ctx->m_n2.R2) % ctx->n2))) return bail(rc);
+    if ((rc = build_encrypt(ctx))) return bail(rc);
+    *out = ctx;
+    return PGPU_OK;
+    GUARD_END(nullptr)
+}
+
+int pgpu_ctx_destroy(pgpu_ctx* ctx) {
+    if (!ctx) return PGPU_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    modctx_free(ctx->m_n); modctx_free(ctx->m_n2); modctx_free(ctx->m_n3); modctx_free(ctx->m_p2); modctx_free(ctx->m_q2);
+    program_free(ctx->prog_enc); program_free(ctx->prog_dec_p); program_free(ctx->prog_dec_q); program_free(ctx->prog_pdec);
+    for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
+    if (ctx->d_crt) cudaFree(ctx->d_crt);
+    if (ctx->d_table) cudaFree(ctx->d_table);
+    for (void* p : ctx->d_stage) if (p) cudaFree(p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_widths(const pgpu_ctx* ctx, size_t* w_n, size_t* w_n2, size_t* w_n3) {
+    if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
+    if (w_n) *w_n = ctx->wn * 4;
+    if (w_n2) *w_n2 = (size_t)ctx->m_n2.sh.S * 4;
+    if (w_n3) *w_n3 = ctx->m_n3.ready ? (size_t)ctx->m_n3.sh.S * 4 : 0;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_set_stream(pgpu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_set_secret_pq(pgpu_ctx* ctx, const uint8_t* p_be, size_t p_len, const uint8_t* q_be, size_t q_len) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && p_be && q_be, "pgpu_ctx_set_secret_pq: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    ctx->p = BigU::from_be(p_be, p_len); ctx->q = BigU::from_be(q_be, q_len);
+    REQUIRE(ctx, ctx->p * ctx->q == ctx->n, "p*q != n");
+    REQUIRE(ctx, ctx->p != ctx->q, "p == q");
+    return setup_crt(ctx);
+    GUARD_END(ctx)
+}
+
+int pgpu_ctx_set_secret_lambda(pgpu_ctx* ctx, const uint8_t* lambda_be, size_t lambda_len) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && lambda_be, "pgpu_ctx_set_secret_lambda: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    // lambda = (p-1)(q-1) = n - (p+q) + 1  =>  s = p+q = n - lambda + 1, (p-q)^2 = s^2 - 4n
+    const BigU lambda = BigU::from_be(lambda_be, lambda_len);
+    REQUIRE(ctx, lambda < ctx->n, "lambda >= n");
+    const BigU s = ctx->n - lambda + BigU(1);
+    const BigU s2 = s * s, n4 = ctx->n * BigU(4);
+    REQUIRE(ctx, s2 >= n4, "lambda is not (p-1)(q-1) for this n");
+    const BigU d = BigU::isqrt(s2 - n4);
+    REQUIRE(ctx, d * d == s2 - n4, "lambda is not (p-1)(q-1) for this n");
+    ctx->p = (s - d).shr(1); ctx->q = (s + d).shr(1);
+    REQUIRE(ctx, ctx->p * ctx->q == ctx->n, "could not recover p, q from lambda");
+    REQUIRE(ctx, ctx->p != ctx->q, "p == q");
+    return setup_crt(ctx);
+    GUARD_END(ctx)
+}
+
+int pgpu_ctx_set_threshold(pgpu_ctx* ctx, int total_servers, int threshold, int id,
+                           const uint8_t* share_be, size_t share_len, const uint8_t* v_be, size_t v_len,
+                           const void* vkeys_n2w) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx != nullptr, "null context");
+    REQUIRE(ctx, total_servers >= 1 && total_servers <= 1000, "bad TotalNumberOfDecryptionServers");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    ctx->tk_l = total_servers; ctx->tk_w = threshold; ctx->tk_id = id;
+    ctx->tk_delta = BigU::factorial((unsigned)total_servers);
+    ctx->tk_v = v_be ? BigU::from_be(v_be, v_len) : BigU();
+    ctx->tk_vi.clear();
+    if (vkeys_n2w) {
+        const uint32_t* p = (const uint32_t*)vkeys_n2w;
+        for (int i = 0; i < total_servers; ++i) ctx->tk_vi.push_back(BigU::from_limbs(p + (size_t)i * ctx->m_n2.sh.S, ctx->m_n2.sh.S));
+    }
+    ctx->has_threshold = true;
+    ctx->has_share = false;
+    if (share_be) {
+        ctx->tk_share = BigU::from_be(share_be, share_len);
+        if ((rc = build_pdec(ctx))) return rc;
+        ctx->has_share = true;
+    }
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+// ---- device-pointer entry points
+int pgpu_encrypt_with_r_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return encrypt_dev(ctx, count, (const uint32_t*)m, (const uint32_t*)r, (uint32_t*)c);
+    GUARD_END(ctx)
+}
+
+int pgpu_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* m) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && c)), "pgpu_decrypt: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return decrypt_dev(ctx, count, (const uint32_t*)c, (uint32_t*)m);
+    GUARD_END(ctx)
+}
+
+int pgpu_partial_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (out && c)), "pgpu_partial_decrypt: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return pdec_dev(ctx, count, (const uint32_t*)c, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+int pgpu_const_mult_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && k && out)), "pgpu_const_mult: null argument");
+    REQUIRE(ctx, k_bytes > 0 && k_bytes % 4 == 0, "pgpu_const_mult: k_bytes must be a positive multiple of 4");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return modexp_items_dev(ctx, ctx->m_n2, count, (const uint32_t*)c, (const uint32_t*)k, (uint32_t)(k_bytes / 4), (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+int pgpu_add_reduce_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out && (count == 0 || c), "pgpu_add_reduce: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return prod_dev(ctx, ctx->m_n2, count, (const uint32_t*)c, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out && (count == 0 || (c && k)), "pgpu_dot_u64: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    void* tmp;
+    if ((rc = stage(ctx, 2, std::max<size_t>(count, 1) * ctx->m_n2.sh.S * 4, &tmp))) return rc;
+    if ((rc = modexp_items_dev(ctx, ctx->m_n2, count, (const uint32_t*)c, (const uint32_t*)k, 2, (uint32_t*)tmp))) return rc;
+    return prod_dev(ctx, ctx->m_n2, count, (const uint32_t*)tmp, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+// ---- host-buffer entry points
+int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dm = io.in(0, m, count * wn);
+    uint32_t* dr = io.in(1, r, count * wn);
+    uint32_t* dc = io.out(2, count * w2);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = encrypt_dev(ctx, count, dm, dr, dc))) return rc; }
+    return io.finish(c, dc, count * w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* m) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && c)), "pgpu_decrypt: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dc = io.in(0, c, count * w2);
+    uint32_t* dm = io.out(1, count * wn);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = decrypt_dev(ctx, count, dc, dm))) return rc; }
+    return io.finish(m, dm, count * wn);
+    GUARD_END(ctx)
+}
+
+int pgpu_partial_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (out && c)), "pgpu_partial_decrypt: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dc = io.in(0, c, count * w2);
+    uint32_t* dout = io.out(1, count * w2);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = pdec_dev(ctx, count, dc, dout))) return rc; }
+    return io.finish(out, dout, count * w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_modexp(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const void* exp, size_t exp_bytes, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (base && exp && out)), "pgpu_modexp: null argument");
+    REQUIRE(ctx, exp_bytes > 0 && exp_bytes % 4 == 0, "pgpu_modexp: exp_bytes must be a positive multiple of 4");
+    ModCtx* M = select_mod(ctx, modsel);
+    if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modexp: modulus not available for this key");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w = (size_t)M->sh.S * 4;
+    uint32_t* db = io.in(0, base, count * w);
+    uint32_t* de = io.in(1, exp, count * exp_bytes);
+    uint32_t* dout = io.out(2, count * w);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = modexp_items_dev(ctx, *M, count, db, de, (uint32_t)(exp_bytes / 4), dout))) return rc; }
+    return io.finish(out, dout, count * w);
+    GUARD_END(ctx)
+}
+
+int pgpu_const_mult(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out) {
+    return pgpu_modexp(ctx, PGPU_MOD_N2, count, c, k, k_bytes, out);
+}
+
+int pgpu_modexp_shared(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const uint8_t* exp_be, size_t exp_len, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (base && out)) && (exp_be || exp_len == 0), "pgpu_modexp_shared: null argument");
+    ModCtx* M = select_mod(ctx, modsel);
+    if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modexp_shared: modulus not available for this key");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    const BigU e = BigU::from_be(exp_be, exp_len);
+    HostIo io(ctx);
+    const size_t w = (size_t)M->sh.S * 4;
+    uint32_t* db = io.in(0, base, count * w);
+    uint32_t* dout = io.out(2, count * w);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = modexp_shared_dev(ctx, *M, count, db, e, dout))) return rc; }
+    return io.finish(out, dout, count * w);
+    GUARD_END(ctx)
+}
+
+int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const void* b, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (a && b && out)), "pgpu_modmul: null argument");
+    ModCtx* M = select_mod(ctx, modsel);
+    if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modmul: modulus not available for this key");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w = (size_t)M->sh.S * 4;
+    uint32_t* da = io.in(0, a, count * w);
+    uint32_t* db = io.in(1, b, count * w);
+    uint32_t* dout = io.out(2, count * w);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = modmul_dev(ctx, *M, count, da, db, dout))) return rc; }
+    return io.finish(out, dout, count * w);
+    GUARD_END(ctx)
+}
+
+int pgpu_add_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out) {
+    return pgpu_modmul(ctx, PGPU_MOD_N2, count, a, b, out);
+}
+
+int pgpu_add_reduce(pgpu_ctx* ctx, size_t count, const void* c, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out && (count == 0 || c), "pgpu_add_reduce: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dc = io.in(0, c ? c : out, std::max<size_t>(count, 1) * w2);
+    uint32_t* dout = io.out(1, w2);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = prod_dev(ctx, ctx->m_n2, count, dc, dout))) return rc; }
+    return io.finish(out, dout, w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_dot_u64(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out && (count == 0 || (c && k)), "pgpu_dot_u64: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dc = io.in(0, c ? c : out, std::max<size_t>(count, 1) * w2);
+    uint32_t* dk = io.in(1, k ? (const void*)k : (const void*)out, std::max<size_t>(count, 1) * 8);
+    uint32_t* dout = io.out(5, w2);
+    if (io.rc) return io.rc;
+    if ((rc = pgpu_dot_u64_dev(ctx, count, dc, (const uint64_t*)dk, dout))) return rc;
+    return io.finish(out, dout, w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return fail(nullptr, PGPU_ERR_ARG, "null argument");
+    *launches = ctx->launches;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_program_cost(const pgpu_ctx* ctx, int what, uint32_t* limbs, uint32_t* n_sqr, uint32_t* n_mul) {
+    if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
+    uint32_t S = 0, sq = 0, mu = 0;
+    switch (what) {
+        case 0: S = ctx->m_n2.sh.S; sq = ctx->prog_enc.n_sqr; mu = ctx->prog_enc.n_mul; break;
+        case 1:
+            if (!ctx->has_secret) return fail(nullptr, PGPU_ERR_STATE, "no secret key");
+            S = ctx->m_p2.sh.S; sq = ctx->prog_dec_p.n_sqr + ctx->prog_dec_q.n_sqr; mu = ctx->prog_dec_p.n_mul + ctx->prog_dec_q.n_mul; break;
+        case 2:
+            if (!ctx->has_share) return fail(nullptr, PGPU_ERR_STATE, "no share");
+            S = ctx->m_n2.sh.S; sq = ctx->prog_pdec.n_sqr; mu = ctx->prog_pdec.n_mul; break;
+        default: return fail(nullptr, PGPU_ERR_ARG, "bad selector");
+    }
+    if (limbs) *limbs = S;
+    if (n_sqr) *n_sqr = sq;
+    if (n_mul) *n_mul = mu;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_enable_timing(pgpu_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
+    ctx->timing = on != 0; ctx->ev_valid = false;
+    return PGPU_OK;
+}
+
+int pgpu_ctx_last_kernel_ms(pgpu_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(nullptr, PGPU_ERR_ARG, "null argument");
+    if (!ctx->ev_valid) return fail(ctx, PGPU_ERR_STATE, "no timed call recorded");
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return PGPU_OK;
+}
+
+int pgpu_selftest_bn(int op, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len,
+                     const uint8_t* m, size_t m_len, uint8_t* out, size_t* out_len) {
+    GUARD_BEGIN
+    REQUIRE(nullptr, out && out_len, "null argument");
+    const BigU A = BigU::from_be(a, a_len), B = BigU::from_be(b, b_len), M = BigU::from_be(m, m_len);
+    BigU r;
+    switch (op) {
+        case 0: r = A * B; break;
+        case 1: r = A / B; break;
+        case 2: r = A % B; break;
+        case 3: if (!BigU::modinv(A, M, r)) return fail(nullptr, PGPU_ERR_NOT_INVERTIBLE, "not invertible"); break;
+        case 4: r = BigU::modexp(A, B, M); break;
+        case 5: r = BigU::isqrt(A); break;
+        default: return fail(nullptr, PGPU_ERR_ARG, "bad op");
+    }
+    const size_t nbytes = (r.bitlen() + 7) / 8;
+    if (nbytes > *out_len) return fail(nullptr, PGPU_ERR_ARG, "output buffer too small");
+    for (size_t i = 0; i < nbytes; ++i) out[nbytes - 1 - i] = (uint8_t)(r.v[i / 4] >> (8 * (i % 4)));
+    *out_len = nbytes;
+    return PGPU_OK;
+    GUARD_END(nullptr)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

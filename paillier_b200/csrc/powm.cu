@@ -1,0 +1,183 @@
+// powm_vm: the batched modular-exponentiation engine (see vm.h, mont.cuh).
+//
+// Persistent grid: gridDim.x * blockDim.x / TPI groups are resident; group g
+// handles items g, g + n_groups, ...
+// The group's window table lives in a private slot of a global scratch buffer
+// ([entry][group][S] so that neighbouring groups coalesce); at 16 entries x
+// 512 B it stays in the 126 MB L2 for every resident group.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "mont.cuh"
+#include "vm.h"
+#include "launch.h"
+
+namespace pgpu {
+
+template <int L>
+__device__ __forceinline__ void load_vec(uint32_t (&x)[L], const uint32_t* __restrict__ p) {
+    if constexpr (L % 4 == 0) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int k = 0; k < L / 4; ++k) {
+            uint4 v = q[k];
+            x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+        }
+    } else {
+        const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+        for (int k = 0; k < L / 2; ++k) {
+            uint2 v = q[k];
+            x[2 * k] = v.x; x[2 * k + 1] = v.y;
+        }
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void store_vec(uint32_t* __restrict__ p, const uint32_t (&x)[L]) {
+    if constexpr (L % 4 == 0) {
+        uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+        for (int k = 0; k < L / 4; ++k) q[k] = make_uint4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    } else {
+        uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+        for (int k = 0; k < L / 2; ++k) q[k] = make_uint2(x[2 * k], x[2 * k + 1]);
+    }
+}
+
+// bits [pos, pos+w) of a little-endian limb array
+__device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uint32_t nlimbs, uint32_t pos, uint32_t w) {
+    const uint32_t limb = pos >> 5, sh = pos & 31;
+    uint64_t v = e[limb];
+    if (sh + w > 32 && limb + 1 < nlimbs) v |= (uint64_t)e[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+}
+
+template <int TPI, int L>
+__global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
+    constexpr int S = TPI * L;
+    Mont<TPI, L> M;
+    const uint32_t n_groups = P.n_groups;
+    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
+    const uint32_t n_inst = P.n_items;
+    const uint32_t rounds = (n_inst + n_groups - 1) / n_groups;
+    const int lane_t = (threadIdx.x & 31) & (TPI - 1);
+    uint32_t* const tbl = P.table + (size_t)group * S + lane_t * L;
+    const size_t tbl_entry_stride = (size_t)n_groups * S;
+    M.init(P.mod, P.np0);
+    const uint32_t* const kc = P.kconst + lane_t * L;
+
+    for (uint32_t rd = 0; rd < rounds; ++rd) {
+        uint32_t item = rd * n_groups + group;
+        const bool active = item < n_inst;      // whole warps stay in lock-step; idle groups redo item 0
+        if (!active) item = 0;
+
+        uint32_t x[L], y[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) x[k] = 0;
+
+        for (const uint32_t* pc = P.prog;; ++pc) {
+            const uint32_t op = __ldg(pc);
+            const uint32_t code = op >> 28, arg = op & 0x0fffffffu;
+            if (code == OP_END) break;
+            uint32_t nsq = 0, nmul = 0;
+            switch (code) {
+                case OP_LDI: {
+                    const uint32_t* p = P.in[arg] + (size_t)item * P.in_stride[arg];
+                    const uint32_t lim = P.in_limbs[arg];
+#pragma unroll
+                    for (int k = 0; k < L; ++k) {
+                        const uint32_t idx = lane_t * L + k;
+                        x[k] = idx < lim ? __ldg(p + idx) : 0u;
+                    }
+                } break;
+                case OP_LDC: load_vec<L>(x, kc + (size_t)arg * S); break;
+                case OP_LDT: load_vec<L>(x, tbl + arg * tbl_entry_stride); break;
+                case OP_STT: store_vec<L>(tbl + arg * tbl_entry_stride, x); break;
+                case OP_STO: {
+                    if (active) {
+                        uint32_t* p = P.out[arg] + (size_t)item * P.out_stride[arg];
+                        const uint32_t lim = P.out_limbs[arg];
+#pragma unroll
+                        for (int k = 0; k < L; ++k) {
+                            const uint32_t idx = lane_t * L + k;
+                            if (idx < lim) p[idx] = x[k];
+                        }
+                    }
+                } break;
+                case OP_SQR: nsq = arg; break;
+                case OP_MULT: load_vec<L>(y, tbl + arg * tbl_entry_stride); nmul = 1; break;
+                case OP_MULC: load_vec<L>(y, kc + (size_t)arg * S); nmul = 1; break;
+                case OP_MULI: {
+                    const uint32_t* p = P.in[arg] + (size_t)item * P.in_stride[arg];
+                    const uint32_t lim = P.in_limbs[arg];
+#pragma unroll
+                    for (int k = 0; k < L; ++k) {
+                        const uint32_t idx = lane_t * L + k;
+                        y[k] = idx < lim ? __ldg(p + idx) : 0u;
+                    }
+                    nmul = 1;
+                } break;
+                case OP_ADDT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.add(x, x, y); break;
+                case OP_ADDC: load_vec<L>(y, kc + (size_t)arg * S); M.add(x, x, y); break;
+                case OP_WIN: {
+                    const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, tbase = arg >> 24;
+                    const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_stride, pos, w);
+                    load_vec<L>(y, tbl + (tbase + idx) * tbl_entry_stride);
+                    nsq = w; nmul = 1;
+                } break;
+                case OP_SQMT: {
+                    const uint32_t idx = arg >> 12;
+                    load_vec<L>(y, tbl + idx * tbl_entry_stride);
+                    nsq = arg & 0xfffu; nmul = 1;
+                } break;
+                default: break;
+            }
+            // the single Montgomery multiplier of the instruction stream
+            for (uint32_t i = nsq + nmul; i > 0; --i) {
+                const bool sq = i > nmul;
+                uint32_t b[L];
+#pragma unroll
+                for (int k = 0; k < L; ++k) b[k] = sq ? x[k] : y[k];
+                M.mul(x, x, b);
+            }
+        }
+    }
+}
+
+template <int TPI, int L>
+static cudaError_t launch_t(const VmParams& P, int blocks, cudaStream_t stream) {
+    powm_vm<TPI, L><<<blocks, VM_BLOCK_THREADS, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <int TPI, int L>
+static int occupancy_t() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, powm_vm<TPI, L>, VM_BLOCK_THREADS, 0);
+    return nb;
+}
+
+#define PGPU_FOR_EACH_SHAPE(X) \
+    X(2, 16) X(4, 8)           \
+    X(4, 16) X(8, 8)           \
+    X(8, 12) X(4, 24)          \
+    X(8, 16) X(16, 8) X(4, 32) X(32, 4) \
+    X(8, 24) X(16, 12) X(32, 6)
+
+cudaError_t vm_launch(int tpi, int limbs, const VmParams& P, int blocks, cudaStream_t stream) {
+#define X(T, LL) if (tpi == T && limbs == LL) return launch_t<T, LL>(P, blocks, stream);
+    PGPU_FOR_EACH_SHAPE(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+int vm_occupancy(int tpi, int limbs) {
+#define X(T, LL) if (tpi == T && limbs == LL) return occupancy_t<T, LL>();
+    PGPU_FOR_EACH_SHAPE(X)
+#undef X
+    return 0;
+}
+
+}  // namespace pgpu

@@ -1,0 +1,86 @@
+"""CPU-only checks: the C-ABI library loads, exports every symbol include/pgpu.h declares,
+fails loudly without a GPU, and its host-side big-integer code (key setup) matches Python."""
+import ctypes as C
+import os
+import random
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from paillier_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_are_exported_and_bound():
+    L = _lib()
+    header = open(os.path.join(ROOT, "include", "pgpu.h")).read()
+    declared = set(re.findall(r"\b(pgpu_[a-z0-9_]+)\s*\(", header))
+    declared.discard("pgpu_ctx")
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L.lib, name), f"{name} declared in pgpu.h but not exported"
+    assert declared == set(L.SIGNATURES), (declared ^ set(L.SIGNATURES))
+    assert L.lib.pgpu_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    header = open(os.path.join(ROOT, "include", "pgpu.h")).read()
+    assert "torch" not in header.lower() and "at::" not in header
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib()
+    ctx = C.c_void_p()
+    n = (101 * 103).to_bytes(2, "big")
+    rc = L.lib.pgpu_ctx_create(C.byref(ctx), 0, n, len(n))
+    assert rc == L.PGPU_ERR_CUDA
+    assert b"CUDA" in L.lib.pgpu_last_error(None) or b"device" in L.lib.pgpu_last_error(None)
+    from paillier_b200.api import PublicKey
+    with pytest.raises(L.PgpuError):
+        PublicKey(101 * 103)
+
+
+def _bn(op, a, b=0, m=0):
+    L = _lib()
+    be = lambda x: x.to_bytes((x.bit_length() + 7) // 8, "big")
+    out = C.create_string_buffer(4096)
+    n = C.c_size_t(4096)
+    ab, bb, mb = be(a), be(b), be(m)
+    rc = L.lib.pgpu_selftest_bn(op, ab, len(ab), bb, len(bb), mb, len(mb), out, C.byref(n))
+    if rc != 0:
+        return None
+    return int.from_bytes(out.raw[:n.value], "big")
+
+
+def test_host_bignum_against_python():
+    rnd = random.Random(20260101)
+    for it in range(300):
+        abits = rnd.choice([1, 31, 32, 33, 64, 100, 1024, 2048, 4096, 6144])
+        bbits = rnd.choice([1, 17, 32, 33, 63, 64, 65, 512, 1024, 2048])
+        a = rnd.getrandbits(abits) | (1 << (abits - 1))
+        b = rnd.getrandbits(bbits) | (1 << (bbits - 1))
+        assert _bn(0, a, b) == a * b
+        assert _bn(1, a, b) == a // b
+        assert _bn(2, a, b) == a % b
+        m = rnd.getrandbits(bbits + 7) | 1 | (1 << (bbits + 6))
+        inv = _bn(3, a, 0, m)
+        import math
+        if math.gcd(a, m) == 1:
+            assert inv == pow(a, -1, m)
+        else:
+            assert inv is None
+        if it % 10 == 0:
+            e = rnd.getrandbits(70)
+            assert _bn(4, a, e, m) == pow(a, e, m)
+        assert _bn(5, a) == math.isqrt(a)
+    # Knuth D corner: qhat overestimate / add-back paths
+    for a, b in [((1 << 128) - 1, (1 << 64) + 1), ((1 << 96), (1 << 64) - 1), (0x7fffffff800000010000000000000000, 0x800000008000000200000005),
+                 ((1 << 4096) - 1, (1 << 2048) - 1), (3 * ((1 << 64) - 1) ** 2, (1 << 64) - 1)]:
+        assert _bn(1, a, b) == a // b and _bn(2, a, b) == a % b

@@ -1,0 +1,172 @@
+"""GPU parity: libpaillier_b200.so (through the C ABI) against the oracle on identical inputs.
+Bit-exact: all outputs are canonical residues."""
+import numpy as np
+import pytest
+
+from oracle import gmp_ref as G
+from oracle import paillier_ref as R
+from paillier_b200 import synth
+from paillier_b200.api import (Ciphertext, PublicKey, SecretKey, ThresholdSecretKey, from_records, to_records,
+                               MOD_N2, MOD_N3)
+
+pytestmark = pytest.mark.gpu
+
+
+def _key(name):
+    p, q = synth.load_key(name)
+    return p, q, p * q
+
+
+@pytest.fixture(scope="module")
+def sk2048():
+    p, q, n = _key("paillier_2048")
+    sk = SecretKey(n, p=p, q=q)
+    yield sk, R.keygen_from_primes(p, q)[0]
+    sk.close()
+
+
+# ---- reference KATs through the GPU path -------------------------------------------------
+
+def test_partial_decrypt_kat_on_gpu():
+    # thresholdkey_test.go:58-74 (TestDecrypt): 56^(862*2*10!) mod (101*103)^2 = 40644522
+    tsk = ThresholdSecretKey(101 * 103, 10, 6, VerificationKey=4, VerificationKeys=[], ID=9, Share=862)
+    pd = tsk.PartialDecryptBatch([56])
+    assert pd[0].ID == 9 and pd[0].Decryption == 40644522
+    tsk.close()
+
+
+def test_exp_kats_on_gpu():
+    # thresholdkey_generator_test.go:314-324: 54^(s*10!) mod 101^2 for s = 12, 90, 103
+    pk = PublicKey(101)
+    d = R.factorial(10)
+    assert pk.ExpBatch([54, 54, 54], [12 * d, 90 * d, 103 * d]) == [6162, 304, 2728]
+    # thresholdkey_test.go:32-46 (TestExp), modulus 49 = 7^2
+    pk7 = PublicKey(7)
+    assert pk7.ExpBatch([720 % 49, 720 % 49], [10, 0]) == [43, 1]
+    assert pk7.ExpSharedBatch([720 % 49], 10) == [43]
+    assert pk7.ExpSharedBatch([720 % 49], 0) == [1]
+    pk.close(); pk7.close()
+
+
+# ---- encrypt / decrypt ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["paillier_64", "paillier_1024", "paillier_2048"])
+def test_encrypt_decrypt_parity_python_oracle(name):
+    p, q, n = _key(name)
+    osk, opk = R.keygen_from_primes(p, q)
+    sk = SecretKey(n, Lambda=osk.Lambda)        # p, q recovered from lambda as the Go SecretKey only has Lambda
+    ms = from_records(synth.plaintexts(12, n, sk.w_n), sk.w_n)
+    rs = from_records(synth.randomness(12, n, sk.w_n), sk.w_n)
+    ms[0], ms[1], ms[2], rs[3], rs[4] = 0, n - 1, 1, 1, n - 1
+    cts = sk.EncryptWithRBatch(ms, rs)
+    assert [c.C for c in cts] == [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms, rs)]
+    assert sk.DecryptBatch(cts) == ms == [R.decrypt(osk, R.Ciphertext(c.C)) for c in cts]
+    sk.close()
+
+
+def test_empty_and_single_batches(sk2048):
+    sk, _ = sk2048
+    assert sk.EncryptWithRBatch([], []) == []
+    assert sk.DecryptBatch([]) == []
+    c = sk.EncryptWithRBatch([42], [3])
+    assert sk.DecryptBatch(c) == [42]
+
+
+def test_encrypt_decrypt_2048_large_batch_vs_libgmp(sk2048):
+    # ragged count: more items than resident groups and not a multiple of anything
+    sk, osk = sk2048
+    n, count = sk.N, 20011
+    m = synth.plaintexts(count, n, sk.w_n)
+    r = synth.randomness(count, n, sk.w_n)
+    c = sk.encrypt_with_r_records(m, r)
+    nref = 4096
+    ref = G.encrypt_with_r(n, m[:nref * sk.w_n], r[:nref * sk.w_n], sk.w_n)
+    assert np.array_equal(c[:nref * sk.w_n2], ref)
+    # tail of the batch against libgmp as well (last partially filled round of groups)
+    tail = slice((count - 64) * sk.w_n, count * sk.w_n)
+    ref_tail = G.encrypt_with_r(n, m[tail], r[tail], sk.w_n)
+    assert np.array_equal(c[(count - 64) * sk.w_n2:], ref_tail)
+    # CRT decrypt: round trip over the whole batch + libgmp lambda-decrypt on a subset
+    d = sk.decrypt_records(c)
+    assert np.array_equal(d, m)
+    refd = G.decrypt(n, osk.Lambda, c[:512 * sk.w_n2], sk.w_n)
+    assert np.array_equal(d[:512 * sk.w_n], refd)
+
+
+# ---- homomorphic operations -------------------------------------------------------------------
+
+def test_const_mult_add_dot(sk2048):
+    sk, osk = sk2048
+    n, n2 = sk.N, sk.N ** 2
+    count = 300
+    m = synth.plaintexts(count, n, sk.w_n)
+    r = synth.randomness(count, n, sk.w_n)
+    c = sk.encrypt_with_r_records(m, r)
+    k = synth.scalars_u64(count)
+    k[0], k[1], k[2] = 0, 1, 2 ** 64 - 1
+    out = sk.const_mult_records(c, k.view(np.uint8), 8)
+    ref = G.modexp(n2, c, sk.w_n2, k.view(np.uint8), 8)
+    assert np.array_equal(out, ref)
+    assert from_records(out[:sk.w_n2], sk.w_n2) == [1]          # ConstMult by 0 -> 1 (gmp Exp semantics)
+    # Add over the batch == left fold of the reference
+    s = sk.add_reduce_records(c)
+    assert np.array_equal(s, G.add_reduce(n2, c, sk.w_n2))
+    ms = from_records(m, sk.w_n)
+    assert sk.DecryptBatch([Ciphertext(from_records(s, sk.w_n2)[0])]) == [sum(ms) % n]
+    # pairs
+    pr = sk.add_pairs_records(c, out)
+    assert np.array_equal(pr, G.modmul(n2, c, out, sk.w_n2))
+    # encrypted dot product (BASELINE config 3) == Add(ConstMult(c_i, k_i))
+    dot = sk.dot_u64_records(c, k)
+    assert np.array_equal(dot, G.add_reduce(n2, ref, sk.w_n2))
+    expect = sum(int(ki) * mi for ki, mi in zip(k, ms)) % n
+    assert sk.DecryptBatch([Ciphertext(from_records(dot, sk.w_n2)[0])]) == [expect]
+
+
+@pytest.mark.parametrize("count", [0, 1, 2, 17, 1000, 9473, 40000])
+def test_add_reduce_sizes(sk2048, count):
+    sk, _ = sk2048
+    n2 = sk.N ** 2
+    c = synth.random_records(count, sk.w_n2, 4094, stream=9)
+    got = sk.add_reduce_records(c)
+    assert np.array_equal(got, G.add_reduce(n2, c, sk.w_n2)) if count else from_records(got, sk.w_n2) == [1]
+
+
+def test_generic_modexp_n2_n3(sk2048):
+    sk, _ = sk2048
+    n2, n3 = sk.N ** 2, sk.N ** 3
+    count = 24
+    for modsel, mod, width, bits in ((MOD_N2, n2, sk.w_n2, 4094), (MOD_N3, n3, sk.w_n3, 6140)):
+        base = synth.random_records(count, width, bits, stream=11)
+        for eb in (4, 8, 256, 512):
+            exp = synth.random_records(count, eb, eb * 8, stream=12)
+            got = sk.modexp_records(modsel, base, exp, eb, width)
+            assert np.array_equal(got, G.modexp(mod, base, width, exp, eb)), (modsel, eb)
+        bases = from_records(base, width)
+        e = sk.N
+        assert sk.ExpSharedBatch(bases[:4], e, modsel) == [pow(b, e, mod) for b in bases[:4]]
+        got = sk.modmul_records(modsel, base, base[::-1].copy(), width)
+        assert np.array_equal(got, G.modmul(mod, base, base[::-1].copy(), width))
+
+
+# ---- threshold partial decryption ----------------------------------------------------------------
+
+@pytest.mark.parametrize("name,l,w", [("threshold_512", 5, 3), ("threshold_2048", 8, 5), ("threshold_3072", 8, 5)])
+def test_partial_decrypt_parity(name, l, w):
+    p, q, n = _key(name)
+    import random
+    rnd = random.Random(synth.SEED)
+    nm = n * ((p - 1) // 2) * ((q - 1) // 2)
+    keys = R.threshold_keys_from(p, q, l, w, v_seed=rnd.randrange(2, n * n), coeffs=[rnd.randrange(nm) for _ in range(w - 1)])
+    ok = keys[2]
+    tsk = ThresholdSecretKey(n, l, w, ok.VerificationKey, ok.VerificationKeys, ok.ID, ok.Share)
+    count = 200
+    m = synth.plaintexts(count, n, tsk.w_n)
+    r = synth.randomness(count, n, tsk.w_n)
+    c = tsk.encrypt_with_r_records(m, r)
+    out = tsk.partial_decrypt_records(c)
+    ref = G.partial_decrypt(n, ok.Share, l, c, tsk.w_n2)
+    assert np.array_equal(out, ref)
+    c0 = from_records(c[:tsk.w_n2], tsk.w_n2)[0]
+    assert from_records(out[:tsk.w_n2], tsk.w_n2)[0] == R.partial_decrypt(ok, c0).Decryption
+    tsk.close()
