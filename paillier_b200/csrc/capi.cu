@@ -30,7 +30,7 @@ struct Shape { int S, tpi, L; };
 
 // smallest built shape holding `limbs` limbs; override with PGPU_SHAPE_<S>="tpi,L"
 bool pick_shape(size_t limbs, Shape& out) {
-    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 8, 12}, {128, 8, 16}, {192, 8, 24}};
+    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 8, 12}, {128, 4, 32}, {192, 8, 24}};
     for (const Shape& s : defaults) {
         if ((size_t)s.S >= limbs) {
             out = s;
@@ -595,7 +595,7 @@ int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_le
     ctx->stream = ctx->own_stream;
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     ctx->n = BigU::from_be(n_be, n_len);
-    if (!ctx->n.is_odd() || ctx->n.bitlen() < 4) return bail(fail(ctx, PGPU_ERR_ARG, "n must be an odd integer >= 9"));
+    if (!ctx->n.is_odd() || ctx->n.bitlen() < 2) return bail(fail(ctx, PGPU_ERR_ARG, "n must be an odd integer >= 3"));
     ctx->n2 = ctx->n * ctx->n;
     ctx->n3 = ctx->n2 * ctx->n;
     if ((rc = modctx_init(ctx, ctx->m_n2, ctx->n2))) return bail(rc);

@@ -170,3 +170,22 @@ def test_partial_decrypt_parity(name, l, w):
     c0 = from_records(c[:tsk.w_n2], tsk.w_n2)[0]
     assert from_records(out[:tsk.w_n2], tsk.w_n2)[0] == R.partial_decrypt(ok, c0).Decryption
     tsk.close()
+
+
+def test_threshold_keygen_matches_oracle():
+    # thresholdkey_generator.go:47-55 with injected randomness; verification keys computed on the GPU
+    import random
+    from paillier_b200.keygen import ThresholdKeyGenerator
+    p, q, n = _key("threshold_512")
+    keys = ThresholdKeyGenerator(512, 6, 4, rng=random.Random(99)).with_safe_primes(p, q).GenerateKeys()
+    rnd = random.Random(99)
+    n2, nm = n * n, n * ((p - 1) // 2) * ((q - 1) // 2)
+    while True:
+        r = rnd.randrange(1, n2)
+        if r % p and r % q:
+            break
+    coeffs = [rnd.randrange(nm) for _ in range(3)]
+    okeys = R.threshold_keys_from(p, q, 6, 4, v_seed=r, coeffs=coeffs)
+    for k, ok in zip(keys, okeys):
+        assert (k.ID, k.Share, k.VerificationKey, k.VerificationKeys) == (ok.ID, ok.Share, ok.VerificationKey, ok.VerificationKeys)
+        k.close()
