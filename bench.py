@@ -174,7 +174,9 @@ def main() -> None:
     p, q = synth.load_key("paillier_2048")
     n = p * q
     sk = SecretKey(n, p=p, q=q, device=local)
-    stream = torch.cuda.current_stream(dev)
+    # the engine enqueues on this (non-default) torch stream, so torch.cuda.Event timing sees its kernels
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     check(lib.pgpu_ctx_set_stream(sk._ctx, C.c_void_p(stream.cuda_stream)), sk._ctx)
     count, w_n, w_n2 = args.count, sk.w_n, sk.w_n2
 
