@@ -104,6 +104,27 @@ int pgpu_dot_u64(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, 
  * out[i] = c[i]^(2*delta*share) mod n^2, delta = l!.   c, out: n2-width. */
 int pgpu_partial_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* out);
 
+/* PublicKey.Sub(a[i], b[i]) (operations.go:32-55): out[i] = a[i] * b[i]^-1 mod n^2.
+ * PGPU_ERR_NOT_INVERTIBLE names the first b[i] that is not a unit. */
+int pgpu_sub_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out);
+/* gmp.Int.ModInverse (mpz_invert) against one of the key's moduli */
+int pgpu_modinv(pgpu_ctx* ctx, int modsel, size_t count, const void* a, void* out);
+
+/* ThresholdSecretKey.PartialDecryptionWithZKP (thresholdkey.go:225-255) with the random r in [0, n^2)
+ * supplied by the caller (the reference draws it from crypto/rand at :233).
+ * c, r, dec: n2-width; e: 32-byte records (SetBytes(sha256 digest), little-endian); z: z-width records
+ * (pgpu_ctx_z_width), Z = r + E*delta*share unreduced (:313-317). */
+int pgpu_pdec_zkp_prove(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z);
+int pgpu_ctx_z_width(const pgpu_ctx* ctx, size_t* w_z);
+/* PartialDecryptionZKP.VerifyProof (thresholdkey.go:278-311) for proofs of server `id`
+ * (verification key VerificationKeys[id-1], :305); ok[i] = 1 if the proof verifies. */
+int pgpu_pdec_zkp_verify(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok);
+/* ThresholdPublicKey.CombinePartialDecryptions (thresholdkey.go:149-161) for a batch of ciphertexts:
+ * k shares with server ids[0..k); decs holds k consecutive batches of `count` n2-width partial
+ * decryptions (share j's batch starts at record j*count).  m: n-width plaintexts.
+ * PGPU_ERR_THRESHOLD for "Threshold not meet" / duplicate ids (:77-89). */
+int pgpu_combine(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
+
 /* Generic batched gmp.Int.Exp (mpz_powm) / Mul+Mod against one of the key's
  * moduli; records are the modulus' width.  exp: per-item unsigned records of
  * exp_bytes bytes.  These back ConstMult, the ZKP and DDLEQ entry points. */
@@ -120,6 +141,9 @@ int pgpu_partial_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* o
 int pgpu_const_mult_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out);
 int pgpu_add_reduce_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out);
 int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out);
+
+int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z);
+int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
 
 /* ---- introspection used by bench.py ------------------------------------ */
 /* number of kernels this context has launched so far */

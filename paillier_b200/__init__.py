@@ -5,5 +5,5 @@ host-side mirror of the reference's interface used by the tests and the benchmar
 """
 from .api import (  # noqa: F401
     Ciphertext, PublicKey, SecretKey, ThresholdPublicKey, ThresholdSecretKey,
-    PartialDecryption, from_records, to_records,
+    PartialDecryption, PartialDecryptionZKP, from_records, to_records,
 )

@@ -55,6 +55,14 @@ SIGNATURES = {
     "pgpu_const_mult_dev": (C.c_int, [_p, _sz, _p, _p, _sz, _p]),
     "pgpu_add_reduce_dev": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_dot_u64_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_sub_pairs": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_modinv": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
+    "pgpu_pdec_zkp_prove": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
+    "pgpu_ctx_z_width": (C.c_int, [_p, C.POINTER(_sz)]),
+    "pgpu_pdec_zkp_verify": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
+    "pgpu_combine": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
+    "pgpu_pdec_zkp_prove_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
+    "pgpu_combine_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),

@@ -72,6 +72,16 @@ class PartialDecryption:
     Decryption: int
 
 
+@dataclass
+class PartialDecryptionZKP:
+    """thresholdkey.go:52-58 (Key is the ThresholdPublicKey the verifier already holds)"""
+    ID: int
+    Decryption: int
+    E: int
+    Z: int
+    C: int
+
+
 class PublicKey:
     """paillier.go:46-56 with g = n+1 (paillier.go:147); owns one engine context on `device`."""
 
@@ -200,6 +210,21 @@ class PublicKey:
         out = self.add_pairs_records(to_records([c.C for c in a], self.w_n2), to_records([c.C for c in b], self.w_n2))
         return [Ciphertext(v, ENC_LEVEL_ONE, MIXED) for v in from_records(out, self.w_n2)]
 
+    def SubPairs(self, a: Sequence[Ciphertext], b: Sequence[Ciphertext]) -> List[Ciphertext]:
+        """N x PublicKey.Sub(a_i, b_i) (operations.go:32-55)"""
+        ar, br = to_records([c.C for c in a], self.w_n2), to_records([c.C for c in b], self.w_n2)
+        out = np.empty(len(a) * self.w_n2, dtype=np.uint8)
+        check(lib.pgpu_sub_pairs(self._ctx, len(a), _ptr(ar), _ptr(br), _ptr(out)), self._ctx)
+        return [Ciphertext(v, ENC_LEVEL_ONE, MIXED) for v in from_records(out, self.w_n2)]
+
+    def ModInverseBatch(self, xs: Sequence[int], modsel: int = MOD_N2) -> List[int]:
+        """N x gmp.Int.ModInverse(x, mod); raises PgpuError(PGPU_ERR_NOT_INVERTIBLE) for a non-unit"""
+        width = {MOD_N2: self.w_n2, MOD_N3: self.w_n3}[modsel]
+        xr = to_records(xs, width)
+        out = np.empty(len(xs) * width, dtype=np.uint8)
+        check(lib.pgpu_modinv(self._ctx, modsel, len(xs), _ptr(xr), _ptr(out)), self._ctx)
+        return from_records(out, width)
+
     def DotProduct(self, cts: Sequence[Ciphertext], ks: Sequence[int]) -> Ciphertext:
         """Add(ConstMult(c_i, k_i) ...) with 64-bit scalars (BASELINE config 3)"""
         out = self.dot_u64_records(to_records([c.C for c in cts], self.w_n2), np.array([int(k) for k in ks], dtype=np.uint64))
@@ -280,6 +305,51 @@ class ThresholdPublicKey(PublicKey):
         check(lib.pgpu_ctx_set_threshold(self._ctx, TotalNumberOfDecryptionServers, Threshold, _id,
                                          sb, len(sb) if sb is not None else 0, vb, len(vb),
                                          _ptr(vk) if vk is not None else None), self._ctx)
+        wz = C.c_size_t()
+        check(lib.pgpu_ctx_z_width(self._ctx, C.byref(wz)), self._ctx)
+        self.w_z = wz.value
+
+    def verify_proof_records(self, ID: int, c, dec, e, z) -> np.ndarray:
+        c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)
+        count = c.size // self.w_n2
+        dec, e, z = _as_u8(dec, count * self.w_n2, "dec"), _as_u8(e, count * 32, "e"), _as_u8(z, count * self.w_z, "z")
+        ok = np.zeros(count, dtype=np.uint8)
+        check(lib.pgpu_pdec_zkp_verify(self._ctx, count, ID, _ptr(c), _ptr(dec), _ptr(e), _ptr(z), _ptr(ok)), self._ctx)
+        return ok
+
+    def VerifyProofBatch(self, proofs: Sequence[PartialDecryptionZKP]) -> List[bool]:
+        """N x PartialDecryptionZKP.VerifyProof (thresholdkey.go:278-291); proofs of one server per call"""
+        if not proofs:
+            return []
+        ids = {p.ID for p in proofs}
+        if len(ids) != 1:
+            raise ValueError("VerifyProofBatch: one server id per batch")
+        ok = self.verify_proof_records(proofs[0].ID, to_records([p.C for p in proofs], self.w_n2),
+                                       to_records([p.Decryption for p in proofs], self.w_n2),
+                                       to_records([p.E for p in proofs], 32), to_records([p.Z for p in proofs], self.w_z))
+        return [bool(x) for x in ok]
+
+    def combine_records(self, ids: Sequence[int], decs) -> np.ndarray:
+        """decs: len(ids) consecutive batches of n2-width records (share j's batch first to last)"""
+        decs = np.ascontiguousarray(decs).view(np.uint8).reshape(-1)
+        k = len(ids)
+        count = decs.size // (self.w_n2 * k) if k else 0
+        out = np.empty(count * self.w_n, dtype=np.uint8)
+        idarr = (C.c_int * max(k, 1))(*ids)
+        check(lib.pgpu_combine(self._ctx, count, k, idarr, _ptr(decs) if decs.size else None, _ptr(out) if count else None), self._ctx)
+        return out
+
+    def CombinePartialDecryptionsBatch(self, shares: Sequence[Sequence[PartialDecryption]]) -> List[int]:
+        """N x CombinePartialDecryptions (thresholdkey.go:149-161): shares[j] is server j's batch, all batches in
+        the same ciphertext order.  Raises PgpuError(PGPU_ERR_THRESHOLD) like the reference's errors (:77-89)."""
+        ids = [s[0].ID if len(s) else 0 for s in shares]
+        flat = [pd.Decryption for s in shares for pd in s]
+        return from_records(self.combine_records(ids, to_records(flat, self.w_n2)), self.w_n)
+
+    def CombinePartialDecryptionsZKPBatch(self, shares: Sequence[Sequence[PartialDecryptionZKP]]) -> List[int]:
+        """thresholdkey.go:164-172 for a batch: a server's batch takes part only if all its proofs verify."""
+        good = [s for s in shares if all(self.VerifyProofBatch(s))]
+        return self.CombinePartialDecryptionsBatch([[PartialDecryption(p.ID, p.Decryption) for p in s] for s in good])
 
 
 class ThresholdSecretKey(ThresholdPublicKey):
@@ -298,6 +368,22 @@ class ThresholdSecretKey(ThresholdPublicKey):
         out = np.empty(count * self.w_n2, dtype=np.uint8)
         check(lib.pgpu_partial_decrypt(self._ctx, count, _ptr(c), _ptr(out)), self._ctx)
         return out
+
+    def zkp_prove_records(self, c, r):
+        c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)
+        count = c.size // self.w_n2
+        r = _as_u8(r, count * self.w_n2, "r")
+        dec = np.empty(count * self.w_n2, dtype=np.uint8)
+        e = np.empty(count * 32, dtype=np.uint8)
+        z = np.empty(count * self.w_z, dtype=np.uint8)
+        check(lib.pgpu_pdec_zkp_prove(self._ctx, count, _ptr(c), _ptr(r), _ptr(dec), _ptr(e), _ptr(z)), self._ctx)
+        return dec, e, z
+
+    def PartialDecryptionWithZKPBatch(self, cs: Sequence[int], rs: Sequence[int]) -> List[PartialDecryptionZKP]:
+        """N x PartialDecryptionWithZKP (thresholdkey.go:225-255); rs are the r in [0, n^2) the reference draws at :233"""
+        dec, e, z = self.zkp_prove_records(to_records(cs, self.w_n2), to_records(rs, self.w_n2))
+        return [PartialDecryptionZKP(self.ID, d, ee, zz, c) for d, ee, zz, c in
+                zip(from_records(dec, self.w_n2), from_records(e, 32), from_records(z, self.w_z), cs)]
 
     def PartialDecryptBatch(self, cs: Sequence[int]) -> List[PartialDecryption]:
         """N x ThresholdSecretKey.PartialDecrypt (thresholdkey.go:192-201)"""

@@ -5,7 +5,7 @@
 
 namespace pgpu {
 
-constexpr int CRT_MAXH = 64;   // limbs of p, q supported by the CRT recombination (4096-bit n)
+constexpr int CRT_MAXH = 96;   // limbs of p, q (CRT recombination) and of n (share combining) supported
 
 // consts: 7 records of h limbs: p, q, p^-1 mod 2^(32h), q^-1 mod 2^(32h),
 // h_p*2^(32h) mod p, h_q*2^(32h) mod q, q^-1*2^(32h) mod p
@@ -34,5 +34,62 @@ struct ProdParams {
     uint32_t* partial;       // one record per block
 };
 cudaError_t prod_reduce_launch(int tpi, int limbs, const ProdParams& P, int blocks, cudaStream_t stream);
+
+// m = L(c') * K mod n with K = (4*delta^2)^-1 mod n (thresholdkey.go:143-146, :63-66).
+// consts: 3 records of h limbs: n, n^-1 mod 2^(32h), K*2^(32h) mod n
+struct CombineParams {
+    uint32_t n_items;
+    int h;
+    const uint32_t* consts;
+    uint32_t np0;
+    const uint32_t* cprime;  // records of cp_stride limbs (n^2 width)
+    uint32_t cp_stride;
+    uint32_t* out;           // h limbs per item
+};
+cudaError_t combine_final_launch(const CombineParams& P, cudaStream_t stream);
+
+// ---- bigops.cu ----
+constexpr int BIG_MAXS = 192;
+
+struct InvParams {
+    uint32_t n_items;
+    int limbs;
+    const uint32_t* mod;
+    const uint32_t* in;
+    uint32_t* out;
+    uint32_t* first_bad;     // atomicMin of the first non-invertible item index
+};
+cudaError_t modinv_launch(const InvParams& P, cudaStream_t stream);
+
+struct MulParams {
+    uint32_t n_items;
+    const uint32_t* a; uint32_t a_stride; int na;
+    const uint32_t* b; uint32_t b_stride; int nb;
+    uint32_t* out; uint32_t out_stride; uint32_t out_limbs;
+};
+cudaError_t bigmul_launch(const MulParams& P, cudaStream_t stream);
+
+struct MulAddParams {
+    uint32_t n_items;
+    const uint32_t* r; uint32_t r_stride; uint32_t nr;
+    const uint32_t* e; uint32_t e_stride; int ne;
+    const uint32_t* k; int nk;
+    uint32_t* out; uint32_t out_stride; uint32_t out_limbs;
+};
+cudaError_t muladd_launch(const MulAddParams& P, cudaStream_t stream);
+
+struct ShaParams {
+    uint32_t n_items;
+    int n_seg;
+    const uint32_t* seg[6];
+    uint32_t stride[6];      // limbs between items (0 = same value for every item)
+    int limbs[6];
+    uint32_t* out;           // 8 limbs per item
+};
+cudaError_t sha256_concat_launch(const ShaParams& P, cudaStream_t stream);
+
+cudaError_t equal_launch(const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint8_t* flags, cudaStream_t stream);
+cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream);
+cudaError_t resize_launch(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items, cudaStream_t stream);
 
 }  // namespace pgpu

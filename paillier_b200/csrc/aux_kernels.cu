@@ -125,6 +125,28 @@ cudaError_t crt_combine_launch(const CrtParams& P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// m = L(c') * (4*delta^2)^-1 mod n   (computeDecryption, thresholdkey.go:143-146)
+__global__ void combine_final_kernel(CombineParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_items) return;
+    const int h = P.h;
+    const uint32_t* n = P.consts;
+    const uint32_t* ninv = P.consts + h;
+    const uint32_t* KM = P.consts + 2 * h;
+    uint32_t l[CRT_MAXH], m[CRT_MAXH];
+    st_L(l, P.cprime + (size_t)i * P.cp_stride, ninv, h);
+    st_mont(m, l, KM, n, P.np0, h);
+    uint32_t* out = P.out + (size_t)i * h;
+    for (int j = 0; j < h; ++j) out[j] = m[j];
+}
+
+cudaError_t combine_final_launch(const CombineParams& P, cudaStream_t stream) {
+    if (P.n_items == 0) return cudaSuccess;
+    const int threads = 64;
+    combine_final_kernel<<<(P.n_items + threads - 1) / threads, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // PublicKey.Add over a batch (operations.go:11-29): one running Montgomery
 // product per group, then a shared-memory tree across the block's groups.

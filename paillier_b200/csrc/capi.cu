@@ -428,7 +428,8 @@ Program* cached_program(pgpu_ctx* ctx, const std::string& key) {
 }
 
 // out[i] = base[i]^exp[i] mod M, exp records of exp_limbs limbs
-int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out) {
+int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,
+                     bool broadcast_base = false) {
     const std::string key = "powi:" + std::to_string(M.sh.S) + ":" + std::to_string(exp_limbs);
     Program* P = cached_program(ctx, key);
     if (!P) {
@@ -442,7 +443,7 @@ int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_
         if (rc) return rc;
         P = &(ctx->prog_cache[key] = np);
     }
-    IoDesc ins[1] = {{base, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    IoDesc ins[1] = {{base, broadcast_base ? 0u : (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
     return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S, exp, exp_limbs);
 }
 
@@ -521,6 +522,171 @@ int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_
     }
     IoDesc ins[1] = {{last, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
     return run_vm(ctx, M, *P, 1, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+// stream-ordered temporary device buffer
+struct DevBuf {
+    pgpu_ctx* c; uint32_t* p = nullptr; cudaError_t err = cudaSuccess;
+    DevBuf(pgpu_ctx* ctx, size_t limbs) : c(ctx) { err = cudaMallocAsync((void**)&p, std::max<size_t>(limbs, 1) * 4, ctx->stream); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, c->stream); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+#define DEVBUF(name, ctx, limbs) DevBuf name(ctx, limbs); if (name.err != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(name.err))
+
+// signed big integer for the Lagrange coefficients of share combining
+struct BigS { BigU mag; bool neg = false; };
+
+// Euclidean division by a small signed integer (Go big.Int.Div semantics, pinned by thresholdkey_test.go:168-177)
+BigS euclid_div(const BigS& num, long den) {
+    const BigU d((uint64_t)(den < 0 ? -den : den));
+    BigU q0, r0; BigU::divmod(num.mag, d, q0, r0);
+    BigS q;
+    if (!num.neg || num.mag.is_zero()) { q.mag = q0; q.neg = den < 0 && !q0.is_zero(); return q; }
+    if (r0.is_zero()) { q.mag = q0; q.neg = den > 0 && !q0.is_zero(); return q; }
+    q.mag = q0 + BigU(1); q.neg = den > 0;
+    return q;
+}
+
+// out[i] = in[i]^-1 mod M; *d_first_bad = index of the first non-invertible item or 0xffffffff
+int modinv_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad) {
+    if (M.sh.S > BIG_MAXS) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus too wide for modinv");
+    CU(ctx, cudaMemsetAsync(d_first_bad, 0xff, 4, ctx->stream));
+    InvParams P{(uint32_t)count, M.sh.S, M.d_mod, in, out, d_first_bad};
+    CU(ctx, modinv_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* out) {
+    MulParams P{(uint32_t)count, a, na, (int)na, b, nb, (int)nb, out, na + nb, na + nb};
+    CU(ctx, bigmul_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, const uint32_t* stride, const int* limbs, uint32_t* out) {
+    ShaParams P{}; P.n_items = (uint32_t)count; P.n_seg = n_seg; P.out = out;
+    for (int i = 0; i < n_seg; ++i) { P.seg[i] = seg[i]; P.stride[i] = stride[i]; P.limbs[i] = limbs[i]; }
+    CU(ctx, sha256_concat_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+uint32_t z_limbs(const pgpu_ctx* ctx) { return (uint32_t)ctx->m_n2.sh.S + 16; }   // Z = r + E*delta*share < 2^(32*(S+16))
+
+// ZKP transcript hash shared by prover and verifier: c^4 and c_i^2 enter unreduced (thresholdkey.go:241,248,319-326)
+int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* dec, uint32_t* e_out) {
+    const uint32_t S = ctx->m_n2.sh.S;
+    DEVBUF(c2, ctx, count * 2 * S); DEVBUF(c4, ctx, count * 4 * S); DEVBUF(ci2, ctx, count * 2 * S);
+    int rc;
+    if ((rc = bigmul_dev(ctx, count, c, S, c, S, c2.p))) return rc;
+    if ((rc = bigmul_dev(ctx, count, c2.p, 2 * S, c2.p, 2 * S, c4.p))) return rc;
+    if ((rc = bigmul_dev(ctx, count, dec, S, dec, S, ci2.p))) return rc;
+    const uint32_t* seg[4] = {a, b, c4.p, ci2.p};
+    const uint32_t stride[4] = {S, S, 4 * S, 2 * S};
+    const int limbs[4] = {(int)S, (int)S, (int)(4 * S), (int)(2 * S)};
+    return sha_dev(ctx, count, 4, seg, stride, limbs, e_out);
+}
+
+// PartialDecryptionWithZKP (thresholdkey.go:225-255), r supplied
+int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z) {
+    if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecryptionWithZKP: no threshold share loaded");
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const BigU k = ctx->tk_delta * ctx->tk_share;
+    if (k.v.size() + 8 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "share too large for the Z record");
+    int rc;
+    if ((rc = pdec_dev(ctx, count, c, dec))) return rc;
+    DEVBUF(c4r, ctx, count * S); DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(v, ctx, S);
+    DEVBUF(kd, ctx, k.v.size() + 1);
+    if ((rc = upload(ctx, v.p, ctx->tk_v.limbs(S)))) return rc;
+    if ((rc = upload(ctx, kd.p, k.limbs(k.v.size() + 1)))) return rc;
+    if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), c4r.p))) return rc;           // c^4 mod n^2: (c^4)^r = (c^4 mod n^2)^r
+    if ((rc = modexp_items_dev(ctx, M, count, c4r.p, r, S, a.p))) return rc;             // a = (c^4)^r        :242
+    if ((rc = modexp_items_dev(ctx, M, count, v.p, r, S, b.p, true))) return rc;         // b = V^r            :245
+    if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e))) return rc;                 // E                  :250
+    MulAddParams Q{(uint32_t)count, r, S, S, e, 8, 8, kd.p, (int)k.v.size(), z, z_limbs(ctx), z_limbs(ctx)};
+    CU(ctx, muladd_launch(Q, ctx->stream));                                              // Z = r + E*delta*share :252
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+// VerifyProof (thresholdkey.go:278-311)
+int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok) {
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "VerifyProof: no threshold key loaded");
+    if (id < 1 || (size_t)id > ctx->tk_vi.size()) return fail(ctx, PGPU_ERR_ARG, "VerifyProof: no verification key for this server id");   // VerificationKeys[ID-1] :305
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S, ZL = z_limbs(ctx);
+    int rc;
+    DEVBUF(t0, ctx, count * S); DEVBUF(t1, ctx, count * S); DEVBUF(t2, ctx, count * S);
+    DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(kv, ctx, S); DEVBUF(kvi, ctx, S); DEVBUF(bad, ctx, 1); DEVBUF(e2, ctx, count * 8);
+    if ((rc = upload(ctx, kv.p, ctx->tk_v.limbs(S)))) return rc;
+    if ((rc = upload(ctx, kvi.p, ctx->tk_vi[id - 1].limbs(S)))) return rc;
+    // a = (c^4)^Z * ((c_i^2)^E)^-1 mod n^2        verifyPart1 :293-302
+    if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), t0.p))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, t0.p, z, ZL, t1.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, dec, dec, t0.p))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, t0.p, e, 8, t2.p))) return rc;
+    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, a.p))) return rc;
+    // b = V^Z * (v_i^E)^-1 mod n^2                verifyPart2 :304-311
+    if ((rc = modexp_items_dev(ctx, M, count, kv.p, z, ZL, t1.p, true))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, kvi.p, e, 8, t2.p, true))) return rc;
+    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, b.p))) return rc;
+    if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e2.p))) return rc;
+    CU(ctx, equal_launch(e, e2.p, 8, (uint32_t)count, ok, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+// CombinePartialDecryptions (thresholdkey.go:149-161); decs = k batches of `count` n^2-width records, one per share
+int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out) {
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "CombinePartialDecryptions: no threshold key loaded");
+    if (k < ctx->tk_w) return fail(ctx, PGPU_ERR_THRESHOLD, "Threshold not meet");                               // :78-80
+    for (int i = 0; i < k; ++i) for (int j = i + 1; j < k; ++j)
+        if (ids[i] == ids[j]) return fail(ctx, PGPU_ERR_THRESHOLD, "two shares has been created by the same server");  // :81-87
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const size_t h = ctx->wn;
+    if (h > (size_t)CRT_MAXH) return fail(ctx, PGPU_ERR_UNSUPPORTED, "n too wide for the combine tail");
+    const BigU Rh = BigU::pow2(32 * h);
+    BigU ninv, K;
+    if (!BigU::modinv(ctx->n, Rh, ninv)) return fail(ctx, PGPU_ERR_ARG, "n must be odd");
+    if (!BigU::modinv((BigU(4) * ctx->tk_delta * ctx->tk_delta) % ctx->n, ctx->n, K)) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "4*delta^2 not invertible mod n");
+    std::vector<uint32_t> kc;
+    for (const BigU& x : {ctx->n, ninv, (K * Rh) % ctx->n}) { auto l = x.limbs(h); kc.insert(kc.end(), l.begin(), l.end()); }
+    int rc;
+    DEVBUF(pos, ctx, count * S); DEVBUF(neg, ctx, count * S); DEVBUF(t, ctx, count * S); DEVBUF(bad, ctx, 1); DEVBUF(kd, ctx, kc.size());
+    if ((rc = upload(ctx, kd.p, kc))) return rc;
+    bool have_pos = false, have_neg = false;
+    for (int i = 0; i < k; ++i) {
+        BigS lam; lam.mag = ctx->tk_delta;                                   // computeLambda :99-107
+        for (int j = 0; j < k; ++j) {
+            if (ids[j] == ids[i]) continue;
+            BigS num; num.mag = lam.mag * BigU((uint64_t)(ids[j] < 0 ? -(long)ids[j] : (long)ids[j]));
+            num.neg = (lam.neg != (ids[j] > 0)) && !num.mag.is_zero();       // lambda * (-j)   :92
+            lam = euclid_div(num, (long)ids[i] - (long)ids[j]);              // Div(num, i - j) :93-94
+        }
+        const BigU e2 = lam.mag * BigU(2);                                   // updateCprime: exponent 2*lambda :119-124
+        if ((rc = modexp_shared_dev(ctx, M, count, decs + (size_t)i * count * S, e2, t.p))) return rc;
+        uint32_t* acc = lam.neg ? neg.p : pos.p;
+        bool& have = lam.neg ? have_neg : have_pos;
+        if (!have) { CU(ctx, cudaMemcpyAsync(acc, t.p, count * S * 4, cudaMemcpyDeviceToDevice, ctx->stream)); have = true; }
+        else if ((rc = modmul_dev(ctx, M, count, acc, t.p, acc))) return rc;
+    }
+    const uint32_t* cprime = pos.p;
+    if (have_neg) {                                                          // negative exponent: ModInverse (exp, :132-138)
+        if ((rc = modinv_dev(ctx, M, count, neg.p, t.p, bad.p))) return rc;
+        if (have_pos) { if ((rc = modmul_dev(ctx, M, count, pos.p, t.p, pos.p))) return rc; }
+        else cprime = t.p;
+    }
+    // computeDecryption: L(c') * (4 delta^2)^-1 mod n  :143-146, :63-66
+    CombineParams C{(uint32_t)count, (int)h, kd.p, mont_np0(ctx->n.v[0]), cprime, S, m_out};
+    CU(ctx, combine_final_launch(C, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
 }
 
 // -------------------------------------------------- host-buffer wrappers
@@ -896,6 +1062,131 @@ int pgpu_dot_u64(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, 
     if (io.rc) return io.rc;
     if ((rc = pgpu_dot_u64_dev(ctx, count, dc, (const uint64_t*)dk, dout))) return rc;
     return io.finish(out, dout, w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_ctx_z_width(const pgpu_ctx* ctx, size_t* w_z) {
+    if (!ctx || !w_z) return fail(nullptr, PGPU_ERR_ARG, "null argument");
+    *w_z = (size_t)z_limbs(ctx) * 4;
+    return PGPU_OK;
+}
+
+int pgpu_modinv(pgpu_ctx* ctx, int modsel, size_t count, const void* a, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (a && out)), "pgpu_modinv: null argument");
+    ModCtx* M = select_mod(ctx, modsel);
+    if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modinv: modulus not available for this key");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w = (size_t)M->sh.S * 4;
+    uint32_t* da = io.in(0, a, count * w);
+    uint32_t* dout = io.out(1, count * w);
+    uint32_t* dbad = io.out(2, 4);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = modinv_dev(ctx, *M, count, da, dout, dbad))) return rc; }
+    uint32_t bad = 0;
+    if ((rc = io.finish(&bad, dbad, 4))) return rc;
+    if ((rc = io.finish(out, dout, count * w))) return rc;
+    if (bad != 0xffffffffu) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "ModInverse: item " + std::to_string(bad) + " is not invertible");
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_sub_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (a && b && out)), "pgpu_sub_pairs: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    ModCtx& M = ctx->m_n2;
+    HostIo io(ctx);
+    const size_t w = (size_t)M.sh.S * 4;
+    uint32_t* da = io.in(0, a, count * w);
+    uint32_t* db = io.in(1, b, count * w);
+    uint32_t* dout = io.out(2, count * w);
+    uint32_t* dbad = io.out(3, 4);
+    if (io.rc) return io.rc;
+    {
+        TimedScope ts(ctx);
+        if ((rc = modinv_dev(ctx, M, count, db, dout, dbad))) return rc;          // neg := ModInverse(c.C, ns1)  operations.go:43
+        if ((rc = modmul_dev(ctx, M, count, da, dout, dout))) return rc;          // Mod(Mul(accumulator, neg))   :44-47
+    }
+    uint32_t bad = 0;
+    if ((rc = io.finish(&bad, dbad, 4))) return rc;
+    if ((rc = io.finish(out, dout, count * w))) return rc;
+    if (bad != 0xffffffffu) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "Sub: ciphertext " + std::to_string(bad) + " is not invertible mod n^2");
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_pdec_zkp_prove(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && r && dec && e && z)), "pgpu_pdec_zkp_prove: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4, wz = (size_t)z_limbs(ctx) * 4;
+    uint32_t* dc = io.in(0, c, count * w2);
+    uint32_t* dr = io.in(1, r, count * w2);
+    uint32_t* ddec = io.out(2, count * w2);
+    uint32_t* de = io.out(3, count * 32);
+    uint32_t* dz = io.out(4, count * wz);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = zkp_prove_dev(ctx, count, dc, dr, ddec, de, dz))) return rc; }
+    if ((rc = io.finish(dec, ddec, count * w2))) return rc;
+    if ((rc = io.finish(e, de, count * 32))) return rc;
+    return io.finish(z, dz, count * wz);
+    GUARD_END(ctx)
+}
+
+int pgpu_pdec_zkp_verify(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && dec && e && z && ok)), "pgpu_pdec_zkp_verify: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4, wz = (size_t)z_limbs(ctx) * 4;
+    uint32_t* dc = io.in(0, c, count * w2);
+    uint32_t* ddec = io.in(1, dec, count * w2);
+    uint32_t* de = io.in(2, e, count * 32);
+    uint32_t* dz = io.in(3, z, count * wz);
+    uint32_t* dok = io.out(4, count);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = zkp_verify_dev(ctx, count, id, dc, ddec, de, dz, (uint8_t*)dok))) return rc; }
+    return io.finish(ok, dok, count);
+    GUARD_END(ctx)
+}
+
+int pgpu_combine(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids) && (count == 0 || k == 0 || (decs && m)), "pgpu_combine: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4, wn = ctx->wn * 4;
+    uint32_t* dd = io.in(0, decs ? decs : (const void*)ids, std::max<size_t>(count * (size_t)k, 1) * (decs ? w2 : 1));
+    uint32_t* dm = io.out(1, std::max<size_t>(count, 1) * wn);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = combine_dev(ctx, count, k, ids, dd, dm))) return rc; }
+    if (count == 0) return PGPU_OK;
+    return io.finish(m, dm, count * wn);
+    GUARD_END(ctx)
+}
+
+int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && r && dec && e && z)), "pgpu_pdec_zkp_prove_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return zkp_prove_dev(ctx, count, (const uint32_t*)c, (const uint32_t*)r, (uint32_t*)dec, (uint32_t*)e, (uint32_t*)z);
+    GUARD_END(ctx)
+}
+
+int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids), "pgpu_combine_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return combine_dev(ctx, count, k, ids, (const uint32_t*)decs, (uint32_t*)m);
     GUARD_END(ctx)
 }
 

@@ -189,3 +189,108 @@ def test_threshold_keygen_matches_oracle():
     for k, ok in zip(keys, okeys):
         assert (k.ID, k.Share, k.VerificationKey, k.VerificationKeys) == (ok.ID, ok.Share, ok.VerificationKey, ok.VerificationKeys)
         k.close()
+
+
+# ---- Sub / ModInverse ---------------------------------------------------------------------------------
+
+def test_sub_and_modinverse(sk2048):
+    sk, osk = sk2048
+    n, n2 = sk.N, sk.N ** 2
+    opk = R.PublicKey(N=n)
+    ms = [5, 1000, n - 3, 77]
+    rs = from_records(synth.randomness(8, n, sk.w_n), sk.w_n)
+    a = sk.EncryptWithRBatch(ms, rs[:4])
+    b = sk.EncryptWithRBatch([2, 1, 4, 70], rs[4:])
+    got = sk.SubPairs(a, b)
+    assert [g.C for g in got] == [R.sub(opk, R.Ciphertext(x.C), R.Ciphertext(y.C)).C for x, y in zip(a, b)]
+    assert sk.DecryptBatch(got) == [3, 999, n - 7, 7]
+    xs = [x.C for x in a] + [1, n2 - 1, 2]
+    assert sk.ModInverseBatch(xs) == [pow(x, -1, n2) for x in xs]
+    from paillier_b200._lib import PgpuError, PGPU_ERR_NOT_INVERTIBLE
+    p, _, _ = _key("paillier_2048")
+    with pytest.raises(PgpuError) as ei:
+        sk.ModInverseBatch([3, p * 5, 7])
+    assert ei.value.code == PGPU_ERR_NOT_INVERTIBLE and "item 1" in str(ei.value)
+    n3 = sk.N ** 3
+    ys = [pow(7, i + 1, n3) for i in range(3)]
+    assert sk.ModInverseBatch(ys, MOD_N3) == [pow(y, -1, n3) for y in ys]
+
+
+# ---- threshold ZKP and share combining (thresholdkey.go:149-326) --------------------------------------
+
+def _threshold_setup(name, l, w, bits):
+    import random
+    from paillier_b200.keygen import ThresholdKeyGenerator
+    p, q, n = _key(name)
+    keys = ThresholdKeyGenerator(bits, l, w, rng=random.Random(5)).with_safe_primes(p, q).GenerateKeys()
+    okeys = [R.ThresholdSecretKey(N=n, TotalNumberOfDecryptionServers=l, Threshold=w, VerificationKey=k.VerificationKey,
+                                  VerificationKeys=k.VerificationKeys, ID=k.ID, Share=k.Share) for k in keys]
+    return n, keys, okeys
+
+
+@pytest.mark.parametrize("name,l,w,bits,count", [("threshold_512", 6, 4, 512, 40), ("threshold_2048", 8, 5, 2048, 6)])
+def test_zkp_prove_verify_combine(name, l, w, bits, count):
+    n, keys, okeys = _threshold_setup(name, l, w, bits)
+    n2 = n * n
+    tk = keys[0]
+    ms = from_records(synth.plaintexts(count, n, tk.w_n), tk.w_n)
+    ms[0] = 0
+    cs = [c.C for c in tk.EncryptWithRBatch(ms, from_records(synth.randomness(count, n, tk.w_n), tk.w_n))]
+    rs = from_records(synth.random_records(count, tk.w_n2, n2.bit_length() - 1, stream=21), tk.w_n2)
+    rs[1] = 0
+    proofs = []
+    for k, ok in zip(keys[:w + 1], okeys):
+        zk = k.PartialDecryptionWithZKPBatch(cs, rs)
+        for i in (0, 1, count - 1):      # transcript bit-exact with the oracle for fixed randomness
+            o = R.partial_decryption_with_zkp(ok, cs[i], rs[i])
+            assert (zk[i].ID, zk[i].Decryption, zk[i].E, zk[i].Z) == (o.ID, o.Decryption, o.E, o.Z)
+        proofs.append(zk)
+    # verification: accept honest proofs, reject a tampered one and a wrong server id (thresholdkey_test.go:137-149,283-292)
+    assert all(tk.VerifyProofBatch(proofs[2]))
+    bad = list(proofs[3])
+    bad[2] = type(bad[2])(bad[2].ID, bad[2].Decryption, bad[2].E, bad[2].Z + 1, bad[2].C)
+    res = tk.VerifyProofBatch(bad)
+    assert res[2] is False and all(r for i, r in enumerate(res) if i != 2)
+    wrong_id = [type(p)(p.ID + 1, p.Decryption, p.E, p.Z, p.C) for p in proofs[0]]
+    assert not any(tk.VerifyProofBatch(wrong_id))
+    from paillier_b200.api import PartialDecryption
+    shares = [[PartialDecryption(p.ID, p.Decryption) for p in s] for s in proofs]
+    assert tk.CombinePartialDecryptionsBatch(shares[:w]) == ms
+    assert tk.CombinePartialDecryptionsBatch(shares) == ms
+    assert tk.CombinePartialDecryptionsBatch(shares[1:w + 1][::-1]) == ms
+    otk = R.threshold_public_key(okeys[0])
+    assert tk.CombinePartialDecryptionsBatch(shares[:w])[0] == R.combine_partial_decryptions(
+        otk, [R.PartialDecryption(s[0].ID, s[0].Decryption) for s in shares[:w]])
+    assert tk.CombinePartialDecryptionsZKPBatch(proofs) == ms
+    from paillier_b200._lib import PgpuError, PGPU_ERR_THRESHOLD
+    with pytest.raises(PgpuError) as ei:
+        tk.CombinePartialDecryptionsBatch(shares[:w - 1])          # "Threshold not meet"
+    assert ei.value.code == PGPU_ERR_THRESHOLD
+    with pytest.raises(PgpuError) as ei:
+        tk.CombinePartialDecryptionsBatch(shares[:w - 1] + [shares[0]])   # duplicate server
+    assert ei.value.code == PGPU_ERR_THRESHOLD
+    for k in keys:
+        k.close()
+
+
+def test_combine_kat_on_gpu():
+    # thresholdkey_test.go:267-281 (TestDecryption): two literal shares -> 100
+    from paillier_b200.api import ThresholdPublicKey, PartialDecryption
+    tk = ThresholdPublicKey(637753, 2, 2, 70661107826, [])
+    got = tk.CombinePartialDecryptionsBatch([[PartialDecryption(1, 384111638639)], [PartialDecryption(2, 235243761043)]])
+    assert got == [100]
+    tk.close()
+
+
+def test_verify_kats_on_gpu():
+    # thresholdkey_test.go:109-135 (TestVerifyPart1 / TestVerifyPart2): n = 131
+    pk = PublicKey(131)
+    n2 = 131 * 131
+    c4, d2 = 99 ** 4 % n2, 101 ** 2 % n2
+    a1 = pk.ExpBatch([c4], [88])[0]
+    a2 = pk.ModInverseBatch(pk.ExpBatch([d2], [112]))[0]
+    assert pk.MulModBatch([a1], [a2]) == [11986]
+    b1 = pk.ExpBatch([101], [88])[0]
+    b2 = pk.ModInverseBatch(pk.ExpBatch([77], [112]))[0]
+    assert pk.MulModBatch([b1], [b2]) == [14602]
+    pk.close()
