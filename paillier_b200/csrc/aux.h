@@ -5,7 +5,7 @@
 
 namespace pgpu {
 
-constexpr int CRT_MAXH = 96;   // limbs of p, q (CRT recombination) and of n (share combining) supported
+constexpr int CRT_MAXH = 128;  // limbs of p, q (CRT recombination) and of n (share combining) supported
 
 // consts: 7 records of h limbs: p, q, p^-1 mod 2^(32h), q^-1 mod 2^(32h),
 // h_p*2^(32h) mod p, h_q*2^(32h) mod q, q^-1*2^(32h) mod p
@@ -47,6 +47,20 @@ struct CombineParams {
     uint32_t* out;           // h limbs per item
 };
 cudaError_t combine_final_launch(const CombineParams& P, cudaStream_t stream);
+
+// Level-2 recovery of Decrypt (recoveryAlgorithm for s = 2, paillier.go:308-340) followed by the
+// multiplication with lambda^-1 mod n^2 (:298-300).  tmp = c^lambda mod n^3 in records of t_stride limbs.
+// consts (H = 2h limbs each): n^2, n^-1 mod 2^(32H), R^2 mod n^2 (R = 2^(32H)), inv2*R mod n^2,
+// mu*R mod n^2 (mu = lambda^-1 mod n^2), n*R mod n^2
+struct Recover2Params {
+    uint32_t n_items;
+    int h;                   // limbs of n; n^2 arithmetic uses H = 2h limbs
+    const uint32_t* consts;
+    uint32_t np0_n2;
+    const uint32_t* tmp; uint32_t t_stride; uint32_t t_limbs;
+    uint32_t* out; uint32_t out_stride;   // H limbs written
+};
+cudaError_t recover2_launch(const Recover2Params& P, cudaStream_t stream);
 
 // ---- bigops.cu ----
 constexpr int BIG_MAXS = 192;
@@ -90,6 +104,8 @@ cudaError_t sha256_concat_launch(const ShaParams& P, cudaStream_t stream);
 
 cudaError_t equal_launch(const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint8_t* flags, cudaStream_t stream);
 cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream);
+// out[i] = in[i / rep] (records of `limbs` limbs): a statement value repeated for each of its proof instances
+cudaError_t repeat_launch(const uint32_t* in, uint32_t limbs, uint32_t rep, uint32_t* out, uint32_t n_out, cudaStream_t stream);
 cudaError_t resize_launch(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items, cudaStream_t stream);
 
 }  // namespace pgpu

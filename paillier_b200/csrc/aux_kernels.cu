@@ -147,6 +147,70 @@ cudaError_t combine_final_launch(const CombineParams& P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// r = (a + b) mod n or (a - b) mod n on H-limb arrays, a, b < n
+__device__ void st_addmod(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* n, int H) {
+    uint64_t c = 0;
+    for (int j = 0; j < H; ++j) { c += (uint64_t)a[j] + b[j]; r[j] = (uint32_t)c; c >>= 32; }
+    bool ge = c != 0;
+    if (!ge) { ge = true; for (int j = H - 1; j >= 0; --j) if (r[j] != n[j]) { ge = r[j] > n[j]; break; } }
+    if (ge) { int64_t bw = 0; for (int j = 0; j < H; ++j) { int64_t d = (int64_t)r[j] - n[j] - bw; bw = d < 0; r[j] = (uint32_t)d; } }
+}
+__device__ void st_submod(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* n, int H) {
+    int64_t bw = 0;
+    for (int j = 0; j < H; ++j) { int64_t d = (int64_t)a[j] - b[j] - bw; bw = d < 0; r[j] = (uint32_t)d; }
+    if (bw) { uint64_t c = 0; for (int j = 0; j < H; ++j) { c += (uint64_t)r[j] + n[j]; r[j] = (uint32_t)c; c >>= 32; } }
+}
+
+// Decrypt at level 2: m = recoveryAlgorithm(c^lambda mod n^3, 2) * lambda^-1 mod n^2  (paillier.go:298-340)
+__global__ void recover2_kernel(Recover2Params P) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.n_items) return;
+    const int h = P.h, H = 2 * h;
+    const uint32_t* N2 = P.consts;            const uint32_t* ninv = P.consts + H;
+    const uint32_t* R2 = P.consts + 2 * H;    const uint32_t* inv2M = P.consts + 3 * H;
+    const uint32_t* muM = P.consts + 4 * H;   const uint32_t* nM = P.consts + 5 * H;
+    const uint32_t* tmp = P.tmp + (size_t)idx * P.t_stride;
+    uint32_t lo[CRT_MAXH], hi[CRT_MAXH], one[CRT_MAXH], a[CRT_MAXH], b[CRT_MAXH], t1[CRT_MAXH];
+    for (int j = 0; j < H; ++j) {
+        lo[j] = tmp[j];
+        hi[j] = (uint32_t)(H + j) < P.t_limbs ? tmp[H + j] : 0;
+        one[j] = j == 0;
+    }
+    // j = 1: amod = tmp mod n^2 (:316); i1 = L(amod, n) (:318), an h-limb value
+    st_mont(a, lo, R2, N2, P.np0_n2, H);      // lo * R
+    st_mont(a, a, one, N2, P.np0_n2, H);      // lo mod n^2
+    st_mont(b, hi, R2, N2, P.np0_n2, H);      // hi * R mod n^2
+    st_addmod(a, a, b, N2, H);                // tmp mod n^2
+    uint32_t i1[CRT_MAXH];
+    st_L(i1, a, ninv, h);                     // (amod - 1) / n, exact
+    for (int j = h; j < H; ++j) i1[j] = 0;
+    // j = 2: t1 = L(tmp mod n^3, n) = (tmp - 1) / n (:316-318), an H-limb value
+    st_L(t1, tmp, ninv, H);
+    // k = 2 (:321-334): t2 = i1*(i1-1) mod n^2; t2 = t2 * n * 2!^-1; t1 = (t1 - t2) mod n^2
+    bool i1_zero = true;
+    for (int j = 0; j < h; ++j) i1_zero = i1_zero && i1[j] == 0;
+    if (!i1_zero) {
+        int64_t bw = 1;
+        for (int j = 0; j < H; ++j) { int64_t d = (int64_t)i1[j] - bw; bw = d < 0; b[j] = (uint32_t)d; }   // i1 - 1
+        st_mont(a, i1, R2, N2, P.np0_n2, H);          // i1 * R
+        st_mont(a, a, b, N2, P.np0_n2, H);            // i1 * (i1 - 1) mod n^2
+        st_mont(a, a, nM, N2, P.np0_n2, H);           // * n
+        st_mont(a, a, inv2M, N2, P.np0_n2, H);        // * 2^-1
+        st_submod(t1, t1, a, N2, H);
+    }
+    // m = i2 * mu mod n^2 (:298-300)
+    st_mont(a, t1, muM, N2, P.np0_n2, H);
+    uint32_t* out = P.out + (size_t)idx * P.out_stride;
+    for (int j = 0; j < H; ++j) out[j] = a[j];
+}
+
+cudaError_t recover2_launch(const Recover2Params& P, cudaStream_t stream) {
+    if (P.n_items == 0) return cudaSuccess;
+    const int threads = 32;
+    recover2_kernel<<<(P.n_items + threads - 1) / threads, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // PublicKey.Add over a batch (operations.go:11-29): one running Montgomery
 // product per group, then a shared-memory tree across the block's groups.

@@ -266,6 +266,19 @@ cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, const uint3
     return cudaGetLastError();
 }
 
+__global__ void repeat_kernel(const uint32_t* in, uint32_t limbs, uint32_t rep, uint32_t* out, uint32_t n_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const uint32_t* src = in + (size_t)(i / rep) * limbs;
+    for (uint32_t k = 0; k < limbs; ++k) out[(size_t)i * limbs + k] = src[k];
+}
+
+cudaError_t repeat_launch(const uint32_t* in, uint32_t limbs, uint32_t rep, uint32_t* out, uint32_t n_out, cudaStream_t stream) {
+    if (n_out == 0) return cudaSuccess;
+    repeat_kernel<<<(n_out + 127) / 128, 128, 0, stream>>>(in, limbs, rep, out, n_out);
+    return cudaGetLastError();
+}
+
 // widen / narrow records: out (out_limbs) = in (in_limbs), zero padded or truncated; stride 0 broadcasts one record
 __global__ void resize_kernel(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
