@@ -125,6 +125,44 @@ int pgpu_pdec_zkp_verify(pgpu_ctx* ctx, size_t count, int id, const void* c, con
  * PGPU_ERR_THRESHOLD for "Threshold not meet" / duplicate ids (:77-89). */
 int pgpu_combine(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
 
+
+/* ---- level 2 (mod n^3), alternative encryption, randomness, nested ops ---- */
+/* `level` is 1 (EncLevelOne) or 2 (EncLevelTwo), paillier.go:17-23.  At level 2 plaintexts are
+ * n2-width, ciphertexts n3-width; PGPU_ERR_UNSUPPORTED if n^3 exceeds the built kernel shapes. */
+
+/* PublicKey.EncryptWithRAtLevel (paillier.go:206-218): c = (1+n)^m * r^(n^s) mod n^(s+1); r: n-width */
+int pgpu_encrypt_with_r_at_level(pgpu_ctx* ctx, int level, size_t count, const void* m, const void* r, void* c);
+/* SecretKey.Decrypt at either level (paillier.go:292-340); level 2 runs recoveryAlgorithm(s = 2) */
+int pgpu_decrypt_at_level(pgpu_ctx* ctx, int level, size_t count, const void* c, void* m);
+/* PublicKey.H and K = 2^k_bits (paillier.go:46-56,151,158-161): enables AltEncrypt; precomputes the
+ * generators h_1, h_2 (getGeneratorOfQuadraticResiduesForLevel, :416-434) and their fixed-base tables */
+int pgpu_ctx_set_alt_generator(pgpu_ctx* ctx, const uint8_t* h_be, size_t h_len, unsigned k_bits);
+/* PublicKey.AltEncryptWithRAtLevel (paillier.go:221-238): c = (1+n)^m * h_s^(r mod K) mod n^(s+1).
+ * r: n-width; the reference reduces the caller's r mod K in place (:228) -- here r is read-only and
+ * the binding applies the same reduction to the caller's value. */
+int pgpu_alt_encrypt_with_r_at_level(pgpu_ctx* ctx, int level, size_t count, const void* m, const void* r, void* c);
+/* PublicKey.Randomize (operations.go:67-69) with the r of the fresh Encrypt(0) supplied: out = c * r^n mod n^2 */
+int pgpu_randomize_with_r(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* out);
+/* SecretKey.ExtractRandonness (operations.go:75-91); out: n-width */
+int pgpu_extract_randomness(pgpu_ctx* ctx, int level, size_t count, const void* c, void* out);
+/* PublicKey.NestedRandomize (operations.go:96-118) with a, b (n-width) supplied: ct^(a^n mod n^2) * b^(n^2) mod n^3 */
+int pgpu_nested_randomize_with(pgpu_ctx* ctx, size_t count, const void* ct, const void* a, const void* b, void* out);
+/* PublicKey.NestedAdd / NestedSub (operations.go:121-140): ct1 level 2 (n3-width), ct2 level 1 (n2-width) */
+int pgpu_nested_add(pgpu_ctx* ctx, size_t count, const void* ct1, const void* ct2, void* out);
+int pgpu_nested_sub(pgpu_ctx* ctx, size_t count, const void* ct1, const void* ct2, void* out);
+
+/* ---- DDLEQ proofs (ddleq.go) ---------------------------------------------- */
+/* SecretKey.ProveDDLEQ (ddleq.go:27-127) for `count` statements (ct1, ct2, a, b) with `secpar` instances
+ * each; instance j of statement i is record i*secpar + j.  x, y (n-width, in Z*_n) are the per-instance
+ * randomness the reference draws at :71-79.  Outputs: alpha, f n3-width; e n2-width (X = x, Y = y).
+ * PGPU_ERR_ARG "cannot prove re-encryption because inputs are wrong" where the reference panics (:67-69). */
+int pgpu_ddleq_prove(pgpu_ctx* ctx, size_t count, unsigned secpar, const void* ct1, const void* ct2, const void* a, const void* b,
+                     const void* x, const void* y, void* alpha, void* e, void* f);
+/* PublicKey.VerifyDDLEQProof (ddleq.go:44-53,129-153): ok[i*secpar + j] = 1 if instance j of proof i
+ * verifies; a proof is valid when all its instances are. */
+int pgpu_ddleq_verify(pgpu_ctx* ctx, size_t count, unsigned secpar, const void* ct1, const void* ct2, const void* x, const void* y,
+                      const void* alpha, const void* e, const void* f, uint8_t* ok);
+
 /* Generic batched gmp.Int.Exp (mpz_powm) / Mul+Mod against one of the key's
  * moduli; records are the modulus' width.  exp: per-item unsigned records of
  * exp_bytes bytes.  These back ConstMult, the ZKP and DDLEQ entry points. */

@@ -63,6 +63,17 @@ SIGNATURES = {
     "pgpu_combine": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
     "pgpu_pdec_zkp_prove_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
     "pgpu_combine_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
+    "pgpu_ctx_set_alt_generator": (C.c_int, [_p, _u8p, _sz, C.c_uint]),
+    "pgpu_encrypt_with_r_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
+    "pgpu_alt_encrypt_with_r_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
+    "pgpu_decrypt_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
+    "pgpu_randomize_with_r": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_extract_randomness": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
+    "pgpu_nested_randomize_with": (C.c_int, [_p, _sz, _p, _p, _p, _p]),
+    "pgpu_nested_add": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_nested_sub": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_ddleq_prove": (C.c_int, [_p, _sz, C.c_uint, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pgpu_ddleq_verify": (C.c_int, [_p, _sz, C.c_uint, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),

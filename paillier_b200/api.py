@@ -82,12 +82,30 @@ class PartialDecryptionZKP:
     C: int
 
 
-class PublicKey:
-    """paillier.go:46-56 with g = n+1 (paillier.go:147); owns one engine context on `device`."""
+@dataclass
+class DDLEQProofInstance:
+    """ddleq.go:11-13"""
+    X: int
+    Y: int
+    Alpha: int
+    E: int
+    F: int
 
-    def __init__(self, N: int, device: int = 0):
+
+@dataclass
+class DDLEQProof:
+    """ddleq.go:15-17"""
+    Instances: List[DDLEQProofInstance]
+
+
+class PublicKey:
+    """paillier.go:46-56 with g = n+1 (paillier.go:147); owns one engine context on `device`.
+    H and K (alternative encryption, paillier.go:151,158-166) are optional."""
+
+    def __init__(self, N: int, device: int = 0, H: Optional[int] = None, K: Optional[int] = None):
         self.N = int(N)
         self.G = self.N + 1
+        self.H, self.K = H, K
         self.device = device
         self._ctx = C.c_void_p()
         nb = _be(self.N)
@@ -95,6 +113,19 @@ class PublicKey:
         wn, w2, w3 = C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(lib.pgpu_ctx_widths(self._ctx, C.byref(wn), C.byref(w2), C.byref(w3)), self._ctx)
         self.w_n, self.w_n2, self.w_n3 = wn.value, w2.value, w3.value
+        if H is not None:
+            if K is None or K < 2 or K & (K - 1):
+                raise ValueError("K must be a power of two (paillier.go:151)")
+            hb = _be(H)
+            check(lib.pgpu_ctx_set_alt_generator(self._ctx, hb, len(hb), K.bit_length() - 1), self._ctx)
+
+    def _level_widths(self, level: int):
+        """(plaintext width, ciphertext width) of getModuliForLevel (paillier.go:403-414)"""
+        if level == ENC_LEVEL_ONE:
+            return self.w_n, self.w_n2
+        if level == ENC_LEVEL_TWO:
+            return self.w_n2, self.w_n3
+        raise ValueError("unknown encryption level")
 
     def close(self) -> None:
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -246,6 +277,79 @@ class PublicKey:
         width = {MOD_N2: self.w_n2, MOD_N3: self.w_n3}[modsel]
         return from_records(self.modmul_records(modsel, to_records(a, width), to_records(b, width), width), width)
 
+    # -- levels, alternative encryption, nested operations (paillier.go:206-238, operations.go:67-140) --
+    def EncryptWithRAtLevelBatch(self, ms: Sequence[int], rs: Sequence[int], level: int) -> List[Ciphertext]:
+        """N x PublicKey.EncryptWithRAtLevel (paillier.go:206-218)"""
+        wm, wc = self._level_widths(level)
+        mr, rr = to_records(ms, wm), to_records(rs, self.w_n)
+        out = np.empty(len(ms) * wc, dtype=np.uint8)
+        check(lib.pgpu_encrypt_with_r_at_level(self._ctx, level + 1, len(ms), _ptr(mr), _ptr(rr), _ptr(out)), self._ctx)
+        return [Ciphertext(c, level, REGULAR) for c in from_records(out, wc)]
+
+    def AltEncryptWithRAtLevelBatch(self, ms: Sequence[int], rs: List[int], level: int) -> List[Ciphertext]:
+        """N x PublicKey.AltEncryptWithRAtLevel (paillier.go:221-238).  Like the reference (:228) the caller's
+        r values are reduced mod K in place."""
+        if self.H is None:
+            raise ValueError("AltEncrypt needs PublicKey.H and K")
+        wm, wc = self._level_widths(level)
+        mr, rr = to_records(ms, wm), to_records([r % (1 << (8 * self.w_n)) for r in rs], self.w_n)   # the engine uses r mod K
+        out = np.empty(len(ms) * wc, dtype=np.uint8)
+        check(lib.pgpu_alt_encrypt_with_r_at_level(self._ctx, level + 1, len(ms), _ptr(mr), _ptr(rr), _ptr(out)), self._ctx)
+        for i in range(len(rs)):
+            rs[i] = rs[i] % self.K
+        return [Ciphertext(c, level, ALTERNATIVE) for c in from_records(out, wc)]
+
+    def RandomizeWithRBatch(self, cts: Sequence[Ciphertext], rs: Sequence[int]) -> List[Ciphertext]:
+        """N x PublicKey.Randomize (operations.go:67-69) = Add(ct, EncryptWithR(0, r)) with r supplied"""
+        cr, rr = to_records([c.C for c in cts], self.w_n2), to_records(rs, self.w_n)
+        out = np.empty(len(cts) * self.w_n2, dtype=np.uint8)
+        check(lib.pgpu_randomize_with_r(self._ctx, len(cts), _ptr(cr), _ptr(rr), _ptr(out)), self._ctx)
+        return [Ciphertext(c, ENC_LEVEL_ONE, MIXED) for c in from_records(out, self.w_n2)]
+
+    def NestedRandomizeWithBatch(self, cts: Sequence[Ciphertext], As: Sequence[int], Bs: Sequence[int]) -> List[Ciphertext]:
+        """N x PublicKey.NestedRandomize (operations.go:96-118) with the randomness (a, b) supplied"""
+        if any(c.Level != ENC_LEVEL_TWO for c in cts):
+            raise ValueError("can only homomorphically randomize doubly encrypted values")          # :97-99
+        cr, ar, br = to_records([c.C for c in cts], self.w_n3), to_records(As, self.w_n), to_records(Bs, self.w_n)
+        out = np.empty(len(cts) * self.w_n3, dtype=np.uint8)
+        check(lib.pgpu_nested_randomize_with(self._ctx, len(cts), _ptr(cr), _ptr(ar), _ptr(br), _ptr(out)), self._ctx)
+        return [Ciphertext(c, ENC_LEVEL_TWO, REGULAR) for c in from_records(out, self.w_n3)]
+
+    def _nested(self, fn, ct1s, ct2s):
+        if any(c.Level != ENC_LEVEL_TWO for c in ct1s) or any(c.Level != ENC_LEVEL_ONE for c in ct2s):
+            raise ValueError("can only homomorphically add an encrypted value to a doubly encrypted value")   # :122-124
+        r1, r2 = to_records([c.C for c in ct1s], self.w_n3), to_records([c.C for c in ct2s], self.w_n2)
+        out = np.empty(len(ct1s) * self.w_n3, dtype=np.uint8)
+        check(fn(self._ctx, len(ct1s), _ptr(r1), _ptr(r2), _ptr(out)), self._ctx)
+        return [Ciphertext(c, a.Level, a.EncMethod) for c, a in zip(from_records(out, self.w_n3), ct1s)]
+
+    def NestedAddBatch(self, ct1s: Sequence[Ciphertext], ct2s: Sequence[Ciphertext]) -> List[Ciphertext]:
+        """N x PublicKey.NestedAdd (operations.go:121-127)"""
+        return self._nested(lib.pgpu_nested_add, ct1s, ct2s)
+
+    def NestedSubBatch(self, ct1s: Sequence[Ciphertext], ct2s: Sequence[Ciphertext]) -> List[Ciphertext]:
+        """N x PublicKey.NestedSub (operations.go:130-140)"""
+        return self._nested(lib.pgpu_nested_sub, ct1s, ct2s)
+
+    def VerifyDDLEQProofBatch(self, ct1s: Sequence[Ciphertext], ct2s: Sequence[Ciphertext], proofs: Sequence[DDLEQProof]) -> List[bool]:
+        """N x PublicKey.VerifyDDLEQProof (ddleq.go:44-53); all proofs of a batch have the same number of instances"""
+        if not proofs:
+            return []
+        secpar = len(proofs[0].Instances)
+        if secpar == 0:
+            return [True] * len(proofs)                                                               # empty loop, :46-51
+        if any(len(p.Instances) != secpar for p in proofs):
+            raise ValueError("VerifyDDLEQProofBatch: one secpar per batch")
+        inst = [i for p in proofs for i in p.Instances]
+        c1, c2 = to_records([c.C for c in ct1s], self.w_n3), to_records([c.C for c in ct2s], self.w_n3)
+        x, y = to_records([i.X for i in inst], self.w_n), to_records([i.Y for i in inst], self.w_n)
+        al, e, f = (to_records([i.Alpha for i in inst], self.w_n3), to_records([i.E for i in inst], self.w_n2),
+                    to_records([i.F for i in inst], self.w_n3))
+        ok = np.zeros(len(inst), dtype=np.uint8)
+        check(lib.pgpu_ddleq_verify(self._ctx, len(proofs), secpar, _ptr(c1), _ptr(c2), _ptr(x), _ptr(y), _ptr(al), _ptr(e), _ptr(f),
+                                    _ptr(ok)), self._ctx)
+        return [bool(ok[i * secpar:(i + 1) * secpar].all()) for i in range(len(proofs))]
+
     # -- introspection -------------------------------------------------------
     def launch_count(self) -> int:
         v = C.c_uint64()
@@ -261,8 +365,9 @@ class PublicKey:
 class SecretKey(PublicKey):
     """paillier.go:59-62: the reference keeps Lambda = (p-1)(q-1) only; either form is accepted."""
 
-    def __init__(self, N: int, Lambda: Optional[int] = None, p: Optional[int] = None, q: Optional[int] = None, device: int = 0):
-        super().__init__(N, device)
+    def __init__(self, N: int, Lambda: Optional[int] = None, p: Optional[int] = None, q: Optional[int] = None, device: int = 0,
+                 H: Optional[int] = None, K: Optional[int] = None):
+        super().__init__(N, device, H, K)
         if p is not None and q is not None:
             pb, qb = _be(p), _be(q)
             check(lib.pgpu_ctx_set_secret_pq(self._ctx, pb, len(pb), qb, len(qb)), self._ctx)
@@ -283,10 +388,69 @@ class SecretKey(PublicKey):
         return out
 
     def DecryptBatch(self, cts: Sequence[Ciphertext]) -> List[int]:
-        """N x SecretKey.Decrypt (paillier.go:292-303), level 1"""
-        if any(c.Level != ENC_LEVEL_ONE for c in cts):
-            raise ValueError("DecryptBatch handles level-1 ciphertexts")
-        return from_records(self.decrypt_records(to_records([c.C for c in cts], self.w_n2)), self.w_n)
+        """N x SecretKey.Decrypt (paillier.go:292-303); one level per batch"""
+        if not cts:
+            return []
+        level = cts[0].Level
+        if any(c.Level != level for c in cts):
+            raise ValueError("DecryptBatch: one encryption level per batch")
+        if level == ENC_LEVEL_ONE:
+            return from_records(self.decrypt_records(to_records([c.C for c in cts], self.w_n2)), self.w_n)
+        wm, wc = self._level_widths(level)
+        cr = to_records([c.C for c in cts], wc)
+        out = np.empty(len(cts) * wm, dtype=np.uint8)
+        check(lib.pgpu_decrypt_at_level(self._ctx, level + 1, len(cts), _ptr(cr), _ptr(out)), self._ctx)
+        return from_records(out, wm)
+
+    def DecryptNestedCiphertextLayerBatch(self, cts: Sequence[Ciphertext]) -> List[Ciphertext]:
+        """N x SecretKey.DecryptNestedCiphertextLayer (paillier.go:360-372)"""
+        if any(c.Level == ENC_LEVEL_ONE for c in cts):
+            raise ValueError("no nested ciphertexts to recover")                                      # :362-364
+        return [Ciphertext(v, ENC_LEVEL_ONE, MIXED) for v in self.DecryptBatch(cts)]
+
+    def NestedDecryptBatch(self, cts: Sequence[Ciphertext]) -> List[int]:
+        """N x SecretKey.NestedDecrypt (paillier.go:344-356): the inner value 0 decrypts to 0 (:350-354)"""
+        inner = self.DecryptNestedCiphertextLayerBatch(cts)
+        nz = [i for i, c in enumerate(inner) if c.C != 0]
+        vals = self.DecryptBatch([inner[i] for i in nz])
+        out = [0] * len(cts)
+        for i, v in zip(nz, vals):
+            out[i] = v
+        return out
+
+    def ExtractRandonnessBatch(self, cts: Sequence[Ciphertext]) -> List[int]:
+        """N x SecretKey.ExtractRandonness (operations.go:75-91); one level per batch"""
+        if not cts:
+            return []
+        level = cts[0].Level
+        _, wc = self._level_widths(level)
+        cr = to_records([c.C for c in cts], wc)
+        out = np.empty(len(cts) * self.w_n, dtype=np.uint8)
+        check(lib.pgpu_extract_randomness(self._ctx, level + 1, len(cts), _ptr(cr), _ptr(out)), self._ctx)
+        return from_records(out, self.w_n)
+
+    def ProveDDLEQBatch(self, secpar: int, ct1s: Sequence[Ciphertext], ct2s: Sequence[Ciphertext], As: Sequence[int], Bs: Sequence[int],
+                        xs: Sequence[Sequence[int]], ys: Sequence[Sequence[int]]) -> List[DDLEQProof]:
+        """N x SecretKey.ProveDDLEQ (ddleq.go:27-40); xs[i][j], ys[i][j] in Z*_n are the randomness of instance j of
+        statement i (ddleq.go:71-79).  Raises PgpuError where the reference panics on wrong inputs (:67-69)."""
+        count = len(ct1s)
+        if secpar == 0 or count == 0:
+            return [DDLEQProof([]) for _ in range(count)]
+        fx = [x for row in xs for x in row]
+        fy = [y for row in ys for y in row]
+        if len(fx) != count * secpar or len(fy) != count * secpar:
+            raise ValueError("ProveDDLEQBatch: secpar values of x and y per statement")
+        c1, c2 = to_records([c.C for c in ct1s], self.w_n3), to_records([c.C for c in ct2s], self.w_n3)
+        a, b = to_records(As, self.w_n), to_records(Bs, self.w_n)
+        x, y = to_records(fx, self.w_n), to_records(fy, self.w_n)
+        total = count * secpar
+        al, e, f = (np.empty(total * self.w_n3, dtype=np.uint8), np.empty(total * self.w_n2, dtype=np.uint8),
+                    np.empty(total * self.w_n3, dtype=np.uint8))
+        check(lib.pgpu_ddleq_prove(self._ctx, count, secpar, _ptr(c1), _ptr(c2), _ptr(a), _ptr(b), _ptr(x), _ptr(y),
+                                   _ptr(al), _ptr(e), _ptr(f)), self._ctx)
+        A, E, F = from_records(al, self.w_n3), from_records(e, self.w_n2), from_records(f, self.w_n3)
+        return [DDLEQProof([DDLEQProofInstance(fx[k], fy[k], A[k], E[k], F[k]) for k in range(i * secpar, (i + 1) * secpar)])
+                for i in range(count)]
 
 
 class ThresholdPublicKey(PublicKey):

@@ -98,12 +98,16 @@ struct ShaParams {
     const uint32_t* seg[6];
     uint32_t stride[6];      // limbs between items (0 = same value for every item)
     int limbs[6];
+    uint32_t div[6];         // item i hashes record i / div (0 is read as 1)
     uint32_t* out;           // 8 limbs per item
 };
 cudaError_t sha256_concat_launch(const ShaParams& P, cudaStream_t stream);
 
 cudaError_t equal_launch(const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint8_t* flags, cudaStream_t stream);
-cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream);
+// *first = smallest i with flags[i] == 0, else 0xffffffff
+cudaError_t first_zero_launch(const uint8_t* flags, uint32_t n_items, uint32_t* first, cudaStream_t stream);
+// out[i] = (digest[i] & 1) ? a[i / a_div] : b[i / b_div]
+cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, uint32_t a_div, const uint32_t* b, uint32_t b_div, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream);
 // out[i] = in[i / rep] (records of `limbs` limbs): a statement value repeated for each of its proof instances
 cudaError_t repeat_launch(const uint32_t* in, uint32_t limbs, uint32_t rep, uint32_t* out, uint32_t n_out, cudaStream_t stream);
 cudaError_t resize_launch(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items, cudaStream_t stream);

@@ -224,7 +224,7 @@ __global__ void sha256_concat_kernel(ShaParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_items) return;
     Sha256 S; S.init();
-    for (int s = 0; s < P.n_seg; ++s) S.put_int(P.seg[s] + (size_t)i * P.stride[s], P.limbs[s]);
+    for (int s = 0; s < P.n_seg; ++s) S.put_int(P.seg[s] + (size_t)(i / (P.div[s] ? P.div[s] : 1u)) * P.stride[s], P.limbs[s]);
     S.finish();
     uint32_t* out = P.out + (size_t)i * 8;
     for (int k = 0; k < 8; ++k) out[k] = S.h[7 - k];
@@ -252,17 +252,30 @@ cudaError_t equal_launch(const uint32_t* a, const uint32_t* b, uint32_t limbs, u
     return cudaGetLastError();
 }
 
+__global__ void first_zero_kernel(const uint8_t* flags, uint32_t n_items, uint32_t* first) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && blockIdx.x == 0) atomicMin(first, 0xffffffffu);
+    if (i < n_items && flags[i] == 0) atomicMin(first, i);
+}
+
+cudaError_t first_zero_launch(const uint8_t* flags, uint32_t n_items, uint32_t* first, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(first, 0xff, 4, stream);
+    if (e != cudaSuccess || n_items == 0) return e;
+    first_zero_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(flags, n_items, first);
+    return cudaGetLastError();
+}
+
 // out[i] = pick[i] ? a[i] : b[i]  (records of `limbs` limbs; pick = low bit of an 8-limb digest record)
-__global__ void select_kernel(const uint32_t* digest, const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint32_t* out) {
+__global__ void select_kernel(const uint32_t* digest, const uint32_t* a, uint32_t a_div, const uint32_t* b, uint32_t b_div, uint32_t limbs, uint32_t n_items, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
-    const uint32_t* src = (digest[(size_t)i * 8] & 1) ? a + (size_t)i * limbs : b + (size_t)i * limbs;
+    const uint32_t* src = (digest[(size_t)i * 8] & 1) ? a + (size_t)(i / a_div) * limbs : b + (size_t)(i / b_div) * limbs;
     for (uint32_t k = 0; k < limbs; ++k) out[(size_t)i * limbs + k] = src[k];
 }
 
-cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, const uint32_t* b, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream) {
+cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, uint32_t a_div, const uint32_t* b, uint32_t b_div, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream) {
     if (n_items == 0) return cudaSuccess;
-    select_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(digest, a, b, limbs, n_items, out);
+    select_kernel<<<(n_items + 127) / 128, 128, 0, stream>>>(digest, a, a_div ? a_div : 1, b, b_div ? b_div : 1, limbs, n_items, out);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,627 @@
+// Engine internals (engine.hpp): key constants, program compiler, device-side operations.
+#include "engine.hpp"
+
+namespace pgpu {
+
+namespace { thread_local std::string g_err; }
+std::string& thread_error() { return g_err; }
+
+// smallest built shape holding `limbs` limbs; override with PGPU_SHAPE_<S>="tpi,L"
+bool pick_shape(size_t limbs, Shape& out) {
+    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 8, 12}, {128, 4, 32}, {192, 8, 24}};
+    for (const Shape& s : defaults) {
+        if ((size_t)s.S >= limbs) {
+            out = s;
+            char name[32];
+            snprintf(name, sizeof name, "PGPU_SHAPE_%d", s.S);
+            if (const char* e = getenv(name)) {
+                int t = 0, l = 0;
+                if (sscanf(e, "%d,%d", &t, &l) == 2 && t * l == s.S && vm_occupancy(t, l) > 0) { out.tpi = t; out.L = l; }
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+int fail(pgpu_ctx* ctx, int code, const std::string& msg) {
+    g_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v) {
+    CU(ctx, cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PGPU_OK;
+}
+
+int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v) {
+    return upload(ctx, m.d_kconst + (size_t)slot * m.sh.S, v.limbs(m.sh.S));
+}
+
+int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
+    if (!N.is_odd()) return fail(ctx, PGPU_ERR_ARG, "modulus must be odd");
+    if (!pick_shape(N.v.size(), m.sh)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus wider than the built kernel shapes");
+    m.N = N;
+    const BigU R = BigU::pow2(32 * (size_t)m.sh.S);
+    m.R1 = R % N;
+    m.R2 = (m.R1 * m.R1) % N;
+    m.R3 = (m.R2 * m.R1) % N;
+    m.np0 = mont_np0(N.v[0]);
+    CU(ctx, cudaMalloc(&m.d_mod, (size_t)m.sh.S * 4));
+    CU(ctx, cudaMalloc(&m.d_kconst, (size_t)K_SLOTS * m.sh.S * 4));
+    CU(ctx, cudaMemsetAsync(m.d_kconst, 0, (size_t)K_SLOTS * m.sh.S * 4, ctx->stream));
+    int rc;
+    if ((rc = upload(ctx, m.d_mod, N.limbs(m.sh.S)))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R2, m.R2))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R1, m.R1))) return rc;
+    if ((rc = set_kconst(ctx, m, K_ONE, BigU(1)))) return rc;
+    if ((rc = set_kconst(ctx, m, K_R3, m.R3))) return rc;
+    m.blocks_per_sm = vm_occupancy(m.sh.tpi, m.sh.L);
+    if (m.blocks_per_sm <= 0) return fail(ctx, PGPU_ERR_CUDA, "powm_vm occupancy query failed for shape");
+    m.ready = true;
+    return PGPU_OK;
+}
+
+void modctx_free(ModCtx& m) {
+    if (m.d_mod) cudaFree(m.d_mod);
+    if (m.d_kconst) cudaFree(m.d_kconst);
+    m = ModCtx();
+}
+
+// ------------------------------------------------------- program compiler
+int choose_window(size_t bits) {
+    int best = 1; double best_cost = 1e300;
+    for (int w = 1; w <= 7; ++w) {
+        double cost = (w == 1 ? 0.0 : (double)(1u << (w - 1))) + (double)bits / (w + 1);
+        if (cost < best_cost) { best_cost = cost; best = w; }
+    }
+    return best;
+}
+
+// x holds the base in Montgomery form; afterwards x = base^e (Montgomery form).
+// Sliding window over the shared exponent e: odd powers in T[tb .. tb+2^(w-1)),
+// base^2 in T[tb+2^(w-1)].   gmp semantics: e = 0 gives 1.
+void emit_pow_shared(Program& P, const BigU& e, uint32_t tb) {
+    const size_t bits = e.bitlen();
+    if (bits == 0) { P.emit(OP_LDC, K_R1); return; }
+    const int w = choose_window(bits);
+    const uint32_t nodd = 1u << (w - 1);
+    P.emit(OP_STT, tb); P.use_slot(tb);
+    if (w > 1) {
+        const uint32_t sq = tb + nodd;
+        P.emit(OP_SQR, 1); P.n_sqr += 1;
+        P.emit(OP_STT, sq); P.use_slot(sq);
+        for (uint32_t i = 1; i < nodd; ++i) {   // x = T[i-1] * base^2
+            if (i == 1) P.emit(OP_LDT, tb);
+            P.emit(OP_MULT, sq); P.n_mul += 1;
+            P.emit(OP_STT, tb + i);
+        }
+    }
+    bool first = true;
+    uint32_t pending = 0;
+    long i = (long)bits - 1;
+    while (i >= 0) {
+        if (!e.bit(i)) { ++pending; --i; continue; }
+        long j = std::max<long>(i - w + 1, 0);
+        while (!e.bit(j)) ++j;
+        uint32_t val = 0;
+        for (long k = i; k >= j; --k) val = (val << 1) | (e.bit(k) ? 1u : 0u);
+        const uint32_t len = (uint32_t)(i - j + 1), idx = tb + (val >> 1);
+        if (first) {
+            P.emit(OP_LDT, idx);
+            first = false;
+        } else {
+            uint32_t nsq = pending + len;
+            if (nsq > 0xfff) { P.emit(OP_SQR, nsq - len); nsq = len; }
+            P.emit(OP_SQMT, nsq | (idx << 12));
+            P.n_sqr += pending + len; P.n_mul += 1;
+        }
+        pending = 0;
+        i = j - 1;
+    }
+    if (pending) { P.emit(OP_SQR, pending); P.n_sqr += pending; }
+}
+
+// per-item exponents of exp_bits bits (OP_WIN): full table T[tb .. tb+2^w), fixed window
+void emit_pow_items(Program& P, size_t exp_bits, uint32_t tb) {
+    int w = 1;
+    { double best = 1e300; for (int c = 1; c <= 6; ++c) { double cost = (double)(1u << c) + (double)exp_bits / c; if (cost < best) { best = cost; w = c; } } }
+    const uint32_t n = 1u << w;
+    // T[tb+1] = base, T[tb] = 1, T[tb+i] = T[tb+i-1] * base
+    P.emit(OP_STT, tb + 1);
+    for (uint32_t i = 2; i < n; ++i) { P.emit(OP_MULT, tb + 1); P.n_mul += 1; P.emit(OP_STT, tb + i); }
+    P.emit(OP_LDC, K_R1); P.emit(OP_STT, tb);
+    P.use_slot(tb + n - 1);
+    const size_t nwin = (exp_bits + w - 1) / w;
+    for (size_t k = nwin; k-- > 0;) {
+        // x starts at 1, so the first squarings are of 1; keep the program uniform
+        P.emit(OP_WIN, (uint32_t)(k * w) | ((uint32_t)w << 20) | (tb << 24));
+        P.n_sqr += w; P.n_mul += 1;
+    }
+}
+
+int program_upload(pgpu_ctx* ctx, Program& P) {
+    P.ops.push_back(vm_op(OP_END, 0));
+    if (P.d_ops) cudaFree(P.d_ops);
+    CU(ctx, cudaMalloc(&P.d_ops, P.ops.size() * 4));
+    return upload(ctx, P.d_ops, P.ops);
+}
+
+void program_free(Program& P) { if (P.d_ops) cudaFree(P.d_ops); P = Program(); }
+
+// ------------------------------------------------------------- launching
+int ensure_table(pgpu_ctx* ctx, size_t limbs) {
+    if (limbs <= ctx->table_limbs) return PGPU_OK;
+    if (ctx->d_table) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_limbs = 0; }
+    CU(ctx, cudaMalloc(&ctx->d_table, limbs * 4));
+    ctx->table_limbs = limbs;
+    return PGPU_OK;
+}
+
+int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
+           const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
+           const ExpDesc& ex) {
+    if (count == 0) return PGPU_OK;
+    if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
+    const int gpb = VM_BLOCK_THREADS / m.sh.tpi;
+    const size_t max_blocks = (size_t)ctx->sms * m.blocks_per_sm;
+    const size_t want = (count + gpb - 1) / gpb;
+    const int blocks = (int)std::min(max_blocks, want);
+    VmParams P{};
+    P.prog = prog.d_ops;
+    P.n_items = (uint32_t)count;
+    P.mod = m.d_mod; P.np0 = m.np0; P.kconst = m.d_kconst;
+    for (int i = 0; i < VM_MAX_IN; ++i) P.in_div[i] = 1;
+    for (int i = 0; i < n_in; ++i) { P.in[i] = ins[i].ptr; P.in_stride[i] = ins[i].stride; P.in_limbs[i] = ins[i].limbs; P.in_div[i] = std::max<uint32_t>(ins[i].div, 1); }
+    P.out[0] = out; P.out_stride[0] = out_stride; P.out_limbs[0] = out_limbs;
+    P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed;
+    P.n_groups = (uint32_t)blocks * gpb;
+    int rc = ensure_table(ctx, (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S);
+    if (rc) return rc;
+    P.table = ctx->d_table;
+    CU(ctx, vm_launch(m.sh.tpi, m.sh.L, P, blocks, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->stage_bytes[slot] < bytes) {
+        if (ctx->d_stage[slot]) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_stage[slot]); ctx->d_stage[slot] = nullptr; ctx->stage_bytes[slot] = 0; }
+        CU(ctx, cudaMalloc(&ctx->d_stage[slot], std::max<size_t>(bytes, 256)));
+        ctx->stage_bytes[slot] = std::max<size_t>(bytes, 256);
+    }
+    *out = ctx->d_stage[slot];
+    return PGPU_OK;
+}
+
+ModCtx* select_mod(pgpu_ctx* ctx, int modsel) {
+    switch (modsel) {
+        case PGPU_MOD_N: return ctx->m_n.ready ? &ctx->m_n : nullptr;
+        case PGPU_MOD_N2: return ctx->m_n2.ready ? &ctx->m_n2 : nullptr;
+        case PGPU_MOD_N3: return ctx->m_n3.ready ? &ctx->m_n3 : nullptr;
+    }
+    return nullptr;
+}
+
+// ---------------------------------------------------- compiled key programs
+// EncryptWithR, level 1 (paillier.go:206-218) with the g = n+1 shortcut:
+// c = (1 + m*n) * r^n mod n^2.   in0 = r, in1 = m.
+int build_encrypt(pgpu_ctx* ctx) {
+    Program& P = ctx->prog_enc;
+    program_free(P);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;           // r -> Montgomery form
+    emit_pow_shared(P, ctx->n, 0);              // r^n
+    const uint32_t RES = P.tbl_entries;         // next free table slot
+    P.emit(OP_STT, RES); P.use_slot(RES);
+    P.emit(OP_LDI, 1);
+    P.emit(OP_MULC, K_NR2); P.n_mul++;          // m*n (Montgomery form), exact since m*n < n^2
+    P.emit(OP_ADDC, K_R1);                      // + 1
+    P.emit(OP_MULT, RES); P.n_mul++;
+    P.emit(OP_MULC, K_ONE); P.n_mul++;          // out of Montgomery form
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+// One CRT half of Decrypt: x = c^(p-1) mod p^2.  in0 = low half of c, in1 = high half
+// (c = lo + hi*R with R = 2^(32*S) of the p^2 shape).
+int build_decrypt_half(pgpu_ctx* ctx, Program& P, const BigU& pm1) {
+    program_free(P);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;           // lo*R
+    P.emit(OP_STT, 0); P.use_slot(0);
+    P.emit(OP_LDI, 1);
+    P.emit(OP_MULC, K_R3); P.n_mul++;           // hi*R*R
+    P.emit(OP_ADDT, 0);                         // (c mod p^2) in Montgomery form
+    emit_pow_shared(P, pm1, 0);
+    P.emit(OP_MULC, K_ONE); P.n_mul++;
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+// PartialDecrypt (thresholdkey.go:192-201): c^(2*delta*share) mod n^2
+int build_pdec(pgpu_ctx* ctx) {
+    Program& P = ctx->prog_pdec;
+    program_free(P);
+    const BigU e = ctx->tk_share * (BigU(2) * ctx->tk_delta);
+    P.emit(OP_LDI, 0);
+    P.emit(OP_MULC, K_R2); P.n_mul++;
+    emit_pow_shared(P, e, 0);
+    P.emit(OP_MULC, K_ONE); P.n_mul++;
+    P.emit(OP_STO, 0);
+    return program_upload(ctx, P);
+}
+
+int setup_crt(pgpu_ctx* ctx) {
+    const BigU &p = ctx->p, &q = ctx->q;
+    int rc;
+    modctx_free(ctx->m_p2); modctx_free(ctx->m_q2);
+    if ((rc = modctx_init(ctx, ctx->m_p2, p * p))) return rc;
+    if ((rc = modctx_init(ctx, ctx->m_q2, q * q))) return rc;
+    if (ctx->m_p2.sh.S != ctx->m_q2.sh.S) return fail(ctx, PGPU_ERR_UNSUPPORTED, "p and q of different width");
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec_p, p - BigU(1)))) return rc;
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec_q, q - BigU(1)))) return rc;
+    const int h = ctx->m_p2.sh.S / 2;
+    if (h > CRT_MAXH || p.v.size() > (size_t)h || q.v.size() > (size_t)h) return fail(ctx, PGPU_ERR_UNSUPPORTED, "prime factors too wide for the CRT recombination");
+    ctx->crt_h = h;
+    const BigU Rh = BigU::pow2(32 * (size_t)h);
+    BigU pinv, qinv, qinv_p, hp, hq, t;
+    if (!BigU::modinv(p, Rh, pinv) || !BigU::modinv(q, Rh, qinv)) return fail(ctx, PGPU_ERR_ARG, "p, q must be odd");
+    if (!BigU::modinv(q % p, p, qinv_p)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
+    // h_p = L_p(g^(p-1) mod p^2)^-1 mod p with g = n+1: g^(p-1) = 1 + (p-1)*n mod p^2
+    const BigU p2 = p * p, q2 = q * q;
+    BigU gp = (BigU(1) + (p - BigU(1)) * ctx->n) % p2, gq = (BigU(1) + (q - BigU(1)) * ctx->n) % q2;
+    BigU lp = ((gp - BigU(1)) / p) % p, lq = ((gq - BigU(1)) / q) % q;
+    if (!BigU::modinv(lp, p, hp) || !BigU::modinv(lq, q, hq)) return fail(ctx, PGPU_ERR_ARG, "invalid key: L(g^(p-1)) not invertible");
+    std::vector<uint32_t> K;
+    auto push = [&](const BigU& x) { auto l = x.limbs(h); K.insert(K.end(), l.begin(), l.end()); };
+    push(p); push(q); push(pinv); push(qinv);
+    push((hp * Rh) % p); push((hq * Rh) % q); push((qinv_p * Rh) % p);
+    if (ctx->d_crt) cudaFree(ctx->d_crt);
+    CU(ctx, cudaMalloc(&ctx->d_crt, K.size() * 4));
+    if ((rc = upload(ctx, ctx->d_crt, K))) return rc;
+    ctx->crt_np0_p = mont_np0(p.v[0]); ctx->crt_np0_q = mont_np0(q.v[0]);
+    ctx->has_secret = true;
+    return setup_level2_secret(ctx);
+}
+
+// ------------------------------------------------------- device-side ops
+int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    const ModCtx& M = ctx->m_n2;
+    IoDesc ins[2] = {{r, (uint32_t)ctx->wn, (uint32_t)ctx->wn}, {m, (uint32_t)ctx->wn, (uint32_t)ctx->wn}};
+    return run_vm(ctx, M, ctx->prog_enc, count, ins, 2, c, M.sh.S, M.sh.S);
+}
+
+int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "Decrypt: no secret key loaded");
+    const ModCtx &P2 = ctx->m_p2, &Q2 = ctx->m_q2;
+    const uint32_t S2 = ctx->m_n2.sh.S, Sp = P2.sh.S;
+    // c (S2 limbs) = lo (Sp limbs) + hi * 2^(32*Sp); S2 <= 2*Sp
+    const uint32_t hi_limbs = S2 > Sp ? S2 - Sp : 0;
+    void *xp, *xq; int rc;
+    if ((rc = stage(ctx, 4, count * Sp * 4, &xp))) return rc;
+    if ((rc = stage(ctx, 5, count * Sp * 4, &xq))) return rc;
+    IoDesc ins[2] = {{c, S2, std::min(S2, Sp)}, {c + Sp, S2, hi_limbs}};
+    if ((rc = run_vm(ctx, P2, ctx->prog_dec_p, count, ins, 2, (uint32_t*)xp, Sp, Sp))) return rc;
+    if ((rc = run_vm(ctx, Q2, ctx->prog_dec_q, count, ins, 2, (uint32_t*)xq, Sp, Sp))) return rc;
+    CrtParams C{};
+    C.n_items = (uint32_t)count; C.h = ctx->crt_h; C.consts = ctx->d_crt;
+    C.np0_p = ctx->crt_np0_p; C.np0_q = ctx->crt_np0_q;
+    C.xp = (const uint32_t*)xp; C.xq = (const uint32_t*)xq; C.x_stride = Sp;
+    C.out = m; C.out_stride = (uint32_t)ctx->wn; C.out_limbs = (uint32_t)ctx->wn;
+    CU(ctx, crt_combine_launch(C, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out) {
+    if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecrypt: no threshold share loaded");
+    const ModCtx& M = ctx->m_n2;
+    IoDesc ins[1] = {{c, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, ctx->prog_pdec, count, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+Program* cached_program(pgpu_ctx* ctx, const std::string& key) {
+    auto it = ctx->prog_cache.find(key);
+    return it == ctx->prog_cache.end() ? nullptr : &it->second;
+}
+
+// out[i] = base[i]^exp[i] mod M with per-item exponents of exp.bits bits (fixed window)
+int modexp_items_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const ExpDesc& exp, uint32_t* out) {
+    const std::string key = "powi:" + std::to_string(M.sh.S) + ":" + std::to_string(exp.bits);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        emit_pow_items(np, exp.bits, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {base};
+    return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S, exp);
+}
+
+int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,
+                     bool broadcast_base) {
+    return modexp_items_io(ctx, M, count, IoDesc{base, broadcast_base ? 0u : (uint32_t)M.sh.S, (uint32_t)M.sh.S},
+                           ExpDesc{exp, exp_limbs, 32 * exp_limbs, nullptr}, out);
+}
+
+// out[i] = base[i]^e mod M, one exponent for the whole batch (sliding window compiled on the host)
+int modexp_shared_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const BigU& e, uint32_t* out) {
+    const std::string key = "pows:" + std::to_string(M.sh.S) + ":" + e.hex();
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        emit_pow_shared(np, e, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        if (ctx->prog_cache.size() > 64) {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
+            ctx->prog_cache.clear();
+        }
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {base};
+    return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+int modexp_shared_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const BigU& e, uint32_t* out) {
+    return modexp_shared_io(ctx, M, count, IoDesc{base, (uint32_t)M.sh.S, (uint32_t)M.sh.S}, e, out);
+}
+
+int modmul_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& a, const IoDesc& b, uint32_t* out) {
+    const std::string key = "mul:" + std::to_string(M.sh.S);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_MULI, 1); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[2] = {a, b};
+    return run_vm(ctx, M, *P, count, ins, 2, out, M.sh.S, M.sh.S);
+}
+
+int modmul_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    return modmul_io(ctx, M, count, IoDesc{a, (uint32_t)M.sh.S, (uint32_t)M.sh.S}, IoDesc{b, (uint32_t)M.sh.S, (uint32_t)M.sh.S}, out);
+}
+
+// out = prod in[i] mod M (Add over a batch)
+int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_t* out) {
+    const int gpb = 128 / M.sh.tpi;
+    const size_t max_blocks = (size_t)ctx->sms * 4;
+    size_t b1 = std::min(max_blocks, (count + gpb - 1) / gpb);
+    if (b1 == 0) b1 = 1;
+    void* part; int rc;
+    if ((rc = stage(ctx, 3, (b1 + 1) * M.sh.S * 4, &part))) return rc;
+    uint32_t* partial = (uint32_t*)part;
+    auto rounds = [&](size_t n, size_t blocks) { size_t G = blocks * gpb; return n == 0 ? (size_t)1 : (n + G - 1) / G; };
+    // stage 1: b1 blocks -> b1 partials, each carrying R^-(gpb*rounds1 - 1)
+    ProdParams P1{in, (uint32_t)count, M.d_mod, M.np0, partial};
+    CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P1, (int)b1, ctx->stream));
+    ctx->launches++;
+    uint64_t T = (uint64_t)b1 * (gpb * rounds(count, b1) - 1);
+    uint32_t* last = partial;
+    if (b1 > 1) {
+        uint32_t* fin = partial + b1 * M.sh.S;
+        ProdParams P2{partial, (uint32_t)b1, M.d_mod, M.np0, fin};
+        CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P2, 1, ctx->stream));
+        ctx->launches++;
+        T += gpb * rounds(b1, 1) - 1;
+        last = fin;
+    }
+    // final correction: times R^(T+1), one more Montgomery multiply
+    const BigU fix = BigU::modexp(M.R1, BigU(T + 1), M.N);
+    if ((rc = set_kconst(ctx, M, K_FIX, fix))) return rc;
+    const std::string key = "fix:" + std::to_string(M.sh.S);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_FIX); np.n_mul++;
+        np.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{last, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, 1, ins, 1, out, M.sh.S, M.sh.S);
+}
+
+
+// signed big integer for the Lagrange coefficients of share combining
+struct BigS { BigU mag; bool neg = false; };
+
+// Euclidean division by a small signed integer (Go big.Int.Div semantics, pinned by thresholdkey_test.go:168-177)
+BigS euclid_div(const BigS& num, long den) {
+    const BigU d((uint64_t)(den < 0 ? -den : den));
+    BigU q0, r0; BigU::divmod(num.mag, d, q0, r0);
+    BigS q;
+    if (!num.neg || num.mag.is_zero()) { q.mag = q0; q.neg = den < 0 && !q0.is_zero(); return q; }
+    if (r0.is_zero()) { q.mag = q0; q.neg = den > 0 && !q0.is_zero(); return q; }
+    q.mag = q0 + BigU(1); q.neg = den > 0;
+    return q;
+}
+
+// out[i] = in[i]^-1 mod M; *d_first_bad = index of the first non-invertible item or 0xffffffff
+int modinv_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad) {
+    if (M.sh.S > BIG_MAXS) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus too wide for modinv");
+    CU(ctx, cudaMemsetAsync(d_first_bad, 0xff, 4, ctx->stream));
+    InvParams P{(uint32_t)count, M.sh.S, M.d_mod, in, out, d_first_bad};
+    CU(ctx, modinv_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* out) {
+    MulParams P{(uint32_t)count, a, na, (int)na, b, nb, (int)nb, out, na + nb, na + nb};
+    CU(ctx, bigmul_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, const uint32_t* stride, const int* limbs, uint32_t* out,
+            const uint32_t* div) {
+    ShaParams P{}; P.n_items = (uint32_t)count; P.n_seg = n_seg; P.out = out;
+    for (int i = 0; i < n_seg; ++i) { P.seg[i] = seg[i]; P.stride[i] = stride[i]; P.limbs[i] = limbs[i]; P.div[i] = div ? div[i] : 1; }
+    CU(ctx, sha256_concat_launch(P, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+uint32_t z_limbs(const pgpu_ctx* ctx) { return (uint32_t)ctx->m_n2.sh.S + 16; }   // Z = r + E*delta*share < 2^(32*(S+16))
+
+// ZKP transcript hash shared by prover and verifier: c^4 and c_i^2 enter unreduced (thresholdkey.go:241,248,319-326)
+int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* dec, uint32_t* e_out) {
+    const uint32_t S = ctx->m_n2.sh.S;
+    DEVBUF(c2, ctx, count * 2 * S); DEVBUF(c4, ctx, count * 4 * S); DEVBUF(ci2, ctx, count * 2 * S);
+    int rc;
+    if ((rc = bigmul_dev(ctx, count, c, S, c, S, c2.p))) return rc;
+    if ((rc = bigmul_dev(ctx, count, c2.p, 2 * S, c2.p, 2 * S, c4.p))) return rc;
+    if ((rc = bigmul_dev(ctx, count, dec, S, dec, S, ci2.p))) return rc;
+    const uint32_t* seg[4] = {a, b, c4.p, ci2.p};
+    const uint32_t stride[4] = {S, S, 4 * S, 2 * S};
+    const int limbs[4] = {(int)S, (int)S, (int)(4 * S), (int)(2 * S)};
+    return sha_dev(ctx, count, 4, seg, stride, limbs, e_out);
+}
+
+// PartialDecryptionWithZKP (thresholdkey.go:225-255), r supplied
+int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z) {
+    if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecryptionWithZKP: no threshold share loaded");
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const BigU k = ctx->tk_delta * ctx->tk_share;
+    if (k.v.size() + 8 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "share too large for the Z record");
+    int rc;
+    if ((rc = pdec_dev(ctx, count, c, dec))) return rc;
+    DEVBUF(c4r, ctx, count * S); DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(v, ctx, S);
+    DEVBUF(kd, ctx, k.v.size() + 1);
+    if ((rc = upload(ctx, v.p, ctx->tk_v.limbs(S)))) return rc;
+    if ((rc = upload(ctx, kd.p, k.limbs(k.v.size() + 1)))) return rc;
+    if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), c4r.p))) return rc;           // c^4 mod n^2: (c^4)^r = (c^4 mod n^2)^r
+    if ((rc = modexp_items_dev(ctx, M, count, c4r.p, r, S, a.p))) return rc;             // a = (c^4)^r        :242
+    if ((rc = modexp_items_dev(ctx, M, count, v.p, r, S, b.p, true))) return rc;         // b = V^r            :245
+    if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e))) return rc;                 // E                  :250
+    MulAddParams Q{(uint32_t)count, r, S, S, e, 8, 8, kd.p, (int)k.v.size(), z, z_limbs(ctx), z_limbs(ctx)};
+    CU(ctx, muladd_launch(Q, ctx->stream));                                              // Z = r + E*delta*share :252
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+// VerifyProof (thresholdkey.go:278-311)
+int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok) {
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "VerifyProof: no threshold key loaded");
+    if (id < 1 || (size_t)id > ctx->tk_vi.size()) return fail(ctx, PGPU_ERR_ARG, "VerifyProof: no verification key for this server id");   // VerificationKeys[ID-1] :305
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S, ZL = z_limbs(ctx);
+    int rc;
+    DEVBUF(t0, ctx, count * S); DEVBUF(t1, ctx, count * S); DEVBUF(t2, ctx, count * S);
+    DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(kv, ctx, S); DEVBUF(kvi, ctx, S); DEVBUF(bad, ctx, 1); DEVBUF(e2, ctx, count * 8);
+    if ((rc = upload(ctx, kv.p, ctx->tk_v.limbs(S)))) return rc;
+    if ((rc = upload(ctx, kvi.p, ctx->tk_vi[id - 1].limbs(S)))) return rc;
+    // a = (c^4)^Z * ((c_i^2)^E)^-1 mod n^2        verifyPart1 :293-302
+    if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), t0.p))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, t0.p, z, ZL, t1.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, dec, dec, t0.p))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, t0.p, e, 8, t2.p))) return rc;
+    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, a.p))) return rc;
+    // b = V^Z * (v_i^E)^-1 mod n^2                verifyPart2 :304-311
+    if ((rc = modexp_items_dev(ctx, M, count, kv.p, z, ZL, t1.p, true))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, kvi.p, e, 8, t2.p, true))) return rc;
+    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, b.p))) return rc;
+    if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e2.p))) return rc;
+    CU(ctx, equal_launch(e, e2.p, 8, (uint32_t)count, ok, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+// CombinePartialDecryptions (thresholdkey.go:149-161); decs = k batches of `count` n^2-width records, one per share
+int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out) {
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "CombinePartialDecryptions: no threshold key loaded");
+    if (k < ctx->tk_w) return fail(ctx, PGPU_ERR_THRESHOLD, "Threshold not meet");                               // :78-80
+    for (int i = 0; i < k; ++i) for (int j = i + 1; j < k; ++j)
+        if (ids[i] == ids[j]) return fail(ctx, PGPU_ERR_THRESHOLD, "two shares has been created by the same server");  // :81-87
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const size_t h = ctx->wn;
+    if (h > (size_t)CRT_MAXH) return fail(ctx, PGPU_ERR_UNSUPPORTED, "n too wide for the combine tail");
+    const BigU Rh = BigU::pow2(32 * h);
+    BigU ninv, K;
+    if (!BigU::modinv(ctx->n, Rh, ninv)) return fail(ctx, PGPU_ERR_ARG, "n must be odd");
+    if (!BigU::modinv((BigU(4) * ctx->tk_delta * ctx->tk_delta) % ctx->n, ctx->n, K)) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "4*delta^2 not invertible mod n");
+    std::vector<uint32_t> kc;
+    for (const BigU& x : {ctx->n, ninv, (K * Rh) % ctx->n}) { auto l = x.limbs(h); kc.insert(kc.end(), l.begin(), l.end()); }
+    int rc;
+    DEVBUF(pos, ctx, count * S); DEVBUF(neg, ctx, count * S); DEVBUF(t, ctx, count * S); DEVBUF(bad, ctx, 1); DEVBUF(kd, ctx, kc.size());
+    if ((rc = upload(ctx, kd.p, kc))) return rc;
+    bool have_pos = false, have_neg = false;
+    for (int i = 0; i < k; ++i) {
+        BigS lam; lam.mag = ctx->tk_delta;                                   // computeLambda :99-107
+        for (int j = 0; j < k; ++j) {
+            if (ids[j] == ids[i]) continue;
+            BigS num; num.mag = lam.mag * BigU((uint64_t)(ids[j] < 0 ? -(long)ids[j] : (long)ids[j]));
+            num.neg = (lam.neg != (ids[j] > 0)) && !num.mag.is_zero();       // lambda * (-j)   :92
+            lam = euclid_div(num, (long)ids[i] - (long)ids[j]);              // Div(num, i - j) :93-94
+        }
+        const BigU e2 = lam.mag * BigU(2);                                   // updateCprime: exponent 2*lambda :119-124
+        if ((rc = modexp_shared_dev(ctx, M, count, decs + (size_t)i * count * S, e2, t.p))) return rc;
+        uint32_t* acc = lam.neg ? neg.p : pos.p;
+        bool& have = lam.neg ? have_neg : have_pos;
+        if (!have) { CU(ctx, cudaMemcpyAsync(acc, t.p, count * S * 4, cudaMemcpyDeviceToDevice, ctx->stream)); have = true; }
+        else if ((rc = modmul_dev(ctx, M, count, acc, t.p, acc))) return rc;
+    }
+    const uint32_t* cprime = pos.p;
+    if (have_neg) {                                                          // negative exponent: ModInverse (exp, :132-138)
+        if ((rc = modinv_dev(ctx, M, count, neg.p, t.p, bad.p))) return rc;
+        if (have_pos) { if ((rc = modmul_dev(ctx, M, count, pos.p, t.p, pos.p))) return rc; }
+        else cprime = t.p;
+    }
+    // computeDecryption: L(c') * (4 delta^2)^-1 mod n  :143-146, :63-66
+    CombineParams C{(uint32_t)count, (int)h, kd.p, mont_np0(ctx->n.v[0]), cprime, S, m_out};
+    CU(ctx, combine_final_launch(C, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+uint32_t* HostIo::in(int slot, const void* host, size_t bytes) {
+    void* d = nullptr;
+    if (rc) return nullptr;
+    if ((rc = stage(ctx, slot, bytes, &d))) return nullptr;
+    cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { rc = fail(ctx, PGPU_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); return nullptr; }
+    return (uint32_t*)d;
+}
+uint32_t* HostIo::out(int slot, size_t bytes) {
+    void* d = nullptr;
+    if (rc) return nullptr;
+    if ((rc = stage(ctx, slot, bytes, &d))) return nullptr;
+    return (uint32_t*)d;
+}
+int HostIo::finish(void* host, const uint32_t* dev, size_t bytes) {
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+    return PGPU_OK;
+}
+
+int set_device(pgpu_ctx* ctx) { CU(ctx, cudaSetDevice(ctx->device)); return PGPU_OK; }
+
+}  // namespace pgpu

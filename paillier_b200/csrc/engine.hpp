@@ -1,0 +1,215 @@
+// Internal interface of the engine behind include/pgpu.h: key contexts, the host-side compiler from
+// reference functions to powm_vm micro-programs (vm.h) and the device-side operations the C ABI
+// (capi.cu) and the protocol layers (protocols.cu) are assembled from.  Nothing here runs CPU
+// arithmetic on a batch item: the host derives per-key constants and programs, then launches kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pgpu.h"
+#include "aux.h"
+#include "bn_host.hpp"
+#include "launch.h"
+#include "vm.h"
+
+namespace pgpu {
+
+struct Shape { int S, tpi, L; };
+
+// kconst slots shared by every modulus
+enum : uint32_t {
+    K_R2 = 0, K_R1 = 1, K_ONE = 2, K_R3 = 3, K_NR2 = 4, K_FIX = 5,
+    K_NEG1 = 6,   // -1                         (Montgomery form; level-2 g^m shortcut)
+    K_C1 = 7,     // n^2 / 2 mod n^3            (Montgomery form)
+    K_NM = 8,     // n                          (Montgomery form)
+    K_NSM = 9,    // n^s for the modulus n^(s+1) (Montgomery form; g^(-v) = g^(n^s - v))
+    K_R4 = 10,    // R^4 mod N
+    K_SLOTS = 16
+};
+
+struct Program {
+    std::vector<uint32_t> ops;
+    uint32_t* d_ops = nullptr;
+    uint32_t n_sqr = 0, n_mul = 0, tbl_entries = 0;
+    void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); }
+    void use_slot(uint32_t s) { tbl_entries = std::max(tbl_entries, s + 1); }
+};
+
+struct ModCtx {
+    bool ready = false;
+    Shape sh{};
+    BigU N, R1, R2, R3;
+    uint32_t np0 = 0;
+    uint32_t* d_mod = nullptr;
+    uint32_t* d_kconst = nullptr;   // K_SLOTS records of S limbs
+    int blocks_per_sm = 0;
+};
+
+// fixed-base comb table for OP_FIXW: row k holds base^(d * 2^(w*k)), d = 0 .. 2^w-1, Montgomery form
+struct FixedTable {
+    uint32_t* d = nullptr;
+    uint32_t w = 0, nwin = 0, bits = 0;
+};
+
+}  // namespace pgpu
+
+struct pgpu_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    pgpu::BigU n, n2, n3;
+    size_t wn = 0;         // limbs of an n-width record
+    pgpu::ModCtx m_n, m_n2, m_n3, m_p2, m_q2;
+
+    // secret key
+    bool has_secret = false;
+    pgpu::BigU p, q;
+    uint32_t* d_crt = nullptr;
+    uint32_t crt_np0_p = 0, crt_np0_q = 0;
+    int crt_h = 0;
+
+    // threshold key
+    bool has_threshold = false, has_share = false;
+    int tk_l = 0, tk_w = 0, tk_id = 0;
+    pgpu::BigU tk_share, tk_v, tk_delta;
+    std::vector<pgpu::BigU> tk_vi;
+
+    pgpu::Program prog_enc, prog_dec_p, prog_dec_q, prog_pdec;
+
+    // level 2 (mod n^3), alternative encryption, randomness extraction (protocols.cu)
+    bool level2_ready = false;
+    pgpu::Program prog_enc2, prog_rand;
+    uint32_t* d_rec2 = nullptr;             // constants of recover2_kernel
+    bool has_alt = false;
+    pgpu::BigU alt_h; uint32_t alt_kbits = 0;
+    pgpu::FixedTable fix_h1, fix_h2, fix_v;
+    pgpu::Program prog_alt1, prog_alt2;
+    std::map<std::string, pgpu::Program> prog_cache;
+
+    // scratch
+    uint32_t* d_table = nullptr; size_t table_limbs = 0;
+    void* d_stage[12] = {};
+    size_t stage_bytes[12] = {};
+
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+namespace pgpu {
+
+int fail(pgpu_ctx* ctx, int code, const std::string& msg);
+std::string& thread_error();
+
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return ::pgpu::fail(ctx, PGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define REQUIRE(ctx, cond, msg) do { if (!(cond)) return ::pgpu::fail(ctx, PGPU_ERR_ARG, msg); } while (0)
+#define GUARD_BEGIN try {
+#define GUARD_END(ctx) } catch (const std::exception& ex) { return ::pgpu::fail(ctx, PGPU_ERR_ARG, ex.what()); }
+
+struct IoDesc { const uint32_t* ptr; uint32_t stride, limbs; uint32_t div = 1; };   // item i reads record i / div
+// per-item exponents (OP_WIN / OP_FIXW): records `stride` limbs apart of which the low `bits` bits count
+struct ExpDesc { const uint32_t* ptr = nullptr; uint32_t stride = 0, bits = 0; const uint32_t* fixed = nullptr; };
+
+// stream-ordered temporary device buffer
+struct DevBuf {
+    pgpu_ctx* c; uint32_t* p = nullptr; cudaError_t err = cudaSuccess;
+    DevBuf(pgpu_ctx* ctx, size_t limbs) : c(ctx) { err = cudaMallocAsync((void**)&p, std::max<size_t>(limbs, 1) * 4, ctx->stream); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, c->stream); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+#define DEVBUF(name, ctx, limbs) ::pgpu::DevBuf name(ctx, limbs); if (name.err != cudaSuccess) return ::pgpu::fail(ctx, PGPU_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(name.err))
+
+struct TimedScope {
+    pgpu_ctx* c;
+    explicit TimedScope(pgpu_ctx* ctx) : c(ctx) { if (c->timing) { cudaEventRecord(c->ev0, c->stream); } }
+    ~TimedScope() { if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->ev_valid = true; } }
+};
+
+// host-buffer staging for the blocking entry points
+struct HostIo {
+    pgpu_ctx* ctx;
+    int rc = PGPU_OK;
+    explicit HostIo(pgpu_ctx* c) : ctx(c) {}
+    uint32_t* in(int slot, const void* host, size_t bytes);
+    uint32_t* out(int slot, size_t bytes);
+    int finish(void* host, const uint32_t* dev, size_t bytes);
+};
+
+bool pick_shape(size_t limbs, Shape& out);
+int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v);
+int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v);
+int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N);
+void modctx_free(ModCtx& m);
+int choose_window(size_t bits);
+void emit_pow_shared(Program& P, const BigU& e, uint32_t tb);
+void emit_pow_items(Program& P, size_t exp_bits, uint32_t tb);
+int program_upload(pgpu_ctx* ctx, Program& P);
+void program_free(Program& P);
+int ensure_table(pgpu_ctx* ctx, size_t limbs);
+int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
+           const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
+           const ExpDesc& ex = ExpDesc());
+int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out);
+ModCtx* select_mod(pgpu_ctx* ctx, int modsel);
+int build_encrypt(pgpu_ctx* ctx);
+int build_pdec(pgpu_ctx* ctx);
+int setup_crt(pgpu_ctx* ctx);
+int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
+int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
+int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out);
+Program* cached_program(pgpu_ctx* ctx, const std::string& key);
+int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,
+                     bool broadcast_base = false);
+int modexp_shared_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const BigU& e, uint32_t* out);
+int modmul_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* a, const uint32_t* b, uint32_t* out);
+// the same three with explicit record descriptors (narrower records, broadcast, one record per `div` items)
+int modexp_items_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const ExpDesc& exp, uint32_t* out);
+int modexp_shared_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const BigU& e, uint32_t* out);
+int modmul_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& a, const IoDesc& b, uint32_t* out);
+int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_t* out);
+int modinv_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad);
+int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* out);
+int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, const uint32_t* stride, const int* limbs, uint32_t* out,
+            const uint32_t* div = nullptr);
+uint32_t z_limbs(const pgpu_ctx* ctx);
+int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z);
+int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok);
+int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out);
+int set_device(pgpu_ctx* ctx);
+
+// ---- protocols.cu: level 2, alternative encryption, randomness extraction, nested operations, DDLEQ
+void protocols_free(pgpu_ctx* ctx);
+int fixed_table_build(pgpu_ctx* ctx, const ModCtx& M, const BigU& base, uint32_t exp_bits, FixedTable& T);
+void fixed_table_free(FixedTable& T);
+int setup_level2(pgpu_ctx* ctx);
+int setup_level2_secret(pgpu_ctx* ctx);
+int setup_alt(pgpu_ctx* ctx);
+int encrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
+int decrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
+int alt_encrypt_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
+int randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* out);
+int extract_randomness_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_t* c, uint32_t* out);
+int nested_randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* ct, const uint32_t* a, const uint32_t* b, uint32_t* out);
+int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t* ct1, const uint32_t* ct2, const uint32_t* a, const uint32_t* b,
+                    const uint32_t* x, const uint32_t* y, uint32_t* alpha, uint32_t* e, uint32_t* f, uint32_t* d_bad);
+int ddleq_verify_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t* ct1, const uint32_t* ct2, const uint32_t* x, const uint32_t* y,
+                     const uint32_t* alpha, const uint32_t* e, const uint32_t* f, uint8_t* ok);
+
+}  // namespace pgpu

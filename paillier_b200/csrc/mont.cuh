@@ -220,6 +220,44 @@ struct Mont {
         addc(ov, 0, 0);
         resolve_reduce(r, ov);
     }
+
+    // r = (a - b) mod n, a, b < n
+    __device__ __forceinline__ void sub(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+        uint32_t d[L], bw;
+        sub_cc(d[0], a[0], b[0]);
+#pragma unroll
+        for (int k = 1; k < L; ++k) subc_cc(d[k], a[k], b[k]);
+        subc(bw, 0, 0);
+        uint32_t any = d[0];
+#pragma unroll
+        for (int k = 1; k < L; ++k) any |= d[k];
+        const uint32_t bg = gballot(bw != 0);
+        const uint32_t bp = gballot(any == 0);
+        const uint64_t bi = lookahead(bg, bp);
+        const uint32_t bin = (uint32_t)(bi >> t) & 1u;
+        sub_cc(d[0], d[0], bin);
+#pragma unroll
+        for (int k = 1; k < L; ++k) subc_cc(d[k], d[k], 0);
+        const bool negative = ((uint32_t)(bi >> TPI) & 1u) != 0;
+        // a < b: add n back (the value is d + n - 2^(32S), exact in S limbs)
+        uint32_t s[L], cy;
+        add_cc(s[0], d[0], n[0]);
+#pragma unroll
+        for (int k = 1; k < L; ++k) addc_cc(s[k], d[k], n[k]);
+        addc(cy, 0, 0);
+        uint32_t all1 = s[0];
+#pragma unroll
+        for (int k = 1; k < L; ++k) all1 &= s[k];
+        const uint32_t g = gballot(cy != 0);
+        const uint32_t p = gballot(all1 == 0xffffffffu);
+        const uint64_t ci = lookahead(g, p);
+        const uint32_t cin = (uint32_t)(ci >> t) & 1u;
+        add_cc(s[0], s[0], cin);
+#pragma unroll
+        for (int k = 1; k < L; ++k) addc_cc(s[k], s[k], 0);
+#pragma unroll
+        for (int k = 0; k < L; ++k) r[k] = negative ? s[k] : d[k];
+    }
 };
 
 }  // namespace pgpu

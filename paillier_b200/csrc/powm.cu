@@ -47,11 +47,14 @@ __device__ __forceinline__ void store_vec(uint32_t* __restrict__ p, const uint32
 }
 
 // bits [pos, pos+w) of a little-endian limb array
-__device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uint32_t nlimbs, uint32_t pos, uint32_t w) {
-    const uint32_t limb = pos >> 5, sh = pos & 31;
+__device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uint32_t nbits, uint32_t pos, uint32_t w) {
+    if (pos >= nbits) return 0;
+    const uint32_t limb = pos >> 5, sh = pos & 31, nlimbs = (nbits + 31) >> 5;
     uint64_t v = e[limb];
     if (sh + w > 32 && limb + 1 < nlimbs) v |= (uint64_t)e[limb + 1] << 32;
-    return (uint32_t)(v >> sh) & ((1u << w) - 1u);
+    uint32_t r = (uint32_t)(v >> sh) & ((1u << w) - 1u);
+    if (pos + w > nbits) r &= (1u << (nbits - pos)) - 1u;
+    return r;
 }
 
 template <int TPI, int L>
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
             uint32_t nsq = 0, nmul = 0;
             switch (code) {
                 case OP_LDI: {
-                    const uint32_t* p = P.in[arg] + (size_t)item * P.in_stride[arg];
+                    const uint32_t* p = P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg];
                     const uint32_t lim = P.in_limbs[arg];
 #pragma unroll
                     for (int k = 0; k < L; ++k) {
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                 case OP_MULT: load_vec<L>(y, tbl + arg * tbl_entry_stride); nmul = 1; break;
                 case OP_MULC: load_vec<L>(y, kc + (size_t)arg * S); nmul = 1; break;
                 case OP_MULI: {
-                    const uint32_t* p = P.in[arg] + (size_t)item * P.in_stride[arg];
+                    const uint32_t* p = P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg];
                     const uint32_t lim = P.in_limbs[arg];
 #pragma unroll
                     for (int k = 0; k < L; ++k) {
@@ -123,10 +126,17 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                 case OP_ADDC: load_vec<L>(y, kc + (size_t)arg * S); M.add(x, x, y); break;
                 case OP_WIN: {
                     const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, tbase = arg >> 24;
-                    const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_stride, pos, w);
+                    const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w);
                     load_vec<L>(y, tbl + (tbase + idx) * tbl_entry_stride);
                     nsq = w; nmul = 1;
                 } break;
+                case OP_FIXW: {
+                    const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu;
+                    const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w);
+                    load_vec<L>(y, P.fixed + ((size_t)(pos / w) * (1u << w) + idx) * S + lane_t * L);
+                    nmul = 1;
+                } break;
+                case OP_SUBT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
                 case OP_SQMT: {
                     const uint32_t idx = arg >> 12;
                     load_vec<L>(y, tbl + idx * tbl_entry_stride);

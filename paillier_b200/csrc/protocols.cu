@@ -1,0 +1,400 @@
+// Level-2 (mod n^3) encryption and decryption, alternative encryption with fixed-base tables,
+// randomness extraction, nested operations and the DDLEQ proofs, assembled from the engine's
+// device-side operations (engine.hpp).  Reference: paillier.go:206-238,292-372,
+// operations.go:67-140, ddleq.go:27-153, random_oracle.go:10-32.
+#include "engine.hpp"
+
+namespace pgpu {
+
+namespace {
+
+BigU to_mont(const ModCtx& M, const BigU& x) { return ((x % M.N) * M.R1) % M.N; }
+
+// x = m*R on entry (Montgomery form); afterwards x = (1+n)^m * R mod n^2 = (1 + m*n) * R
+void emit_g_pow_level1(Program& P) {
+    P.emit(OP_MULC, K_NM); P.n_mul++;
+    P.emit(OP_ADDC, K_R1);
+}
+
+// x = m*R on entry; afterwards x = (1+n)^m * R mod n^3 = (1 + m*n + m(m-1)/2 * n^2) * R.
+// Uses table slot `slot`.
+void emit_g_pow_level2(Program& P, uint32_t slot) {
+    P.emit(OP_STT, slot); P.use_slot(slot);
+    P.emit(OP_ADDC, K_NEG1);                 // m - 1
+    P.emit(OP_MULC, K_C1); P.n_mul++;        // (m - 1) * n^2/2
+    P.emit(OP_ADDC, K_NM);                   // + n
+    P.emit(OP_MULT, slot); P.n_mul++;        // * m
+    P.emit(OP_ADDC, K_R1);                   // + 1
+}
+
+// x = product of base^(digit_k * 2^(w*k)) from the fixed table T (starts from 1)
+void emit_pow_fixed(Program& P, const FixedTable& T) {
+    P.emit(OP_LDC, K_R1);
+    for (uint32_t k = 0; k < T.nwin; ++k) { P.emit(OP_FIXW, (k * T.w) | (T.w << 20)); P.n_mul++; }
+}
+
+}  // namespace
+
+void fixed_table_free(FixedTable& T) { if (T.d) cudaFree(T.d); T = FixedTable(); }
+
+// T = comb table of base^(d * 2^(w*k)) mod M for exponents of exp_bits bits, built on the device:
+// rows base^(2^(w*k)) by one batched exponentiation, the 2^w multiples of each row by a second one.
+int fixed_table_build(pgpu_ctx* ctx, const ModCtx& M, const BigU& base, uint32_t exp_bits, FixedTable& T) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    fixed_table_free(T);
+    if (exp_bits == 0) return fail(ctx, PGPU_ERR_ARG, "fixed-base table for an empty exponent");
+    const uint32_t S = M.sh.S;
+    uint32_t w = 1;
+    for (uint32_t c = 2; c <= 8; ++c) {
+        const size_t nwin = (exp_bits + c - 1) / c;
+        if ((nwin << c) * S * 4 <= ((size_t)32 << 20)) w = c;
+    }
+    const uint32_t nwin = (exp_bits + w - 1) / w, per = 1u << w;
+    const uint32_t el = (w * (nwin - 1)) / 32 + 1;
+    std::vector<uint32_t> e1((size_t)nwin * el, 0), e2((size_t)nwin * per);
+    for (uint32_t k = 0; k < nwin; ++k) e1[(size_t)k * el + (w * k) / 32] = 1u << ((w * k) % 32);
+    for (size_t i = 0; i < e2.size(); ++i) e2[i] = (uint32_t)(i % per);
+    DEVBUF(de1, ctx, e1.size()); DEVBUF(de2, ctx, e2.size()); DEVBUF(db, ctx, S); DEVBUF(dr1, ctx, S);
+    DEVBUF(rows, ctx, (size_t)nwin * S); DEVBUF(ent, ctx, (size_t)nwin * per * S);
+    int rc;
+    if ((rc = upload(ctx, de1.p, e1))) return rc;
+    if ((rc = upload(ctx, de2.p, e2))) return rc;
+    if ((rc = upload(ctx, db.p, (base % M.N).limbs(S)))) return rc;
+    if ((rc = upload(ctx, dr1.p, M.R1.limbs(S)))) return rc;
+    if ((rc = modexp_items_io(ctx, M, nwin, IoDesc{db.p, 0, S}, ExpDesc{de1.p, el, 32 * el, nullptr}, rows.p))) return rc;
+    if ((rc = modexp_items_io(ctx, M, (size_t)nwin * per, IoDesc{rows.p, S, S, per}, ExpDesc{de2.p, 1, w, nullptr}, ent.p))) return rc;
+    CU(ctx, cudaMalloc(&T.d, (size_t)nwin * per * S * 4));
+    if ((rc = modmul_io(ctx, M, (size_t)nwin * per, IoDesc{ent.p, S, S}, IoDesc{dr1.p, 0, S}, T.d))) return rc;   // -> Montgomery form
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    T.w = w; T.nwin = nwin; T.bits = exp_bits;
+    return PGPU_OK;
+}
+
+void protocols_free(pgpu_ctx* ctx) {
+    program_free(ctx->prog_enc2); program_free(ctx->prog_rand); program_free(ctx->prog_alt1); program_free(ctx->prog_alt2);
+    fixed_table_free(ctx->fix_h1); fixed_table_free(ctx->fix_h2); fixed_table_free(ctx->fix_v);
+    if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
+}
+
+// Public-key constants of the level-1 / level-2 shortcuts and the programs that need no secret.
+int setup_level2(pgpu_ctx* ctx) {
+    int rc;
+    ModCtx &M1 = ctx->m_n, &M2 = ctx->m_n2, &M3 = ctx->m_n3;
+    if ((rc = set_kconst(ctx, M2, K_NM, to_mont(M2, ctx->n)))) return rc;
+    if ((rc = set_kconst(ctx, M2, K_NSM, to_mont(M2, ctx->n)))) return rc;
+    if ((rc = set_kconst(ctx, M1, K_R4, (M1.R3 * M1.R1) % M1.N))) return rc;
+    {   // Randomize with the r supplied: c * r^n mod n^2 (operations.go:67-69 = Add(ct, EncryptWithR(0, r)))
+        Program& P = ctx->prog_rand;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_pow_shared(P, ctx->n, 0);
+        P.emit(OP_MULI, 1); P.n_mul++;               // (r^n * R) * c * R^-1
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    if (!M3.ready) return PGPU_OK;
+    BigU inv2;
+    if (!BigU::modinv(BigU(2), M3.N, inv2)) return fail(ctx, PGPU_ERR_ARG, "n must be odd");
+    if ((rc = set_kconst(ctx, M3, K_NEG1, to_mont(M3, M3.N - BigU(1))))) return rc;
+    if ((rc = set_kconst(ctx, M3, K_C1, to_mont(M3, (ctx->n2 * inv2) % M3.N)))) return rc;
+    if ((rc = set_kconst(ctx, M3, K_NM, to_mont(M3, ctx->n)))) return rc;
+    if ((rc = set_kconst(ctx, M3, K_NSM, to_mont(M3, ctx->n2)))) return rc;
+    {   // EncryptWithRAtLevel, level 2 (paillier.go:206-218): c = (1+n)^m * r^(n^2) mod n^3.  in0 = r, in1 = m
+        Program& P = ctx->prog_enc2;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_pow_shared(P, ctx->n2, 0);
+        const uint32_t RES = P.tbl_entries;
+        P.emit(OP_STT, RES); P.use_slot(RES);
+        P.emit(OP_LDI, 1);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_g_pow_level2(P, RES + 1);
+        P.emit(OP_MULT, RES); P.n_mul++;
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    ctx->level2_ready = true;
+    return PGPU_OK;
+}
+
+int encrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+    const ModCtx& M = ctx->m_n3;
+    const uint32_t wn = (uint32_t)ctx->wn;
+    IoDesc ins[2] = {{r, wn, wn}, {m, 2 * wn, 2 * wn}};
+    return run_vm(ctx, M, ctx->prog_enc2, count, ins, 2, c, M.sh.S, M.sh.S);
+}
+
+// Randomize (operations.go:67-69) with the r of the fresh encryption of zero supplied
+int randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* out) {
+    const ModCtx& M = ctx->m_n2;
+    const uint32_t wn = (uint32_t)ctx->wn, S = M.sh.S;
+    IoDesc ins[2] = {{r, wn, wn}, {c, S, S}};
+    return run_vm(ctx, M, ctx->prog_rand, count, ins, 2, out, S, S);
+}
+
+// Decrypt at level 2 (paillier.go:292-340): c^lambda mod n^3, recoveryAlgorithm(s = 2), times lambda^-1 mod n^2.
+// Secret constants for recover2_kernel; called from setup_crt once p, q are known.
+int setup_level2_secret(pgpu_ctx* ctx) {
+    if (!ctx->level2_ready) return PGPU_OK;
+    const size_t h = ctx->wn, H = 2 * h;
+    if (H > (size_t)CRT_MAXH) return PGPU_OK;      // level-2 decrypt unsupported at this width; reported on use
+    const BigU lambda = (ctx->p - BigU(1)) * (ctx->q - BigU(1));
+    const BigU RH = BigU::pow2(32 * H);
+    const BigU& N2 = ctx->n2;
+    BigU ninv, inv2, mu;
+    if (!BigU::modinv(ctx->n, RH, ninv) || !BigU::modinv(BigU(2), N2, inv2)) return fail(ctx, PGPU_ERR_ARG, "n must be odd");
+    if (!BigU::modinv(lambda % N2, N2, mu)) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "lambda is not invertible mod n^2");
+    const BigU R1 = RH % N2;
+    std::vector<uint32_t> K;
+    for (const BigU& x : {N2, ninv, (R1 * R1) % N2, (inv2 * R1) % N2, (mu * R1) % N2, (ctx->n * R1) % N2}) {
+        auto l = x.limbs(H); K.insert(K.end(), l.begin(), l.end());
+    }
+    if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
+    CU(ctx, cudaMalloc(&ctx->d_rec2, K.size() * 4));
+    return upload(ctx, ctx->d_rec2, K);
+}
+
+int decrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "Decrypt: no secret key loaded");
+    if (!ctx->level2_ready || !ctx->d_rec2) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level-2 Decrypt is not available at this key size");
+    const ModCtx& M = ctx->m_n3;
+    const uint32_t S = M.sh.S;
+    const BigU lambda = (ctx->p - BigU(1)) * (ctx->q - BigU(1));
+    DEVBUF(tmp, ctx, count * S);
+    int rc;
+    if ((rc = modexp_shared_dev(ctx, M, count, c, lambda, tmp.p))) return rc;          // :296
+    const uint32_t H = 2 * (uint32_t)ctx->wn;
+    Recover2Params R{(uint32_t)count, (int)ctx->wn, ctx->d_rec2, mont_np0(ctx->n2.v[0]), tmp.p, S, S, m, H};
+    CU(ctx, recover2_launch(R, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+// AltEncryptWithRAtLevel (paillier.go:221-238): c = (1+n)^m * h_s^(r mod K) mod n^(s+1), h_s a per-key
+// fixed base -> comb table, no squarings.  r: n-width records of which the low kbits bits are used (r mod K).
+int setup_alt(pgpu_ctx* ctx) {
+    int rc;
+    const BigU& H = ctx->alt_h;
+    {
+        ModCtx& M = ctx->m_n2;
+        const BigU h1 = BigU::modexp((ctx->n - (H % ctx->n)) % ctx->n, ctx->n, ctx->n2);     // :420-423 (H < n)
+        if ((rc = fixed_table_build(ctx, M, h1, ctx->alt_kbits, ctx->fix_h1))) return rc;
+        Program& P = ctx->prog_alt1;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_g_pow_level1(P);
+        P.emit(OP_STT, 0); P.use_slot(0);
+        emit_pow_fixed(P, ctx->fix_h1);
+        P.emit(OP_MULT, 0); P.n_mul++;
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    if (ctx->level2_ready) {
+        ModCtx& M = ctx->m_n3;
+        const BigU h2 = BigU::modexp(ctx->n2 - H, ctx->n2, ctx->n3);                         // :428-431
+        if ((rc = fixed_table_build(ctx, M, h2, ctx->alt_kbits, ctx->fix_h2))) return rc;
+        Program& P = ctx->prog_alt2;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_g_pow_level2(P, 1);
+        P.emit(OP_STT, 0); P.use_slot(0);
+        emit_pow_fixed(P, ctx->fix_h2);
+        P.emit(OP_MULT, 0); P.n_mul++;
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    ctx->has_alt = true;
+    return PGPU_OK;
+}
+
+int alt_encrypt_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    if (!ctx->has_alt) return fail(ctx, PGPU_ERR_STATE, "AltEncrypt: H and K were not loaded (pgpu_ctx_set_alt_generator)");
+    const uint32_t wn = (uint32_t)ctx->wn;
+    if (level == 1) {
+        const ModCtx& M = ctx->m_n2;
+        IoDesc ins[1] = {{m, wn, wn}};
+        return run_vm(ctx, M, ctx->prog_alt1, count, ins, 1, c, M.sh.S, M.sh.S, ExpDesc{r, wn, ctx->alt_kbits, ctx->fix_h1.d});
+    }
+    if (level == 2) {
+        if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+        const ModCtx& M = ctx->m_n3;
+        IoDesc ins[1] = {{m, 2 * wn, 2 * wn}};
+        return run_vm(ctx, M, ctx->prog_alt2, count, ins, 1, c, M.sh.S, M.sh.S, ExpDesc{r, wn, ctx->alt_kbits, ctx->fix_h2.d});
+    }
+    return fail(ctx, PGPU_ERR_ARG, "encryption level must be 1 or 2");
+}
+
+// ExtractRandonness (operations.go:75-91): z = (g^v)^-1 * c mod n^(s+1) with v = Decrypt(c), then
+// z^((n^s)^-1 mod lambda) mod n.  (g^v)^-1 = g^(n^s - v) because g = 1+n has order n^s mod n^(s+1).
+int extract_randomness_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_t* c, uint32_t* out) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "ExtractRandonness: no secret key loaded");
+    if (level != 1 && level != 2) return fail(ctx, PGPU_ERR_ARG, "encryption level must be 1 or 2");
+    if (level == 2 && !ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+    const ModCtx& M = level == 1 ? ctx->m_n2 : ctx->m_n3;
+    const ModCtx& MN = ctx->m_n;
+    const uint32_t S = M.sh.S, Sn = MN.sh.S, wn = (uint32_t)ctx->wn, wv = level == 1 ? wn : 2 * wn;
+    const BigU lambda = (ctx->p - BigU(1)) * (ctx->q - BigU(1));
+    const BigU& ns = level == 1 ? ctx->n : ctx->n2;
+    BigU ns_inv;
+    if (!BigU::modinv(ns % lambda, lambda, ns_inv)) return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "n^s is not invertible mod lambda");   // :79
+    int rc;
+    DEVBUF(v, ctx, count * wv); DEVBUF(z, ctx, count * S);
+    if ((rc = level == 1 ? decrypt_dev(ctx, count, c, v.p) : decrypt2_dev(ctx, count, c, v.p))) return rc;     // :81
+    {   // z = g^(n^s - v) * c mod n^(s+1)   (:82-86)
+        const std::string key = "xr-z:" + std::to_string(level);
+        Program* P = cached_program(ctx, key);
+        if (!P) {
+            Program np;
+            np.emit(OP_LDI, 0);
+            np.emit(OP_MULC, K_R2); np.n_mul++;
+            np.emit(OP_STT, 0); np.use_slot(0);
+            np.emit(OP_LDC, K_NSM);
+            np.emit(OP_SUBT, 0);                     // n^s - v
+            if (level == 1) emit_g_pow_level1(np); else emit_g_pow_level2(np, 1);
+            np.emit(OP_MULI, 1); np.n_mul++;         // * c, leaves Montgomery form
+            np.emit(OP_STO, 0);
+            if ((rc = program_upload(ctx, np))) return rc;
+            P = &(ctx->prog_cache[key] = np);
+        }
+        IoDesc ins[2] = {{v.p, wv, wv}, {c, S, S}};
+        if ((rc = run_vm(ctx, M, *P, count, ins, 2, z.p, S, S))) return rc;
+    }
+    {   // (z mod n)^(ns_inv) mod n   (:88); z = sum chunk_k * 2^(32*Sn*k)
+        const uint32_t chunks = (S + Sn - 1) / Sn;
+        if (chunks > 3) return fail(ctx, PGPU_ERR_UNSUPPORTED, "ExtractRandonness: ciphertext record too wide for the n-sized kernel");
+        const std::string key = "xr-p:" + std::to_string(level) + ":" + ns_inv.hex();
+        Program* P = cached_program(ctx, key);
+        if (!P) {
+            Program np;
+            static const uint32_t kslot[3] = {K_R2, K_R3, K_R4};
+            for (uint32_t k = 0; k < chunks; ++k) {
+                np.emit(OP_LDI, k);
+                np.emit(OP_MULC, kslot[k]); np.n_mul++;       // chunk_k * R^k, Montgomery form
+                if (k) np.emit(OP_ADDT, 0);
+                if (k + 1 < chunks) { np.emit(OP_STT, 0); np.use_slot(0); }
+            }
+            emit_pow_shared(np, ns_inv, 0);
+            np.emit(OP_MULC, K_ONE); np.n_mul++;
+            np.emit(OP_STO, 0);
+            if ((rc = program_upload(ctx, np))) return rc;
+            P = &(ctx->prog_cache[key] = np);
+        }
+        IoDesc ins[3];
+        for (uint32_t k = 0; k < chunks; ++k) ins[k] = IoDesc{z.p + k * Sn, S, std::min(Sn, S - k * Sn)};
+        if ((rc = run_vm(ctx, MN, *P, count, ins, (int)chunks, out, wn, wn))) return rc;
+    }
+    return PGPU_OK;
+}
+
+// NestedRandomize (operations.go:96-118) with a, b supplied: ct^(a^n mod n^2) * b^(n^2) mod n^3
+int nested_randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* ct, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+    const ModCtx &M2 = ctx->m_n2, &M3 = ctx->m_n3;
+    const uint32_t S2 = M2.sh.S, S3 = M3.sh.S, wn = (uint32_t)ctx->wn, e2bits = (uint32_t)ctx->n2.bitlen();
+    DEVBUF(an, ctx, count * S2); DEVBUF(bn2, ctx, count * S3); DEVBUF(t, ctx, count * S3);
+    int rc;
+    if ((rc = modexp_shared_io(ctx, M2, count, IoDesc{a, wn, wn}, ctx->n, an.p))) return rc;          // :108
+    if ((rc = modexp_shared_io(ctx, M3, count, IoDesc{b, wn, wn}, ctx->n2, bn2.p))) return rc;        // :109
+    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{ct, S3, S3}, ExpDesc{an.p, S2, e2bits, nullptr}, t.p))) return rc;   // :112
+    return modmul_dev(ctx, M3, count, t.p, bn2.p, out);                                               // :113-114
+}
+
+// digest of RandomOracleBit(ct1, ct2, x, y, alpha): ct1 is skipped (random_oracle.go:24-26)
+static int ddleq_hash(pgpu_ctx* ctx, size_t total, uint32_t secpar, const uint32_t* ct2, const uint32_t* x, const uint32_t* y,
+                      const uint32_t* alpha, uint32_t* digest) {
+    const uint32_t S3 = ctx->m_n3.sh.S, wn = (uint32_t)ctx->wn;
+    const uint32_t* seg[4] = {ct2, x, y, alpha};
+    const uint32_t stride[4] = {S3, wn, wn, S3};
+    const int limbs[4] = {(int)S3, (int)wn, (int)wn, (int)S3};
+    const uint32_t div[4] = {secpar, 1, 1, 1};
+    return sha_dev(ctx, total, 4, seg, stride, limbs, digest, div);
+}
+
+// ProveDDLEQ (ddleq.go:27-127) for `count` statements (ct1, ct2, a, b) with secpar instances each; the
+// x, y in Z*_n of every instance are supplied (ddleq.go:71-79 draws them).  The values that do not
+// depend on the instance (sanity check :62-69, ExtractRandonness :103, a^n :104, a^-1 :96) are computed
+// once per statement.  *d_bad = first statement whose sanity check fails, else 0xffffffff.
+int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t* ct1, const uint32_t* ct2, const uint32_t* a, const uint32_t* b,
+                    const uint32_t* x, const uint32_t* y, uint32_t* alpha, uint32_t* e, uint32_t* f, uint32_t* d_bad) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "ProveDDLEQ: no secret key loaded");
+    if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+    if (secpar == 0) return fail(ctx, PGPU_ERR_ARG, "ProveDDLEQ: secpar must be positive");
+    const ModCtx &M2 = ctx->m_n2, &M3 = ctx->m_n3;
+    const uint32_t S2 = M2.sh.S, S3 = M3.sh.S, wn = (uint32_t)ctx->wn, e2bits = (uint32_t)ctx->n2.bitlen();
+    const size_t total = count * secpar;
+    int rc;
+    // ---- per statement
+    DEVBUF(an, ctx, count * S2); DEVBUF(bn2, ctx, count * S3); DEVBUF(t3, ctx, count * S3); DEVBUF(san, ctx, count * S3);
+    DEVBUF(s, ctx, count * wn); DEVBUF(c0, ctx, count * S3); DEVBUF(ainv, ctx, count * S2); DEVBUF(a2, ctx, count * S2);
+    DEVBUF(flags, ctx, (count + 3) / 4 + 1);
+    if ((rc = modexp_shared_io(ctx, M2, count, IoDesc{a, wn, wn}, ctx->n, an.p))) return rc;                                 // a^n        :63,104
+    if ((rc = modexp_shared_io(ctx, M3, count, IoDesc{b, wn, wn}, ctx->n2, bn2.p))) return rc;                               // b^(n^2)    :64
+    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{ct1, S3, S3}, ExpDesc{an.p, S2, e2bits, nullptr}, t3.p))) return rc;  // ct1^(a^n)  :63
+    if ((rc = modmul_dev(ctx, M3, count, t3.p, bn2.p, san.p))) return rc;                                                    // :64-65
+    CU(ctx, equal_launch(san.p, ct2, S3, (uint32_t)count, (uint8_t*)flags.p, ctx->stream));                                  // :67
+    ctx->launches++;
+    CU(ctx, first_zero_launch((const uint8_t*)flags.p, (uint32_t)count, d_bad, ctx->stream));
+    ctx->launches++;
+    if ((rc = extract_randomness_dev(ctx, 2, count, ct1, s.p))) return rc;                                                   // s          :103
+    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{s.p, wn, wn}, ExpDesc{an.p, S2, e2bits, nullptr}, t3.p))) return rc;  // s^(a^n)    :107
+    if ((rc = modmul_io(ctx, M3, count, IoDesc{t3.p, S3, S3}, IoDesc{b, wn, wn}, c0.p))) return rc;                          // * b        :108
+    CU(ctx, resize_launch(a, wn, wn, a2.p, S2, (uint32_t)count, ctx->stream));
+    ctx->launches++;
+    DEVBUF(badinv, ctx, 1);
+    if ((rc = modinv_dev(ctx, M2, count, a2.p, ainv.p, badinv.p))) return rc;                                                // a^-1 mod n^2 :96
+    // ---- per instance
+    DEVBUF(xn, ctx, total * S2); DEVBUF(yn2, ctx, total * S3); DEVBUF(u3, ctx, total * S3); DEVBUF(dig, ctx, total * 8);
+    DEVBUF(e1, ctx, total * S2); DEVBUF(en, ctx, total * S2); DEVBUF(v3, ctx, total * S3); DEVBUF(f1, ctx, total * S3);
+    if ((rc = modexp_shared_io(ctx, M2, total, IoDesc{x, wn, wn}, ctx->n, xn.p))) return rc;                                 // x^n        :81
+    if ((rc = modexp_shared_io(ctx, M3, total, IoDesc{y, wn, wn}, ctx->n2, yn2.p))) return rc;                               // y^(n^2)    :82
+    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{ct1, S3, S3, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // ct1^xn :85
+    if ((rc = modmul_dev(ctx, M3, total, u3.p, yn2.p, alpha))) return rc;                                                    // alpha      :86-87
+    if ((rc = ddleq_hash(ctx, total, secpar, ct2, x, y, alpha, dig.p))) return rc;                                           // challenge  :91
+    if ((rc = modmul_io(ctx, M2, total, IoDesc{x, wn, wn}, IoDesc{ainv.p, S2, S2, secpar}, e1.p))) return rc;                // e = x*a^-1 mod n^2 :94-99
+    if ((rc = modexp_shared_dev(ctx, M2, total, e1.p, ctx->n, en.p))) return rc;                                             // e^n        :105
+    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{c0.p, S3, S3, secpar}, ExpDesc{en.p, S2, e2bits, nullptr}, u3.p))) return rc;  // (s^an*b)^en :109
+    if ((rc = modinv_dev(ctx, M3, total, u3.p, v3.p, badinv.p))) return rc;                                                  // ^-1        :110
+    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{s.p, wn, wn, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // s^xn  :112
+    if ((rc = modmul_dev(ctx, M3, total, v3.p, u3.p, v3.p))) return rc;                                                      // c          :112
+    if ((rc = modmul_io(ctx, M3, total, IoDesc{y, wn, wn}, IoDesc{v3.p, S3, S3}, f1.p))) return rc;                          // f = y*c    :113-114
+    // challenge bit selects (e, f) = (x*a^-1, y*c) or (x, y)
+    DEVBUF(xw, ctx, total * S2); DEVBUF(yw, ctx, total * S3);
+    CU(ctx, resize_launch(x, wn, wn, xw.p, S2, (uint32_t)total, ctx->stream));
+    CU(ctx, resize_launch(y, wn, wn, yw.p, S3, (uint32_t)total, ctx->stream));
+    CU(ctx, select_launch(dig.p, e1.p, 1, xw.p, 1, S2, (uint32_t)total, e, ctx->stream));
+    CU(ctx, select_launch(dig.p, f1.p, 1, yw.p, 1, S3, (uint32_t)total, f, ctx->stream));
+    ctx->launches += 4;
+    return PGPU_OK;
+}
+
+// VerifyDDLEQProof (ddleq.go:44-53,129-153): ok[i] for every instance
+int ddleq_verify_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t* ct1, const uint32_t* ct2, const uint32_t* x, const uint32_t* y,
+                     const uint32_t* alpha, const uint32_t* e, const uint32_t* f, uint8_t* ok) {
+    if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
+    if (secpar == 0) return fail(ctx, PGPU_ERR_ARG, "VerifyDDLEQProof: secpar must be positive");
+    const ModCtx &M2 = ctx->m_n2, &M3 = ctx->m_n3;
+    const uint32_t S2 = M2.sh.S, S3 = M3.sh.S, e2bits = (uint32_t)ctx->n2.bitlen();
+    const size_t total = count * secpar;
+    int rc;
+    DEVBUF(dig, ctx, total * 8); DEVBUF(chk, ctx, total * S3); DEVBUF(en, ctx, total * S2); DEVBUF(fn2, ctx, total * S3); DEVBUF(t, ctx, total * S3);
+    if ((rc = ddleq_hash(ctx, total, secpar, ct2, x, y, alpha, dig.p))) return rc;                                           // :138
+    CU(ctx, select_launch(dig.p, ct2, secpar, ct1, secpar, S3, (uint32_t)total, chk.p, ctx->stream));                        // :140-143
+    ctx->launches++;
+    if ((rc = modexp_shared_dev(ctx, M2, total, e, ctx->n, en.p))) return rc;                                                // E^n        :145
+    if ((rc = modexp_shared_dev(ctx, M3, total, f, ctx->n2, fn2.p))) return rc;                                              // F^(n^2)    :146
+    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{chk.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, t.p))) return rc;  // check^en   :148
+    if ((rc = modmul_dev(ctx, M3, total, t.p, fn2.p, t.p))) return rc;                                                       // :149-150
+    CU(ctx, equal_launch(alpha, t.p, S3, (uint32_t)total, ok, ctx->stream));                                                 // :152
+    ctx->launches++;
+    return PGPU_OK;
+}
+
+}  // namespace pgpu

@@ -28,6 +28,8 @@ enum VmOp : uint32_t {
     OP_ADDC = 11,  // x = (x + kconst[arg]) mod n
     OP_WIN  = 12,  // x = x^(2^w) * T[tbase + bits(exp[item], pos, w)], arg = pos | w<<20 | tbase<<24
     OP_SQMT = 13,  // x = x^(2^nsq) * T[idx], arg = nsq | idx<<12  (sliding-window step)
+    OP_FIXW = 14,  // x = x * F[(pos/w)*2^w + bits(exp[item], pos, w)], arg = pos | w<<20  (fixed-base comb step, no squarings)
+    OP_SUBT = 15,  // x = (x - T[arg]) mod n
 };
 
 constexpr uint32_t vm_op(uint32_t code, uint32_t arg) { return (code << 28) | (arg & 0x0fffffffu); }
@@ -35,7 +37,7 @@ constexpr uint32_t vm_op(uint32_t code, uint32_t arg) { return (code << 28) | (a
 constexpr int VM_MAX_IN = 4;
 constexpr int VM_MAX_OUT = 2;
 
-// Addresses are in 32-bit limbs.  Item i reads in[k] + i*in_stride[k] and
+// Addresses are in 32-bit limbs.  Item i reads in[k] + (i/in_div[k])*in_stride[k] and
 // writes out[k] + i*out_stride[k].
 struct VmParams {
     const uint32_t* prog;
@@ -46,11 +48,14 @@ struct VmParams {
     const uint32_t* in[VM_MAX_IN];
     uint32_t in_stride[VM_MAX_IN];
     uint32_t in_limbs[VM_MAX_IN];      // limbs actually present per record (<= S, rest reads as 0)
+    uint32_t in_div[VM_MAX_IN];        // item i reads record i / in_div (a statement value shared by its proof instances)
     uint32_t* out[VM_MAX_OUT];
     uint32_t out_stride[VM_MAX_OUT];
     uint32_t out_limbs[VM_MAX_OUT];    // limbs stored per record (<= S)
-    const uint32_t* exp;               // per-item exponents for OP_WIN
-    uint32_t exp_stride;
+    const uint32_t* exp;               // per-item exponents for OP_WIN / OP_FIXW
+    uint32_t exp_stride;               // limbs between exponent records
+    uint32_t exp_bits;                 // bits of an exponent record that count (higher bits read as 0)
+    const uint32_t* fixed;             // fixed-base table for OP_FIXW: records of S limbs, Montgomery form
     uint32_t* table;                   // scratch: [entry][group][S]
     uint32_t n_groups;                 // number of resident groups (table slots)
 };

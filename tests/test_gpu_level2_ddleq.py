@@ -1,0 +1,166 @@
+"""GPU parity for the level-2 (mod n^3) path, alternative encryption, randomness extraction, nested
+operations and the DDLEQ proofs against the Python oracle (oracle/paillier_ref.py), bit-exact.
+Mirrors paillier_test.go:65-138, operations_test.go:56-163 and ddleq_test.go:9-72 with fixed randomness."""
+import random
+
+import pytest
+
+from oracle import paillier_ref as R
+from paillier_b200 import synth
+from paillier_b200._lib import PgpuError, PGPU_ERR_ARG
+from paillier_b200.api import (ALTERNATIVE, Ciphertext, DDLEQProof, DDLEQProofInstance, ENC_LEVEL_ONE, ENC_LEVEL_TWO,
+                               SecretKey)
+
+pytestmark = pytest.mark.gpu
+
+
+def _units(rnd, n, k):
+    out = []
+    while len(out) < k:
+        r = rnd.randrange(1, n)
+        from math import gcd
+        if gcd(r, n) == 1:
+            out.append(r)
+    return out
+
+
+def _keys(name, seed=7):
+    p, q = synth.load_key(name)
+    rnd = random.Random(seed)
+    osk, opk = R.keygen_from_primes(p, q, h_seed_r=_units(rnd, p * q, 1)[0])
+    sk = SecretKey(p * q, p=p, q=q, H=opk.H, K=opk.K)
+    return sk, osk, opk, rnd
+
+
+@pytest.fixture(scope="module", params=["paillier_64", "paillier_1024", "paillier_2048"])
+def keys(request):
+    sk, osk, opk, rnd = _keys(request.param)
+    yield sk, osk, opk, rnd
+    sk.close()
+
+
+def test_level2_encrypt_decrypt(keys):
+    sk, osk, opk, rnd = keys
+    n, n2 = sk.N, sk.N ** 2
+    ms = [0, 1, n2 - 1, n, n - 1] + [rnd.randrange(n2) for _ in range(6)]
+    rs = [1, n - 1] + _units(rnd, n, len(ms) - 2)
+    cts = sk.EncryptWithRAtLevelBatch(ms, rs, ENC_LEVEL_TWO)
+    assert [c.C for c in cts] == [R.encrypt_with_r_at_level(opk, m, r, R.ENC_LEVEL_TWO).C for m, r in zip(ms, rs)]
+    assert sk.DecryptBatch(cts) == ms == [R.decrypt(osk, R.Ciphertext(c.C, R.ENC_LEVEL_TWO)) for c in cts]
+    # level 1 through the same entry point
+    ms1 = [m % n for m in ms]
+    cts1 = sk.EncryptWithRAtLevelBatch(ms1, rs, ENC_LEVEL_ONE)
+    assert [c.C for c in cts1] == [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms1, rs)]
+
+
+def test_nested_encrypt_decrypt(keys):
+    # paillier_test.go:65-76,110-138: [[m]] = Enc2(Enc1(m)); NestedDecrypt peels both layers; inner 0 -> 0
+    sk, osk, opk, rnd = keys
+    n = sk.N
+    ms = [5, 0, n - 1] + [rnd.randrange(n) for _ in range(3)]
+    inner = sk.EncryptWithRBatch(ms, _units(rnd, n, len(ms)))
+    outer = sk.EncryptWithRAtLevelBatch([c.C for c in inner] + [0], _units(rnd, n, len(ms) + 1), ENC_LEVEL_TWO)
+    layer = sk.DecryptNestedCiphertextLayerBatch(outer)
+    assert [c.C for c in layer] == [c.C for c in inner] + [0]
+    assert sk.NestedDecryptBatch(outer) == ms + [0]
+    assert sk.NestedDecryptBatch(outer) == [R.nested_decrypt(osk, R.Ciphertext(c.C, R.ENC_LEVEL_TWO)) for c in outer]
+    with pytest.raises(ValueError):
+        sk.DecryptNestedCiphertextLayerBatch(inner)
+
+
+def test_alt_encrypt(keys):
+    sk, osk, opk, rnd = keys
+    n, n2 = sk.N, sk.N ** 2
+    for level, space in ((ENC_LEVEL_ONE, n), (ENC_LEVEL_TWO, n2)):
+        ms = [0, 1, space - 1] + [rnd.randrange(space) for _ in range(5)]
+        rs = [0, 1, opk.K, opk.K - 1] + [rnd.randrange(n) for _ in range(4)]
+        mine = list(rs)
+        cts = sk.AltEncryptWithRAtLevelBatch(ms, mine, level)
+        ref = [R.alt_encrypt_with_r_at_level(opk, m, r, level) for m, r in zip(ms, rs)]
+        assert [c.C for c in cts] == [c.C for c, _ in ref]
+        assert mine == [r for _, r in ref]                      # r reduced mod K in place (paillier.go:228)
+        assert all(c.EncMethod == ALTERNATIVE for c in cts)
+        assert sk.DecryptBatch(cts) == ms
+
+
+def test_randomize_and_extract_randomness(keys):
+    # operations_test.go:130-163: ExtractRandonness returns the r of EncryptWithRAtLevel
+    sk, osk, opk, rnd = keys
+    n, n2 = sk.N, sk.N ** 2
+    ms = [0, 1, n - 1] + [rnd.randrange(n) for _ in range(4)]
+    rs = [1, 4, 9] + _units(rnd, n, 4)
+    cts = sk.EncryptWithRBatch(ms, rs)
+    assert sk.ExtractRandonnessBatch(cts) == rs == [R.extract_randomness(osk, R.Ciphertext(c.C)) for c in cts]
+    ms2 = [m * 3 % n2 for m in ms]
+    cts2 = sk.EncryptWithRAtLevelBatch(ms2, rs, ENC_LEVEL_TWO)
+    assert sk.ExtractRandonnessBatch(cts2) == rs == [R.extract_randomness(osk, R.Ciphertext(c.C, R.ENC_LEVEL_TWO)) for c in cts2]
+    r2 = _units(rnd, n, len(cts))
+    rz = sk.RandomizeWithRBatch(cts, r2)
+    assert [c.C for c in rz] == [R.add(opk, R.Ciphertext(c.C), R.encrypt_with_r(opk, 0, r)).C for c, r in zip(cts, r2)]
+    assert sk.DecryptBatch(rz) == ms
+    assert sk.ExtractRandonnessBatch(rz) == [a * b % n for a, b in zip(rs, r2)]
+
+
+def test_nested_operations(keys):
+    # operations_test.go:56-128
+    sk, osk, opk, rnd = keys
+    n = sk.N
+    ms = [rnd.randrange(n // 4) for _ in range(4)]
+    ks = [rnd.randrange(n // 4) for _ in range(4)]
+    inner = sk.EncryptWithRBatch(ms, _units(rnd, n, 4))
+    outer = sk.EncryptWithRAtLevelBatch([c.C for c in inner], _units(rnd, n, 4), ENC_LEVEL_TWO)
+    addend = sk.EncryptWithRBatch(ks, _units(rnd, n, 4))
+    o2 = lambda c: R.Ciphertext(c.C, R.ENC_LEVEL_TWO)
+    o1 = lambda c: R.Ciphertext(c.C, R.ENC_LEVEL_ONE)
+    added = sk.NestedAddBatch(outer, addend)
+    assert [c.C for c in added] == [R.nested_add(opk, o2(a), o1(b)).C for a, b in zip(outer, addend)]
+    assert sk.NestedDecryptBatch(added) == [(m + k) % n for m, k in zip(ms, ks)]
+    subbed = sk.NestedSubBatch(outer, addend)
+    assert [c.C for c in subbed] == [R.nested_sub(opk, o2(a), o1(b)).C for a, b in zip(outer, addend)]
+    assert sk.NestedDecryptBatch(subbed) == [(m - k) % n for m, k in zip(ms, ks)]
+    As, Bs = _units(rnd, n, 4), _units(rnd, n, 4)
+    rz = sk.NestedRandomizeWithBatch(outer, As, Bs)
+    assert [c.C for c in rz] == [R.nested_randomize_with(opk, o2(c), a, b).C for c, a, b in zip(outer, As, Bs)]
+    assert sk.NestedDecryptBatch(rz) == ms
+    with pytest.raises(ValueError):
+        sk.NestedRandomizeWithBatch(inner, As, Bs)
+    with pytest.raises(ValueError):
+        sk.NestedAddBatch(inner, addend)
+
+
+def test_ddleq_prove_verify(keys):
+    # ddleq_test.go:9-72 with the instance randomness fixed: transcripts bit-exact with the oracle
+    sk, osk, opk, rnd = keys
+    n = sk.N
+    big = n.bit_length() > 1500
+    count, secpar = (2, 4) if big else (3, 10)
+    ms = [rnd.randrange(n) for _ in range(count)]
+    inner = sk.EncryptWithRBatch(ms, _units(rnd, n, count))
+    ct1 = sk.EncryptWithRAtLevelBatch([c.C for c in inner], _units(rnd, n, count), ENC_LEVEL_TWO)
+    As, Bs = _units(rnd, n, count), _units(rnd, n, count)
+    ct2 = sk.NestedRandomizeWithBatch(ct1, As, Bs)
+    xs = [_units(rnd, n, secpar) for _ in range(count)]
+    ys = [_units(rnd, n, secpar) for _ in range(count)]
+    proofs = sk.ProveDDLEQBatch(secpar, ct1, ct2, As, Bs, xs, ys)
+    o2 = lambda c: R.Ciphertext(c.C, R.ENC_LEVEL_TWO)
+    chal = set()
+    for i in range(count if not big else 1):
+        ref = R.prove_ddleq(osk, secpar, o2(ct1[i]), o2(ct2[i]), As[i], Bs[i], xs[i], ys[i])
+        for g, o in zip(proofs[i].Instances, ref):
+            assert (g.X, g.Y, g.Alpha, g.E, g.F) == (o.X, o.Y, o.Alpha, o.E, o.F)
+            chal.add(o.E != o.X)
+        assert R.verify_ddleq(opk, o2(ct1[i]), o2(ct2[i]), ref)
+    if not big:
+        assert chal == {True, False}          # both challenge values exercised
+    assert sk.VerifyDDLEQProofBatch(ct1, ct2, proofs) == [True] * count
+    # soundness (ddleq_test.go:38-72): a proof for other ciphertexts / a tampered instance must be rejected
+    bad = [DDLEQProof(list(p.Instances)) for p in proofs]
+    i0 = bad[0].Instances[1]
+    bad[0].Instances[1] = DDLEQProofInstance(i0.X, i0.Y, i0.Alpha, i0.E, (i0.F + 1) % n ** 3)
+    assert sk.VerifyDDLEQProofBatch(ct1, ct2, bad) == [False] + [True] * (count - 1)
+    swapped = sk.VerifyDDLEQProofBatch(ct2, ct1, proofs)
+    assert swapped == [False] * count
+    # wrong (a, b): the reference panics (ddleq.go:67-69)
+    with pytest.raises(PgpuError) as ei:
+        sk.ProveDDLEQBatch(secpar, ct1, ct2, As[::-1], Bs, xs, ys)
+    assert ei.value.code == PGPU_ERR_ARG and "inputs are wrong" in str(ei.value)
