@@ -163,6 +163,21 @@ int pgpu_ddleq_prove(pgpu_ctx* ctx, size_t count, unsigned secpar, const void* c
 int pgpu_ddleq_verify(pgpu_ctx* ctx, size_t count, unsigned secpar, const void* ct1, const void* ct2, const void* x, const void* y,
                       const void* alpha, const void* e, const void* f, uint8_t* ok);
 
+/* ---- safe-prime candidate testing (safe_prime.go) ---------------------------- */
+/* One iteration of runGenPrimeRoutine's loop (safe_prime.go:170-263) for each of `count` byte strings
+ * as the reference reads them from its io.Reader: raw = records of ceil((p_bits-1)/8) bytes.  The
+ * masks (:175-202), the sieve mod 3*5*...*53 with the delta search (:208-249, including the cumulative
+ * q += delta), q.ProbablyPrime(20) (Miller-Rabin, bases 2..71), the base-2 Fermat test on p = 2q+1
+ * (:272-278) and the bit-length check (:256-258) run on `device`.  p, q: records of
+ * 4*S bytes, S = 32 / 48 / 64 limbs for p_bits <= 1024 / 1536 / 2048; ok[i] = 1 if candidate i is accepted.
+ * These two calls need no key context; errors are reported by pgpu_primes_last_error(). */
+int pgpu_safe_prime_scan(int device, unsigned p_bits, size_t count, const uint8_t* raw, void* p_out, void* q_out, uint8_t* ok,
+                         uint64_t* launches);
+/* big.Int.ProbablyPrime stand-in: `rounds` (1..20) Miller-Rabin strong tests, bases 2, 3, 5, ... on odd
+ * candidates that all have exactly `bits` bits (same record layout as above). */
+int pgpu_miller_rabin(int device, unsigned bits, size_t count, const void* cand, unsigned rounds, uint8_t* ok, uint64_t* launches);
+const char* pgpu_primes_last_error(void);
+
 /* Generic batched gmp.Int.Exp (mpz_powm) / Mul+Mod against one of the key's
  * moduli; records are the modulus' width.  exp: per-item unsigned records of
  * exp_bytes bytes.  These back ConstMult, the ZKP and DDLEQ entry points. */
@@ -182,6 +197,10 @@ int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t*
 
 int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z);
 int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
+/* as pgpu_combine_dev, but share j's batch starts at record j*share_stride of decs: combines a slice of the
+ * all-gathered [share][ciphertext] buffer in place (one share-holder per GPU) */
+int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, void* m);
+int pgpu_pdec_zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok);
 
 /* ---- introspection used by bench.py ------------------------------------ */
 /* number of kernels this context has launched so far */

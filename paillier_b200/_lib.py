@@ -74,6 +74,11 @@ SIGNATURES = {
     "pgpu_nested_sub": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_ddleq_prove": (C.c_int, [_p, _sz, C.c_uint, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pgpu_ddleq_verify": (C.c_int, [_p, _sz, C.c_uint, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pgpu_safe_prime_scan": (C.c_int, [C.c_int, C.c_uint, _sz, _p, _p, _p, _p, C.POINTER(C.c_uint64)]),
+    "pgpu_miller_rabin": (C.c_int, [C.c_int, C.c_uint, _sz, _p, C.c_uint, _p, C.POINTER(C.c_uint64)]),
+    "pgpu_primes_last_error": (C.c_char_p, []),
+    "pgpu_combine_strided_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _sz, _p]),
+    "pgpu_pdec_zkp_verify_dev": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),

@@ -699,6 +699,25 @@ int pgpu_ddleq_verify(pgpu_ctx* ctx, size_t count, unsigned secpar, const void* 
     GUARD_END(ctx)
 }
 
+int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, void* m) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids), "pgpu_combine_strided_dev: null argument");
+    REQUIRE(ctx, share_stride >= count, "pgpu_combine_strided_dev: share_stride must be at least count");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return combine_dev(ctx, count, k, ids, (const uint32_t*)decs, (uint32_t*)m, share_stride);
+    GUARD_END(ctx)
+}
+
+int pgpu_pdec_zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && dec && e && z && ok)), "pgpu_pdec_zkp_verify_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return zkp_verify_dev(ctx, count, id, (const uint32_t*)c, (const uint32_t*)dec, (const uint32_t*)e, (const uint32_t*)z, ok);
+    GUARD_END(ctx)
+}
+
 int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches) {
     if (!ctx || !launches) return fail(nullptr, PGPU_ERR_ARG, "null argument");
     *launches = ctx->launches;

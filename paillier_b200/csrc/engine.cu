@@ -553,7 +553,8 @@ int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const
 }
 
 // CombinePartialDecryptions (thresholdkey.go:149-161); decs = k batches of `count` n^2-width records, one per share
-int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out) {
+int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out, size_t share_stride) {
+    if (share_stride == 0) share_stride = count;
     if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "CombinePartialDecryptions: no threshold key loaded");
     if (k < ctx->tk_w) return fail(ctx, PGPU_ERR_THRESHOLD, "Threshold not meet");                               // :78-80
     for (int i = 0; i < k; ++i) for (int j = i + 1; j < k; ++j)
@@ -581,7 +582,7 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
             lam = euclid_div(num, (long)ids[i] - (long)ids[j]);              // Div(num, i - j) :93-94
         }
         const BigU e2 = lam.mag * BigU(2);                                   // updateCprime: exponent 2*lambda :119-124
-        if ((rc = modexp_shared_dev(ctx, M, count, decs + (size_t)i * count * S, e2, t.p))) return rc;
+        if ((rc = modexp_shared_dev(ctx, M, count, decs + (size_t)i * share_stride * S, e2, t.p))) return rc;
         uint32_t* acc = lam.neg ? neg.p : pos.p;
         bool& have = lam.neg ? have_neg : have_pos;
         if (!have) { CU(ctx, cudaMemcpyAsync(acc, t.p, count * S * 4, cudaMemcpyDeviceToDevice, ctx->stream)); have = true; }

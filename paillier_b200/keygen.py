@@ -68,3 +68,69 @@ class ThresholdKeyGenerator:
             pk.close()
         return [ThresholdSecretKey(n, l, self.Threshold, v, vks, ID=i + 1, Share=shares[i], device=device)
                 for i in range(l)]                                                 # :256-278
+
+
+# ---- safe_prime.go ---------------------------------------------------------------------------------------
+
+def _prime_shape(p_bits: int) -> int:
+    if p_bits <= 1024:
+        return 32
+    if p_bits <= 1536:
+        return 48
+    if p_bits <= 2048:
+        return 64
+    raise ValueError("safe primes of up to 2048 bits are supported")
+
+
+def safe_prime_scan(p_bit_len: int, raw: bytes, device: int = 0):
+    """The candidate procedure of runGenPrimeRoutine (safe_prime.go:170-263) on the GPU for every
+    ceil((p_bit_len-1)/8)-byte string of `raw`, in stream order.  Returns (ps, qs, accepted)."""
+    import ctypes as C
+    import numpy as np
+    from ._lib import lib, PGPU_OK, PgpuError
+    from .api import from_records
+    nb = (p_bit_len - 1 + 7) // 8
+    count = len(raw) // nb
+    S = _prime_shape(p_bit_len)
+    buf = np.frombuffer(raw[:count * nb], dtype=np.uint8).copy()
+    p = np.zeros(count * S * 4, dtype=np.uint8)
+    q = np.zeros(count * S * 4, dtype=np.uint8)
+    ok = np.zeros(count, dtype=np.uint8)
+    nl = C.c_uint64()
+    rc = lib.pgpu_safe_prime_scan(device, p_bit_len, count, buf.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                  q.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p), C.byref(nl))
+    if rc != PGPU_OK:
+        raise PgpuError(rc, (lib.pgpu_primes_last_error() or b"").decode())
+    return from_records(p, S * 4), from_records(q, S * 4), [bool(x) for x in ok]
+
+
+def miller_rabin(bits: int, candidates: Sequence[int], rounds: int = 20, device: int = 0) -> List[bool]:
+    """big.Int.ProbablyPrime stand-in on the GPU: `rounds` strong tests (bases 2, 3, 5, ...)"""
+    import ctypes as C
+    import numpy as np
+    from ._lib import lib, PGPU_OK, PgpuError
+    from .api import to_records
+    S = _prime_shape(bits)
+    rec = to_records(candidates, S * 4)
+    ok = np.zeros(len(candidates), dtype=np.uint8)
+    rc = lib.pgpu_miller_rabin(device, bits, len(candidates), rec.ctypes.data_as(C.c_void_p), rounds,
+                               ok.ctypes.data_as(C.c_void_p), None)
+    if rc != PGPU_OK:
+        raise PgpuError(rc, (lib.pgpu_primes_last_error() or b"").decode())
+    return [bool(x) for x in ok]
+
+
+def GenerateSafePrime(bitLen: int, random_reader, batch: int = 1 << 14, max_batches: int = 64, device: int = 0):
+    """safe_prime.go:61-105 with the candidate loop on the GPU: reads `batch` candidates at a time from
+    `random_reader(nbytes) -> bytes` and returns (p, q) of the first accepted candidate in stream order.
+    The reference's goroutine race (first finisher wins) and its wall-clock timeout become a bound on
+    the number of batches."""
+    if bitLen < 6:
+        raise ValueError("safe prime size must be at least 6 bits")               # :67-69
+    nb = (bitLen - 1 + 7) // 8
+    for _ in range(max_batches):
+        ps, qs, ok = safe_prime_scan(bitLen, random_reader(batch * nb), device)
+        for p, q, good in zip(ps, qs, ok):
+            if good:
+                return p, q
+    raise TimeoutError(f"generator gave up after {max_batches} batches of {batch} candidates")   # :101-103

@@ -1,0 +1,136 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), SURVEY.md 8(e).
+
+* Encrypt / Decrypt / ConstMult / proofs / safe-prime candidates are independent items: `shard_range`
+  gives rank r its contiguous slice of a batch; there is NO collective on that path.
+* Add over a sharded batch: every rank reduces its slice to one ciphertext, the `world` partial products
+  are gathered and multiplied (modular multiplication is associative and commutative and the result is a
+  canonical residue, so the tree order is bit-identical to the reference's left fold, operations.go:11-29).
+* Threshold decryption with one share-holder per GPU (BASELINE config 4): rank r holds share r+1, computes
+  the partial decryptions of ALL ciphertexts, one all-gather moves them ([share][ciphertext] layout), then
+  rank r combines ciphertext slice r (thresholdkey.go:149-161) straight out of the gathered buffer.
+
+The compute steps are injected as callables so that the plumbing can be exercised with the gloo backend on
+CPU tensors in tests (tests/test_multi_gloo.py); `gpu_threshold_round` binds them to the CUDA engine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+
+def shard_range(count: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of a batch of `count` items for `rank`; the first count % world ranks get one more."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank")
+    base, extra = divmod(count, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def threshold_round(dist, rank: int, world: int, count: int, record_width: int,
+                    partial_decrypt: Callable[[], "torch.Tensor"],
+                    combine: Callable[["torch.Tensor", Sequence[int], int, int], "torch.Tensor"],
+                    verify: Optional[Callable[["torch.Tensor", int], bool]] = None):
+    """One threshold-decryption round.
+
+    partial_decrypt() -> uint8 tensor [count * record_width]: this rank's share applied to every ciphertext.
+    combine(gathered, ids, lo, hi) -> plaintext records of ciphertexts [lo, hi) from the gathered
+        [world][count][record_width] buffer using the shares `ids` (server ids, rank r holds id r+1).
+    verify(gathered, r) (optional) -> whether rank r's partials are to be used (CombinePartialDecryptionsZKP,
+        thresholdkey.go:164-172 drops shares whose proof fails).
+    Returns (plaintext slice tensor, (lo, hi))."""
+    import torch
+    mine = partial_decrypt()
+    if mine.numel() != count * record_width:
+        raise ValueError("partial_decrypt returned a buffer of the wrong size")
+    gathered = torch.empty(world * count * record_width, dtype=torch.uint8, device=mine.device)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, mine.contiguous())
+    else:
+        gathered.copy_(mine)
+    ids = [r + 1 for r in range(world) if verify is None or verify(gathered, r)]
+    lo, hi = shard_range(count, world, rank)
+    return combine(gathered, ids, lo, hi), (lo, hi)
+
+
+def sharded_add(dist, rank: int, world: int, record_width: int, local_product: "torch.Tensor",
+                multiply_all: Callable[["torch.Tensor"], "torch.Tensor"]):
+    """Add over a batch sharded across ranks: gather the `world` per-rank products (one record each) and fold them."""
+    import torch
+    parts = torch.empty(world * record_width, dtype=torch.uint8, device=local_product.device)
+    if world > 1:
+        dist.all_gather_into_tensor(parts, local_product.contiguous())
+    else:
+        parts.copy_(local_product)
+    return multiply_all(parts)
+
+
+def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, with_zkp_r=None):
+    """BASELINE config 4 on the CUDA engine: tsk = this rank's ThresholdSecretKey (share id rank+1),
+    c_dev = device tensor of `count` n2-width ciphertext records (the same on every rank).
+    with_zkp_r: optional device tensor of count n2-width r values -> proofs are produced, all-gathered and
+    verified on the combining rank before its slice is combined."""
+    import torch
+    from ._lib import check, lib
+    w2, wn = tsk.w_n2, tsk.w_n
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    proofs = {}
+    # the engine enqueues on a torch-owned side stream so that NCCL (which orders against torch's current
+    # stream) sees its results; stream 0 would mean "the context's private stream" to pgpu_ctx_set_stream
+    stream = torch.cuda.Stream(c_dev.device)
+    stream.wait_stream(torch.cuda.current_stream(c_dev.device))
+    check(lib.pgpu_ctx_set_stream(tsk._ctx, C.c_void_p(stream.cuda_stream)), tsk._ctx)
+
+    def partial_decrypt():
+        out = torch.empty(count * w2, dtype=torch.uint8, device=c_dev.device)
+        if with_zkp_r is None:
+            check(lib.pgpu_partial_decrypt_dev(tsk._ctx, count, vp(c_dev), vp(out)), tsk._ctx)
+        else:
+            e = torch.empty(count * 32, dtype=torch.uint8, device=c_dev.device)
+            z = torch.empty(count * tsk.w_z, dtype=torch.uint8, device=c_dev.device)
+            check(lib.pgpu_pdec_zkp_prove_dev(tsk._ctx, count, vp(c_dev), vp(with_zkp_r), vp(out), vp(e), vp(z)), tsk._ctx)
+            ge = torch.empty(world * e.numel(), dtype=torch.uint8, device=c_dev.device)
+            gz = torch.empty(world * z.numel(), dtype=torch.uint8, device=c_dev.device)
+            if world > 1:
+                stream.synchronize()
+                dist.all_gather_into_tensor(ge, e)
+                dist.all_gather_into_tensor(gz, z)
+            else:
+                ge.copy_(e); gz.copy_(z)
+            proofs["e"], proofs["z"] = ge, gz
+        stream.synchronize()
+        return out
+
+    lo, hi = shard_range(count, world, rank)
+
+    def verify(gathered, r):
+        if with_zkp_r is None:
+            return True
+        n = hi - lo
+        ok = torch.zeros(max(n, 1), dtype=torch.uint8, device=c_dev.device)
+        dec = gathered[(r * count + lo) * w2:(r * count + hi) * w2]
+        e = proofs["e"][(r * count + lo) * 32:(r * count + hi) * 32]
+        z = proofs["z"][(r * count + lo) * tsk.w_z:(r * count + hi) * tsk.w_z]
+        check(lib.pgpu_pdec_zkp_verify_dev(tsk._ctx, n, r + 1, vp(c_dev[lo * w2:hi * w2]), vp(dec), vp(e), vp(z), vp(ok)), tsk._ctx)
+        stream.synchronize()
+        return bool(ok[:n].all().item()) if n else True
+
+    def combine(gathered, ids, lo, hi):
+        n = hi - lo
+        out = torch.empty(max(n, 1) * wn, dtype=torch.uint8, device=c_dev.device)
+        # shares are rows of the gathered buffer: pick the rows of `ids`; a full set is used in place
+        if ids == list(range(1, world + 1)):
+            base, stride = gathered[lo * w2:], count
+        else:
+            rows = [gathered[((i - 1) * count + lo) * w2:((i - 1) * count + hi) * w2] for i in ids]
+            base, stride = torch.cat(rows) if rows else gathered[:0], n
+        idarr = (C.c_int * max(len(ids), 1))(*ids)
+        check(lib.pgpu_combine_strided_dev(tsk._ctx, n, len(ids), idarr, vp(base), max(stride, n), vp(out)), tsk._ctx)
+        stream.synchronize()
+        return out[:n * wn]
+
+    with torch.cuda.stream(stream):
+        res = threshold_round(dist, rank, world, count, w2, partial_decrypt, combine, verify if with_zkp_r is not None else None)
+    stream.synchronize()
+    check(lib.pgpu_ctx_set_stream(tsk._ctx, None), tsk._ctx)
+    return res
