@@ -134,6 +134,8 @@ int pgpu_ctx_set_threshold(pgpu_ctx* ctx, int total_servers, int threshold, int 
     ctx->tk_l = total_servers; ctx->tk_w = threshold; ctx->tk_id = id;
     ctx->tk_delta = BigU::factorial((unsigned)total_servers);
     ctx->tk_v = v_be ? BigU::from_be(v_be, v_len) : BigU();
+    cudaStreamSynchronize(ctx->stream);
+    fixed_table_free(ctx->fix_v);
     ctx->tk_vi.clear();
     if (vkeys_n2w) {
         const uint32_t* p = (const uint32_t*)vkeys_n2w;
@@ -367,7 +369,7 @@ int pgpu_modinv(pgpu_ctx* ctx, int modsel, size_t count, const void* a, void* ou
     uint32_t* dout = io.out(1, count * w);
     uint32_t* dbad = io.out(2, 4);
     if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = modinv_dev(ctx, *M, count, da, dout, dbad))) return rc; }
+    { TimedScope ts(ctx); if ((rc = modinv_batch_dev(ctx, *M, count, da, dout, dbad))) return rc; }
     uint32_t bad = 0;
     if ((rc = io.finish(&bad, dbad, 4))) return rc;
     if ((rc = io.finish(out, dout, count * w))) return rc;
@@ -391,7 +393,7 @@ int pgpu_sub_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, vo
     if (io.rc) return io.rc;
     {
         TimedScope ts(ctx);
-        if ((rc = modinv_dev(ctx, M, count, db, dout, dbad))) return rc;          // neg := ModInverse(c.C, ns1)  operations.go:43
+        if ((rc = modinv_batch_dev(ctx, M, count, db, dout, dbad))) return rc;          // neg := ModInverse(c.C, ns1)  operations.go:43
         if ((rc = modmul_dev(ctx, M, count, da, dout, dout))) return rc;          // Mod(Mul(accumulator, neg))   :44-47
     }
     uint32_t bad = 0;
@@ -617,7 +619,7 @@ static int nested_addsub(pgpu_ctx* ctx, bool sub, size_t count, const void* ct1,
     const uint32_t* e = d2;
     {
         TimedScope ts(ctx);
-        if (sub) { if ((rc = modinv_dev(ctx, ctx->m_n2, count, d2, dinv, dbad))) return rc; e = dinv; }        // operations.go:137
+        if (sub) { if ((rc = modinv_batch_dev(ctx, ctx->m_n2, count, d2, dinv, dbad))) return rc; e = dinv; }        // operations.go:137
         if ((rc = modexp_items_io(ctx, ctx->m_n3, count, IoDesc{d1, S3, S3}, ExpDesc{e, S2, (uint32_t)ctx->n2.bitlen(), nullptr}, dout))) return rc;   // ConstMult :126,139
     }
     uint32_t bad = 0xffffffffu;

@@ -162,7 +162,7 @@ int ensure_table(pgpu_ctx* ctx, size_t limbs) {
 
 int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
-           const ExpDesc& ex) {
+           const ExpDesc& ex, uint32_t* out2, uint32_t out2_stride) {
     if (count == 0) return PGPU_OK;
     if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
     const int gpb = VM_BLOCK_THREADS / m.sh.tpi;
@@ -176,6 +176,7 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     for (int i = 0; i < VM_MAX_IN; ++i) P.in_div[i] = 1;
     for (int i = 0; i < n_in; ++i) { P.in[i] = ins[i].ptr; P.in_stride[i] = ins[i].stride; P.in_limbs[i] = ins[i].limbs; P.in_div[i] = std::max<uint32_t>(ins[i].div, 1); }
     P.out[0] = out; P.out_stride[0] = out_stride; P.out_limbs[0] = out_limbs;
+    P.out[1] = out2; P.out_stride[1] = out2_stride; P.out_limbs[1] = m.sh.S;
     P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed;
     P.n_groups = (uint32_t)blocks * gpb;
     int rc = ensure_table(ctx, (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S);
@@ -468,6 +469,75 @@ int modinv_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in,
     return PGPU_OK;
 }
 
+// Montgomery's batch inversion: chunks of K items share one extended-Euclid inversion (5 multiplications per item
+// instead of one xgcd).  Any non-unit makes its chunk's product a non-unit: the caller then falls back to modinv_dev,
+// which names the first offending item.  *all_ok (host) = every chunk product was invertible.
+static int batch_inverse_chunks(pgpu_ctx* ctx, const ModCtx& M, size_t chunks, uint32_t K, const uint32_t* in, uint32_t* out,
+                                uint32_t* prefix, uint32_t* totals, uint32_t* tinv, uint32_t* d_bad) {
+    const uint32_t S = M.sh.S;
+    const std::string kf = "binv-f:" + std::to_string(S) + ":" + std::to_string(K), kb = "binv-b:" + std::to_string(S) + ":" + std::to_string(K);
+    Program* F = cached_program(ctx, kf);
+    int rc;
+    if (!F) {
+        Program np;
+        for (uint32_t k = 0; k < K; ++k) {
+            np.emit(OP_LDIO, 0 | (k << 2));
+            np.emit(OP_MULC, K_R2); np.n_mul++;                       // x_k * R
+            if (k) { np.emit(OP_MULT, 0); np.n_mul++; }              // * prefix_{k-1}
+            np.emit(OP_STT, 0); np.use_slot(0);
+            np.emit(OP_STOO, 1 | (k << 2));                           // prefix_k (Montgomery form) -> out[1]
+        }
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);                                           // chunk product, plain
+        if ((rc = program_upload(ctx, np))) return rc;
+        F = &(ctx->prog_cache[kf] = np);
+    }
+    Program* B = cached_program(ctx, kb);
+    if (!B) {
+        Program np;
+        np.emit(OP_LDI, 2);                                           // I = (x_0 ... x_{K-1})^-1, plain
+        np.emit(OP_STT, 0); np.use_slot(0);
+        for (uint32_t k = K - 1; k >= 1; --k) {
+            np.emit(OP_MULIO, 1 | ((k - 1) << 2)); np.n_mul++;        // I * prefix_{k-1} * R * R^-1 = x_k^-1
+            np.emit(OP_STOO, 0 | (k << 2));
+            np.emit(OP_LDIO, 0 | (k << 2));
+            np.emit(OP_MULC, K_R2); np.n_mul++;                       // x_k * R
+            np.emit(OP_MULT, 0); np.n_mul++;                          // * I * R^-1 = (x_0 ... x_{k-1})^-1
+            np.emit(OP_STT, 0);
+        }
+        np.emit(OP_STOO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        B = &(ctx->prog_cache[kb] = np);
+    }
+    IoDesc fin[1] = {{in, K * S, S}};
+    if ((rc = run_vm(ctx, M, *F, chunks, fin, 1, totals, S, S, ExpDesc(), prefix, K * S))) return rc;
+    InvParams P{(uint32_t)chunks, (int)S, M.d_mod, totals, tinv, d_bad};
+    CU(ctx, modinv_launch(P, ctx->stream));
+    ctx->launches++;
+    IoDesc bin[3] = {{in, K * S, S}, {prefix, K * S, S}, {tinv, S, S}};
+    return run_vm(ctx, M, *B, chunks, bin, 3, out, K * S, S);
+}
+
+// out[i] = in[i]^-1 mod M for large batches; *d_first_bad as modinv_dev.  in and out may alias.
+int modinv_batch_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad) {
+    const uint32_t K = 32, S = M.sh.S;
+    if (count < 4 * K || S > BIG_MAXS) return modinv_dev(ctx, M, count, in, out, d_first_bad);
+    const size_t chunks = count / K, tail = count % K;
+    DEVBUF(prefix, ctx, count * S); DEVBUF(totals, ctx, (chunks + 1) * S); DEVBUF(tinv, ctx, (chunks + 1) * S); DEVBUF(src, ctx, in == out ? count * S : 1);
+    const uint32_t* x = in;
+    if (in == out) { CU(ctx, cudaMemcpyAsync(src.p, in, count * S * 4, cudaMemcpyDeviceToDevice, ctx->stream)); x = src.p; }
+    CU(ctx, cudaMemsetAsync(d_first_bad, 0xff, 4, ctx->stream));
+    int rc;
+    if ((rc = batch_inverse_chunks(ctx, M, chunks, K, x, out, prefix.p, totals.p, tinv.p, d_first_bad))) return rc;
+    if (tail && (rc = batch_inverse_chunks(ctx, M, 1, (uint32_t)tail, x + chunks * K * S, out + chunks * K * S, prefix.p + chunks * K * S,
+                                           totals.p + chunks * S, tinv.p + chunks * S, d_first_bad))) return rc;
+    uint32_t bad = 0;
+    CU(ctx, cudaMemcpyAsync(&bad, d_first_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad != 0xffffffffu) return modinv_dev(ctx, M, count, x, out, d_first_bad);     // a non-unit somewhere: exact per-item pass
+    return PGPU_OK;
+}
+
 int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* out) {
     MulParams P{(uint32_t)count, a, na, (int)na, b, nb, (int)nb, out, na + nb, na + nb};
     CU(ctx, bigmul_launch(P, ctx->stream));
@@ -515,7 +585,8 @@ int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t
     if ((rc = upload(ctx, kd.p, k.limbs(k.v.size() + 1)))) return rc;
     if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), c4r.p))) return rc;           // c^4 mod n^2: (c^4)^r = (c^4 mod n^2)^r
     if ((rc = modexp_items_dev(ctx, M, count, c4r.p, r, S, a.p))) return rc;             // a = (c^4)^r        :242
-    if ((rc = modexp_items_dev(ctx, M, count, v.p, r, S, b.p, true))) return rc;         // b = V^r            :245
+    if ((rc = ensure_fix_v(ctx))) return rc;
+    if ((rc = modexp_fixed_dev(ctx, M, ctx->fix_v, count, ExpDesc{r, S, 32 * S, nullptr}, b.p))) return rc;   // b = V^r (fixed base) :245
     if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e))) return rc;                 // E                  :250
     MulAddParams Q{(uint32_t)count, r, S, S, e, 8, 8, kd.p, (int)k.v.size(), z, z_limbs(ctx), z_limbs(ctx)};
     CU(ctx, muladd_launch(Q, ctx->stream));                                              // Z = r + E*delta*share :252
@@ -539,12 +610,13 @@ int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const
     if ((rc = modexp_items_dev(ctx, M, count, t0.p, z, ZL, t1.p))) return rc;
     if ((rc = modmul_dev(ctx, M, count, dec, dec, t0.p))) return rc;
     if ((rc = modexp_items_dev(ctx, M, count, t0.p, e, 8, t2.p))) return rc;
-    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modinv_batch_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
     if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, a.p))) return rc;
     // b = V^Z * (v_i^E)^-1 mod n^2                verifyPart2 :304-311
-    if ((rc = modexp_items_dev(ctx, M, count, kv.p, z, ZL, t1.p, true))) return rc;
+    if ((rc = ensure_fix_v(ctx))) return rc;
+    if ((rc = modexp_fixed_dev(ctx, M, ctx->fix_v, count, ExpDesc{z, ZL, 32 * ZL, nullptr}, t1.p))) return rc;   // V^Z (fixed base)
     if ((rc = modexp_items_dev(ctx, M, count, kvi.p, e, 8, t2.p, true))) return rc;
-    if ((rc = modinv_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modinv_batch_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
     if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, b.p))) return rc;
     if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e2.p))) return rc;
     CU(ctx, equal_launch(e, e2.p, 8, (uint32_t)count, ok, ctx->stream));
@@ -590,7 +662,7 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
     }
     const uint32_t* cprime = pos.p;
     if (have_neg) {                                                          // negative exponent: ModInverse (exp, :132-138)
-        if ((rc = modinv_dev(ctx, M, count, neg.p, t.p, bad.p))) return rc;
+        if ((rc = modinv_batch_dev(ctx, M, count, neg.p, t.p, bad.p))) return rc;
         if (have_pos) { if ((rc = modmul_dev(ctx, M, count, pos.p, t.p, pos.p))) return rc; }
         else cprime = t.p;
     }

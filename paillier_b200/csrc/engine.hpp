@@ -165,7 +165,7 @@ void program_free(Program& P);
 int ensure_table(pgpu_ctx* ctx, size_t limbs);
 int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
-           const ExpDesc& ex = ExpDesc());
+           const ExpDesc& ex = ExpDesc(), uint32_t* out2 = nullptr, uint32_t out2_stride = 0);
 int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out);
 ModCtx* select_mod(pgpu_ctx* ctx, int modsel);
 int build_encrypt(pgpu_ctx* ctx);
@@ -185,6 +185,7 @@ int modexp_shared_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc&
 int modmul_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& a, const IoDesc& b, uint32_t* out);
 int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_t* out);
 int modinv_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad);
+int modinv_batch_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* in, uint32_t* out, uint32_t* d_first_bad);
 int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, const uint32_t* b, uint32_t nb, uint32_t* out);
 int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, const uint32_t* stride, const int* limbs, uint32_t* out,
             const uint32_t* div = nullptr);
@@ -199,6 +200,8 @@ int set_device(pgpu_ctx* ctx);
 void protocols_free(pgpu_ctx* ctx);
 int fixed_table_build(pgpu_ctx* ctx, const ModCtx& M, const BigU& base, uint32_t exp_bits, FixedTable& T);
 void fixed_table_free(FixedTable& T);
+int modexp_fixed_dev(pgpu_ctx* ctx, const ModCtx& M, const FixedTable& T, size_t count, const ExpDesc& exp, uint32_t* out);
+int ensure_fix_v(pgpu_ctx* ctx);
 int setup_level2(pgpu_ctx* ctx);
 int setup_level2_secret(pgpu_ctx* ctx);
 int setup_alt(pgpu_ctx* ctx);

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
 
         for (const uint32_t* pc = P.prog;; ++pc) {
             const uint32_t op = __ldg(pc);
-            const uint32_t code = op >> 28, arg = op & 0x0fffffffu;
+            const uint32_t code = op >> 27, arg = op & 0x07ffffffu;
             if (code == OP_END) break;
             uint32_t nsq = 0, nmul = 0;
             switch (code) {
@@ -135,6 +135,26 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                     const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w);
                     load_vec<L>(y, P.fixed + ((size_t)(pos / w) * (1u << w) + idx) * S + lane_t * L);
                     nmul = 1;
+                } break;
+                case OP_LDIO: case OP_MULIO: {
+                    const uint32_t a = arg & 3u, off = arg >> 2;
+                    const uint32_t* p = P.in[a] + (size_t)item * P.in_stride[a] + (size_t)off * S;
+                    uint32_t v[L];
+                    load_vec<L>(v, p + lane_t * L);
+                    if (code == OP_LDIO) {
+#pragma unroll
+                        for (int k = 0; k < L; ++k) x[k] = v[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < L; ++k) y[k] = v[k];
+                        nmul = 1;
+                    }
+                } break;
+                case OP_STOO: {
+                    if (active) {
+                        const uint32_t a = arg & 1u, off = arg >> 2;
+                        store_vec<L>(P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S + lane_t * L, x);
+                    }
                 } break;
                 case OP_SUBT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
                 case OP_SQMT: {

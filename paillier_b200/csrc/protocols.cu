@@ -70,6 +70,34 @@ int fixed_table_build(pgpu_ctx* ctx, const ModCtx& M, const BigU& base, uint32_t
     return PGPU_OK;
 }
 
+// out[i] = base^exp[i] mod M for the fixed base of table T (comb method: one multiplication per window)
+int modexp_fixed_dev(pgpu_ctx* ctx, const ModCtx& M, const FixedTable& T, size_t count, const ExpDesc& exp, uint32_t* out) {
+    if (!T.d) return fail(ctx, PGPU_ERR_STATE, "fixed-base table was not built");
+    if (exp.bits > T.bits) return fail(ctx, PGPU_ERR_ARG, "exponent wider than the fixed-base table");
+    const uint32_t nwin = (exp.bits + T.w - 1) / T.w;
+    const std::string key = "powf:" + std::to_string(M.sh.S) + ":" + std::to_string(T.w) + ":" + std::to_string(nwin);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDC, K_R1);
+        for (uint32_t k = 0; k < nwin; ++k) { np.emit(OP_FIXW, (k * T.w) | (T.w << 20)); np.n_mul++; }
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    ExpDesc ex = exp; ex.fixed = T.d;
+    return run_vm(ctx, M, *P, count, nullptr, 0, out, M.sh.S, M.sh.S, ex);
+}
+
+// comb table of the threshold key's V for b = V^r (thresholdkey.go:245) and V^Z (:306); Z is the widest exponent
+int ensure_fix_v(pgpu_ctx* ctx) {
+    if (ctx->fix_v.d) return PGPU_OK;
+    if (ctx->tk_v.is_zero()) return fail(ctx, PGPU_ERR_STATE, "threshold key has no verification base V");
+    return fixed_table_build(ctx, ctx->m_n2, ctx->tk_v, 32 * z_limbs(ctx), ctx->fix_v);
+}
+
 void protocols_free(pgpu_ctx* ctx) {
     program_free(ctx->prog_enc2); program_free(ctx->prog_rand); program_free(ctx->prog_alt1); program_free(ctx->prog_alt2);
     fixed_table_free(ctx->fix_h1); fixed_table_free(ctx->fix_h2); fixed_table_free(ctx->fix_v);
@@ -349,7 +377,7 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     CU(ctx, resize_launch(a, wn, wn, a2.p, S2, (uint32_t)count, ctx->stream));
     ctx->launches++;
     DEVBUF(badinv, ctx, 1);
-    if ((rc = modinv_dev(ctx, M2, count, a2.p, ainv.p, badinv.p))) return rc;                                                // a^-1 mod n^2 :96
+    if ((rc = modinv_batch_dev(ctx, M2, count, a2.p, ainv.p, badinv.p))) return rc;                                                // a^-1 mod n^2 :96
     // ---- per instance
     DEVBUF(xn, ctx, total * S2); DEVBUF(yn2, ctx, total * S3); DEVBUF(u3, ctx, total * S3); DEVBUF(dig, ctx, total * 8);
     DEVBUF(e1, ctx, total * S2); DEVBUF(en, ctx, total * S2); DEVBUF(v3, ctx, total * S3); DEVBUF(f1, ctx, total * S3);
@@ -361,7 +389,7 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     if ((rc = modmul_io(ctx, M2, total, IoDesc{x, wn, wn}, IoDesc{ainv.p, S2, S2, secpar}, e1.p))) return rc;                // e = x*a^-1 mod n^2 :94-99
     if ((rc = modexp_shared_dev(ctx, M2, total, e1.p, ctx->n, en.p))) return rc;                                             // e^n        :105
     if ((rc = modexp_items_io(ctx, M3, total, IoDesc{c0.p, S3, S3, secpar}, ExpDesc{en.p, S2, e2bits, nullptr}, u3.p))) return rc;  // (s^an*b)^en :109
-    if ((rc = modinv_dev(ctx, M3, total, u3.p, v3.p, badinv.p))) return rc;                                                  // ^-1        :110
+    if ((rc = modinv_batch_dev(ctx, M3, total, u3.p, v3.p, badinv.p))) return rc;                                                  // ^-1        :110
     if ((rc = modexp_items_io(ctx, M3, total, IoDesc{s.p, wn, wn, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // s^xn  :112
     if ((rc = modmul_dev(ctx, M3, total, v3.p, u3.p, v3.p))) return rc;                                                      // c          :112
     if ((rc = modmul_io(ctx, M3, total, IoDesc{y, wn, wn}, IoDesc{v3.p, S3, S3}, f1.p))) return rc;                          // f = y*c    :113-114

@@ -26,13 +26,18 @@ enum VmOp : uint32_t {
     OP_MULI = 9,   // x = mont(x, in[arg][item])
     OP_ADDT = 10,  // x = (x + T[arg]) mod n
     OP_ADDC = 11,  // x = (x + kconst[arg]) mod n
-    OP_WIN  = 12,  // x = x^(2^w) * T[tbase + bits(exp[item], pos, w)], arg = pos | w<<20 | tbase<<24
+    OP_WIN  = 12,  // x = x^(2^w) * T[tbase + bits(exp[item], pos, w)], arg = pos | w<<20 | tbase<<24 (tbase < 8)
     OP_SQMT = 13,  // x = x^(2^nsq) * T[idx], arg = nsq | idx<<12  (sliding-window step)
     OP_FIXW = 14,  // x = x * F[(pos/w)*2^w + bits(exp[item], pos, w)], arg = pos | w<<20  (fixed-base comb step, no squarings)
     OP_SUBT = 15,  // x = (x - T[arg]) mod n
+    // chunked access (Montgomery's batch inversion walks a chunk of records per item): record = item*stride + off*S
+    OP_LDIO  = 16, // x = in[arg & 3][item, off = arg >> 2]
+    OP_MULIO = 17, // x = mont(x, in[arg & 3][item, off = arg >> 2])
+    OP_STOO  = 18, // out[arg & 1][item, off = arg >> 2] = x
 };
 
-constexpr uint32_t vm_op(uint32_t code, uint32_t arg) { return (code << 28) | (arg & 0x0fffffffu); }
+// 5-bit opcode, 27-bit argument
+constexpr uint32_t vm_op(uint32_t code, uint32_t arg) { return (code << 27) | (arg & 0x07ffffffu); }
 
 constexpr int VM_MAX_IN = 4;
 constexpr int VM_MAX_OUT = 2;

@@ -294,3 +294,43 @@ def test_verify_kats_on_gpu():
     b2 = pk.ModInverseBatch(pk.ExpBatch([77], [112]))[0]
     assert pk.MulModBatch([b1], [b2]) == [14602]
     pk.close()
+
+
+def test_batch_inversion_path(sk2048):
+    # >= 128 items take Montgomery's batch-inversion route (chunks of 32 + a ragged tail)
+    sk, _ = sk2048
+    n2, n3 = sk.N ** 2, sk.N ** 3
+    import random
+    rnd = random.Random(77)
+    for modsel, mod, count in ((MOD_N2, n2, 300), (MOD_N3, n3, 131)):
+        xs = [rnd.randrange(1, mod) for _ in range(count)]
+        xs[0], xs[1], xs[-1] = 1, mod - 1, 2
+        assert sk.ModInverseBatch(xs, modsel) == [pow(x, -1, mod) for x in xs]
+    p, _, _ = _key("paillier_2048")
+    from paillier_b200._lib import PgpuError, PGPU_ERR_NOT_INVERTIBLE
+    xs = [rnd.randrange(1, n2) for _ in range(200)]
+    xs[137] = p * 12345
+    xs[190] = 0
+    with pytest.raises(PgpuError) as ei:
+        sk.ModInverseBatch(xs)
+    assert ei.value.code == PGPU_ERR_NOT_INVERTIBLE and "item 137" in str(ei.value)
+
+
+def test_zkp_large_batch_fixed_base_and_batch_inverse():
+    # 160 proofs: V^r / V^Z through the comb table, the verifier's inversions through the batch route
+    n, keys, okeys = _threshold_setup("threshold_512", 5, 3, 512)
+    tk = keys[1]
+    count = 160
+    ms = from_records(synth.plaintexts(count, n, tk.w_n), tk.w_n)
+    cs = [c.C for c in tk.EncryptWithRBatch(ms, from_records(synth.randomness(count, n, tk.w_n), tk.w_n))]
+    rs = from_records(synth.random_records(count, tk.w_n2, (n * n).bit_length() - 1, stream=23), tk.w_n2)
+    zk = tk.PartialDecryptionWithZKPBatch(cs, rs)
+    for i in (0, 77, count - 1):
+        o = R.partial_decryption_with_zkp(okeys[1], cs[i], rs[i])
+        assert (zk[i].Decryption, zk[i].E, zk[i].Z) == (o.Decryption, o.E, o.Z)
+    bad = list(zk)
+    bad[99] = type(bad[99])(bad[99].ID, bad[99].Decryption, bad[99].E ^ 1, bad[99].Z, bad[99].C)
+    res = tk.VerifyProofBatch(bad)
+    assert res[99] is False and sum(res) == count - 1
+    for k in keys:
+        k.close()
