@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpaillier_b200.so")
+LIB_PATH = os.environ.get("PGPU_LIB_PATH") or os.path.join(_HERE, "libpaillier_b200.so")
 
 PGPU_OK, PGPU_ERR_ARG, PGPU_ERR_CUDA, PGPU_ERR_NCCL, PGPU_ERR_STATE = 0, 1, 2, 3, 4
 PGPU_ERR_NOT_INVERTIBLE, PGPU_ERR_THRESHOLD, PGPU_ERR_UNSUPPORTED = 5, 6, 7

@@ -179,9 +179,12 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     P.out[1] = out2; P.out_stride[1] = out2_stride; P.out_limbs[1] = m.sh.S;
     P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed;
     P.n_groups = (uint32_t)blocks * gpb;
-    int rc = ensure_table(ctx, (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S);
+    { static const bool no_sqr = getenv("PGPU_NO_SQR") != nullptr; P.flags = no_sqr ? 1u : 0u; }
+    const size_t tbl_limbs = (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S;
+    int rc = ensure_table(ctx, tbl_limbs + (size_t)P.n_groups * m.sh.S);
     if (rc) return rc;
     P.table = ctx->d_table;
+    P.dump = ctx->d_table + tbl_limbs;
     CU(ctx, vm_launch(m.sh.tpi, m.sh.L, P, blocks, ctx->stream));
     ctx->launches++;
     return PGPU_OK;

@@ -58,9 +58,10 @@ __device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uin
 }
 
 template <int TPI, int L>
-__global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
+__global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 : 1)) powm_vm(const VmParams P) {
     constexpr int S = TPI * L;
-    Mont<TPI, L> M;
+    using MontT = Mont<TPI, L, SqrShape<TPI, L>::value>;
+    MontT M;
     const uint32_t n_groups = P.n_groups;
     const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
     const uint32_t n_inst = P.n_items;
@@ -69,14 +70,19 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
     uint32_t* const tbl = P.table + (size_t)group * S + lane_t * L;
     const size_t tbl_entry_stride = (size_t)n_groups * S;
     M.init(P.mod, P.np0);
+    if constexpr (MontT::HAS_SQR) {
+        extern __shared__ uint4 vm_smem[];
+        M.init_sqr(vm_smem + (threadIdx.x >> 5) * (MontT::SQR_ROWS * 32));
+    }
     const uint32_t* const kc = P.kconst + lane_t * L;
+    uint32_t* const dump = P.dump + (size_t)group * S;
 
     for (uint32_t rd = 0; rd < rounds; ++rd) {
         uint32_t item = rd * n_groups + group;
         const bool active = item < n_inst;      // whole warps stay in lock-step; idle groups redo item 0
         if (!active) item = 0;
 
-        uint32_t x[L], y[L];
+        uint32_t x[L], y[L], y2[L];
 #pragma unroll
         for (int k = 0; k < L; ++k) x[k] = 0;
 
@@ -99,14 +105,14 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                 case OP_LDT: load_vec<L>(x, tbl + arg * tbl_entry_stride); break;
                 case OP_STT: store_vec<L>(tbl + arg * tbl_entry_stride, x); break;
                 case OP_STO: {
-                    if (active) {
-                        uint32_t* p = P.out[arg] + (size_t)item * P.out_stride[arg];
-                        const uint32_t lim = P.out_limbs[arg];
+                    // idle groups (they redo item 0 in lock step) store into their dump record: no branch on `active`,
+                    // which would make the compiler clone the whole interpreter loop
+                    uint32_t* p = active ? P.out[arg] + (size_t)item * P.out_stride[arg] : dump;
+                    const uint32_t lim = P.out_limbs[arg];
 #pragma unroll
-                        for (int k = 0; k < L; ++k) {
-                            const uint32_t idx = lane_t * L + k;
-                            if (idx < lim) p[idx] = x[k];
-                        }
+                    for (int k = 0; k < L; ++k) {
+                        const uint32_t idx = lane_t * L + k;
+                        if (idx < lim) p[idx] = x[k];
                     }
                 } break;
                 case OP_SQR: nsq = arg; break;
@@ -151,10 +157,9 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                     }
                 } break;
                 case OP_STOO: {
-                    if (active) {
-                        const uint32_t a = arg & 1u, off = arg >> 2;
-                        store_vec<L>(P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S + lane_t * L, x);
-                    }
+                    const uint32_t a = arg & 1u, off = arg >> 2;
+                    uint32_t* p = active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump;
+                    store_vec<L>(p + lane_t * L, x);
                 } break;
                 case OP_SUBT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
                 case OP_SQMT: {
@@ -165,27 +170,66 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS) powm_vm(const VmParams P) {
                 default: break;
             }
             // the single Montgomery multiplier of the instruction stream
-            for (uint32_t i = nsq + nmul; i > 0; --i) {
-                const bool sq = i > nmul;
-                uint32_t b[L];
+            if constexpr (MontT::HAS_SQR) {
+                if (P.flags & 1u) {
+#pragma unroll 1
+                    for (uint32_t i = nsq; i > 0; --i) {
 #pragma unroll
-                for (int k = 0; k < L; ++k) b[k] = sq ? x[k] : y[k];
-                M.mul(x, x, b);
+                        for (int k = 0; k < L; ++k) y2[k] = x[k];
+                        M.mul(x, x, y2);
+                    }
+                } else {
+#pragma unroll 1
+                    for (uint32_t i = nsq; i > 0; --i) M.sqr(x, x);
+                }
+                if (nmul) M.mul(x, x, y);
+            } else {
+                for (uint32_t i = nsq + nmul; i > 0; --i) {
+                    const bool sq = i > nmul;
+                    uint32_t b[L];
+#pragma unroll
+                    for (int k = 0; k < L; ++k) b[k] = sq ? x[k] : y[k];
+                    M.mul(x, x, b);
+                }
             }
         }
     }
 }
 
 template <int TPI, int L>
+constexpr size_t vm_smem_bytes() {
+    using MontT = Mont<TPI, L, SqrShape<TPI, L>::value>;
+    return MontT::HAS_SQR ? MontT::SQR_SMEM_PER_WARP * (VM_BLOCK_THREADS / 32) : 0;
+}
+
+template <int TPI, int L>
+static cudaError_t prepare_t() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && done[dev]) return cudaSuccess;
+    if (vm_smem_bytes<TPI, L>() > 48 * 1024) {
+        e = cudaFuncSetAttribute(powm_vm<TPI, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<TPI, L>());
+        if (e != cudaSuccess) return e;
+    }
+    if (dev < 64) done[dev] = true;
+    return cudaSuccess;
+}
+
+template <int TPI, int L>
 static cudaError_t launch_t(const VmParams& P, int blocks, cudaStream_t stream) {
-    powm_vm<TPI, L><<<blocks, VM_BLOCK_THREADS, 0, stream>>>(P);
+    cudaError_t e = prepare_t<TPI, L>();
+    if (e != cudaSuccess) return e;
+    powm_vm<TPI, L><<<blocks, VM_BLOCK_THREADS, vm_smem_bytes<TPI, L>(), stream>>>(P);
     return cudaGetLastError();
 }
 
 template <int TPI, int L>
 static int occupancy_t() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, powm_vm<TPI, L>, VM_BLOCK_THREADS, 0);
+    if (prepare_t<TPI, L>() != cudaSuccess) return 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, powm_vm<TPI, L>, VM_BLOCK_THREADS, vm_smem_bytes<TPI, L>());
     return nb;
 }
 

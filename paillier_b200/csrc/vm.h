@@ -63,6 +63,8 @@ struct VmParams {
     const uint32_t* fixed;             // fixed-base table for OP_FIXW: records of S limbs, Montgomery form
     uint32_t* table;                   // scratch: [entry][group][S]
     uint32_t n_groups;                 // number of resident groups (table slots)
+    uint32_t flags;                    // bit 0: use the general multiplier for squarings too
+    uint32_t* dump;                    // n_groups records of S limbs: where idle groups of the last round store
 };
 
 }  // namespace pgpu
