@@ -296,27 +296,83 @@ def main() -> None:
         Sp, p_sqr, p_mul = tsk.program_cost(2)
         breakdown["pdec_per_s"] = world * pcount / (pms * 1e-3)
         breakdown["pdec_program"] = {"limbs": Sp, "sqr": p_sqr, "mul": p_mul, "mac32_per_item": mont_macs(Sp, p_sqr, p_mul), "items": pcount}
+        # PartialDecryptionWithZKP (thresholdkey.go:225-255) on a smaller slice: 3 full exponentiations + a fixed-base one per item
+        zcount = max(1, min(pcount, 1 << 14))
+        zr = torch.from_numpy(synth.random_records(zcount, w_n2, (n * n).bit_length() - 1, stream=31)).to(dev)
+        ze = torch.empty(zcount * 32, dtype=torch.uint8, device=dev)
+        zz = torch.empty(zcount * tsk.w_z, dtype=torch.uint8, device=dev)
+        zin = c_dev[:zcount * w_n2]
+        zout = torch.empty_like(zin)
+        for timed in (False, True):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            check(lib.pgpu_pdec_zkp_prove_dev(tsk._ctx, zcount, vp(zin), vp(zr), vp(zout), vp(ze), vp(zz)), tsk._ctx)
+            e1.record(stream)
+            barrier()
+        breakdown["pdec_zkp_prove_per_s"] = world * zcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        breakdown["pdec_zkp_items"] = zcount
         tsk.close()
+        # BASELINE config 3: encrypted dot product with 64-bit scalars (ConstMult + Add) over the ciphertexts of this step
+        dcount = max(1, count // 4)
+        k64 = torch.from_numpy(synth.scalars_u64(dcount, seed).view(np.int64).copy()).to(dev)
+        dot = torch.empty(w_n2, dtype=torch.uint8, device=dev)
+        for timed in (False, True):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            check(lib.pgpu_dot_u64_dev(sk._ctx, dcount, vp(c_dev), C.cast(C.c_void_p(k64.data_ptr()), C.POINTER(C.c_uint64)), vp(dot)), sk._ctx)
+            e1.record(stream)
+            barrier()
+        breakdown["dot_u64_terms_per_s"] = world * dcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        breakdown["dot_u64_terms"] = dcount
+        # BASELINE configs[4]: safe-prime candidate procedure (sieve + Miller-Rabin + Fermat) at 1024-bit p
+        if rank == 0:
+            from paillier_b200.keygen import safe_prime_scan
+            ncand = 1 << 15
+            rawb = synth.random_records(ncand, 128, 1024, stream=41).tobytes()
+            safe_prime_scan(1024, rawb[:128 * 256], device=local)
+            t0 = time.perf_counter()
+            _, _, okf = safe_prime_scan(1024, rawb, device=local)
+            breakdown["safe_prime_candidates_per_s"] = ncand / (time.perf_counter() - t0)
+            breakdown["safe_prime_candidates"] = ncand
 
     if rank == 0:
         peak = imad_peak() if not args.no_extras else None
         peak_t = peak["imad_wide_tmacs"] if peak else None
         achieved = enc_macs * count / (enc_ms * 1e-3) / 1e12      # per GPU: one launch processes `count` items
+        # what the multiplier pipe actually executes: powm_vm<4,32> squares with the general multiplier (2s^2+s)
+        executed = (n_sqr + n_mul) * (2.0 * S * S + S) * count / (enc_ms * 1e-3) / 1e12
         mp = {}
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         alg_bytes = count * (2 * w_n + w_n2)
+        # DRAM bytes of the EncryptWithR launch: per-item traffic of the committed `ncu --set full` capture of the same
+        # kernel (profiles/r01_ncu_powm_vm_summary_v2.json, 18944 items) scaled to this launch's item count
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_powm_vm_summary_v2.json")))
+            k0 = prof["kernels"][0]
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            def _b(sv):
+                v, u = sv.split()[:2]
+                return float(v) * unit[u]
+            traffic = (_b(k0["dram__bytes_read.sum"]) + _b(k0["dram__bytes_write.sum"])) / prof["items_per_launch"] * count
+        except Exception:
+            traffic = None
         roofline = {
             "bound": "imad", "kernel": "powm_vm (EncryptWithR launch)", "achieved": achieved, "peak": peak_t, "unit": "TMAC32/s",
             "frac": (achieved / peak_t) if peak_t else None,
             "peak_source": "tools/imad_peak.cu run live on this GPU: dependency-free IMAD.WIDE.U32 issue rate (SURVEY.md 8d); "
                            "MEASURED_PEAKS.json holds HBM and bf16 peaks only, which do not bound this integer carry-chain kernel",
             "mac32_per_item": enc_macs, "items_per_launch": count, "launch_ms": enc_ms,
+            "executed_tmac32": executed, "executed_frac": (executed / peak_t) if peak_t else None,
+            "note": "achieved counts squarings at 1.5s^2+1.5s (SURVEY.md 8d); the 4096-bit kernel issues 2s^2+s for them, see executed_*",
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (enc_ms * 1e-3) / 1e9,
                     "peak_gbs": mp.get("hbm_gbs"), "frac": (alg_bytes / (enc_ms * 1e-3) / 1e9 / mp["hbm_gbs"]) if mp.get("hbm_gbs") else None},
-            "traffic": None,
+            "traffic": traffic,
             "imad_peak": peak,
         }
         cpu = None

@@ -142,20 +142,13 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
                     load_vec<L>(y, P.fixed + ((size_t)(pos / w) * (1u << w) + idx) * S + lane_t * L);
                     nmul = 1;
                 } break;
-                case OP_LDIO: case OP_MULIO: {
-                    const uint32_t a = arg & 3u, off = arg >> 2;
-                    const uint32_t* p = P.in[a] + (size_t)item * P.in_stride[a] + (size_t)off * S;
-                    uint32_t v[L];
-                    load_vec<L>(v, p + lane_t * L);
-                    if (code == OP_LDIO) {
-#pragma unroll
-                        for (int k = 0; k < L; ++k) x[k] = v[k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < L; ++k) y[k] = v[k];
-                        nmul = 1;
-                    }
-                } break;
+                case OP_LDIO:
+                    load_vec<L>(x, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S + lane_t * L);
+                    break;
+                case OP_MULIO:
+                    load_vec<L>(y, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S + lane_t * L);
+                    nmul = 1;
+                    break;
                 case OP_STOO: {
                     const uint32_t a = arg & 1u, off = arg >> 2;
                     uint32_t* p = active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump;

@@ -103,7 +103,9 @@ struct StrongParams {
     const uint32_t* idx;         // items to test, or nullptr for 0..n_items-1
     const uint32_t* mod;         // records of S limbs, odd
     uint32_t bits;               // bit length of every modulus
-    uint32_t base;               // small base a >= 2
+    uint32_t base;               // small base a >= 2 (used when bases == nullptr)
+    const uint32_t* bases;       // nb bases: slot s tests item idx[s / nb] to base bases[s % nb]
+    uint32_t nb;
     uint32_t fermat;             // 0: Miller-Rabin strong test; 1: Fermat test a^(m-1) = 1
     uint8_t* flags;              // flags[item] &= pass
 };
@@ -120,7 +122,10 @@ __global__ void __launch_bounds__(128) strong_kernel(StrongParams P) {
         uint32_t slot = rd * n_groups + group;
         const bool active = slot < P.n_items;
         if (!active) slot = 0;
-        const uint32_t item = P.idx ? P.idx[slot] : slot;
+        const uint32_t nb = P.bases ? P.nb : 1u;
+        const uint32_t which = slot / nb;
+        const uint32_t item = P.idx ? P.idx[which] : which;
+        const uint32_t base = P.bases ? P.bases[slot - which * nb] : P.base;
         const uint32_t* mod = P.mod + (size_t)item * S;
         // -m^-1 mod 2^32 by Newton iteration on the lowest limb
         const uint32_t m0 = mod[0];
@@ -152,12 +157,12 @@ __global__ void __launch_bounds__(128) strong_kernel(StrongParams P) {
 #pragma unroll
         for (int k = 0; k < L; ++k) aR[k] = one[k];
         {
-            int hb = 31 - __clz(P.base);
+            int hb = 31 - __clz(base);
             for (int bpos = hb - 1; bpos >= 0; --bpos) {
                 M.add(aR, aR, aR);
                 uint32_t t[L];
                 M.add(t, aR, one);
-                const bool take = (P.base >> bpos) & 1u;
+                const bool take = (base >> bpos) & 1u;
 #pragma unroll
                 for (int k = 0; k < L; ++k) aR[k] = take ? t[k] : aR[k];
             }
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(128) strong_kernel(StrongParams P) {
 #pragma unroll
         for (int k = 0; k < L; ++k) x[k] = aR[k];
         bool pass = false;
-        const bool base2 = P.base == 2;
+        const bool base2 = P.bases == nullptr && P.base == 2;
         const int last = P.fermat ? 0 : 1;
         for (int i = (int)P.bits - 2; i >= last; --i) {
             M.mul(x, x, x);
@@ -258,8 +263,8 @@ const char* primes_last_error() { return g_perr.c_str(); }
 // flags[i] = 1 if cand[i] (records of S limbs, all of `bits` bits, odd) passes `rounds` Miller-Rabin rounds
 // (bases 2, 3, 5, ...).  Items that fail base 2 are not tested further.
 static int mr_filter(int S, int sms, cudaStream_t st, size_t count, const uint32_t* d_cand, uint32_t bits, unsigned rounds,
-                     uint8_t* d_flags, std::vector<uint8_t>& h_flags, uint32_t* d_idx, uint64_t* launches, std::string& err) {
-    StrongParams P{(uint32_t)count, nullptr, d_cand, bits, 2, 0, d_flags};
+                     uint8_t* d_flags, std::vector<uint8_t>& h_flags, uint32_t* d_idx, const uint32_t* d_bases, uint64_t* launches, std::string& err) {
+    StrongParams P{(uint32_t)count, nullptr, d_cand, bits, 2, nullptr, 0, 0, d_flags};
     cudaError_t e = strong_launch(S, P, sms, st);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return PGPU_ERR_CUDA; }
     ++*launches;
@@ -272,8 +277,9 @@ static int mr_filter(int S, int sms, cudaStream_t st, size_t count, const uint32
     if (idx.empty() || rounds <= 1) return PGPU_OK;
     e = cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return PGPU_ERR_CUDA; }
-    for (unsigned r = 1; r < rounds && r < 20; ++r) {
-        StrongParams Q{(uint32_t)idx.size(), d_idx, d_cand, bits, MR_BASES[r], 0, d_flags};
+    {   // the remaining bases of every survivor in one launch
+        const unsigned nb = std::min(rounds, 20u) - 1;
+        StrongParams Q{(uint32_t)(idx.size() * nb), d_idx, d_cand, bits, 0, d_bases + 1, nb, 0, d_flags};
         e = strong_launch(S, Q, sms, st);
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return PGPU_ERR_CUDA; }
         ++*launches;
@@ -305,16 +311,17 @@ int pgpu_miller_rabin(int device, unsigned bits, size_t count, const void* cand,
         const unsigned b = top ? 32 * (top - 1) + (32 - __builtin_clz(c[top - 1])) : 0;
         if (b != bits || !(c[0] & 1)) return pfail(PGPU_ERR_ARG, "pgpu_miller_rabin: candidate " + std::to_string(i) + " is even or not of the stated bit length");
     }
-    uint32_t *d_cand = nullptr, *d_idx = nullptr; uint8_t* d_flags = nullptr; cudaStream_t st = nullptr;
-    auto cleanup = [&]() { if (d_cand) cudaFree(d_cand); if (d_idx) cudaFree(d_idx); if (d_flags) cudaFree(d_flags); if (st) cudaStreamDestroy(st); };
+    uint32_t *d_cand = nullptr, *d_idx = nullptr, *d_bases = nullptr; uint8_t* d_flags = nullptr; cudaStream_t st = nullptr;
+    auto cleanup = [&]() { if (d_cand) cudaFree(d_cand); if (d_idx) cudaFree(d_idx); if (d_bases) cudaFree(d_bases); if (d_flags) cudaFree(d_flags); if (st) cudaStreamDestroy(st); };
     PCU(cudaSetDevice(device));
-    cudaDeviceProp prop; PCU(cudaGetDeviceProperties(&prop, device));
+    int sms_attr = 0; PCU(cudaDeviceGetAttribute(&sms_attr, cudaDevAttrMultiProcessorCount, device));
     PCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    PCU(cudaMalloc(&d_cand, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4)); PCU(cudaMalloc(&d_flags, count));
+    PCU(cudaMalloc(&d_cand, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4)); PCU(cudaMalloc(&d_flags, count)); PCU(cudaMalloc(&d_bases, sizeof MR_BASES));
+    PCU(cudaMemcpyAsync(d_bases, MR_BASES, sizeof MR_BASES, cudaMemcpyHostToDevice, st));
     PCU(cudaMemcpyAsync(d_cand, cand, count * S * 4, cudaMemcpyHostToDevice, st));
     PCU(cudaMemsetAsync(d_flags, 1, count, st));
     std::vector<uint8_t> h; std::string err; uint64_t nl = 0;
-    int rc = mr_filter(S, prop.multiProcessorCount, st, count, d_cand, bits, rounds, d_flags, h, d_idx, &nl, err);
+    int rc = mr_filter(S, sms_attr, st, count, d_cand, bits, rounds, d_flags, h, d_idx, d_bases, &nl, err);
     if (rc == PGPU_OK) memcpy(ok, h.data(), count);
     if (launches) *launches = nl;
     cleanup();
@@ -329,17 +336,17 @@ int pgpu_safe_prime_scan(int device, unsigned p_bits, size_t count, const uint8_
     if (count == 0) return PGPU_OK;
     if (count > 0x7fffffffu) return pfail(PGPU_ERR_ARG, "pgpu_safe_prime_scan: batch too large");
     const unsigned q_bits = p_bits - 1, raw_bytes = (q_bits + 7) / 8;
-    uint8_t *d_raw = nullptr, *d_state = nullptr, *d_pf = nullptr; uint32_t *d_q = nullptr, *d_p = nullptr, *d_idx = nullptr; cudaStream_t st = nullptr;
+    uint8_t *d_raw = nullptr, *d_state = nullptr, *d_pf = nullptr; uint32_t *d_q = nullptr, *d_p = nullptr, *d_idx = nullptr, *d_bases = nullptr; cudaStream_t st = nullptr;
     auto cleanup = [&]() {
-        for (void* x : {(void*)d_raw, (void*)d_state, (void*)d_pf, (void*)d_q, (void*)d_p, (void*)d_idx}) if (x) cudaFree(x);
+        for (void* x : {(void*)d_raw, (void*)d_state, (void*)d_pf, (void*)d_q, (void*)d_p, (void*)d_idx, (void*)d_bases}) if (x) cudaFree(x);
         if (st) cudaStreamDestroy(st);
     };
     PCU(cudaSetDevice(device));
-    cudaDeviceProp prop; PCU(cudaGetDeviceProperties(&prop, device));
-    const int sms = prop.multiProcessorCount;
+    int sms = 0; PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     PCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     PCU(cudaMalloc(&d_raw, count * raw_bytes)); PCU(cudaMalloc(&d_state, count)); PCU(cudaMalloc(&d_pf, count));
-    PCU(cudaMalloc(&d_q, count * S * 4)); PCU(cudaMalloc(&d_p, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4));
+    PCU(cudaMalloc(&d_q, count * S * 4)); PCU(cudaMalloc(&d_p, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4)); PCU(cudaMalloc(&d_bases, sizeof MR_BASES));
+    PCU(cudaMemcpyAsync(d_bases, MR_BASES, sizeof MR_BASES, cudaMemcpyHostToDevice, st));
     PCU(cudaMemcpyAsync(d_raw, raw, count * raw_bytes, cudaMemcpyHostToDevice, st));
     uint64_t nl = 0;
     SieveParams SP{(uint32_t)count, q_bits, raw_bytes, (uint32_t)S, d_raw, d_q, d_p, d_state};
@@ -355,7 +362,7 @@ int pgpu_safe_prime_scan(int device, unsigned p_bits, size_t count, const uint8_
     std::vector<uint8_t> flags(count, 0);
     if (!idx.empty()) {
         PCU(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
-        StrongParams P{(uint32_t)idx.size(), d_idx, d_q, q_bits, 2, 0, d_state};
+        StrongParams P{(uint32_t)idx.size(), d_idx, d_q, q_bits, 2, nullptr, 0, 0, d_state};
         PCU(strong_launch(S, P, sms, st)); ++nl;
         PCU(cudaMemcpyAsync(state.data(), d_state, count, cudaMemcpyDeviceToHost, st));
         PCU(cudaStreamSynchronize(st));
@@ -363,12 +370,12 @@ int pgpu_safe_prime_scan(int device, unsigned p_bits, size_t count, const uint8_
         for (size_t i = 0; i < count; ++i) if (state[i]) idx.push_back((uint32_t)i);
         if (!idx.empty()) {
             PCU(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
-            for (unsigned r = 1; r < 20; ++r) {
-                StrongParams Q{(uint32_t)idx.size(), d_idx, d_q, q_bits, MR_BASES[r], 0, d_state};
+            {   // bases 3 .. 71 of every survivor in one launch
+                StrongParams Q{(uint32_t)(idx.size() * 19), d_idx, d_q, q_bits, 0, d_bases + 1, 19, 0, d_state};
                 PCU(strong_launch(S, Q, sms, st)); ++nl;
             }
             // isPocklingtonCriterionSatisfied(p) (:257, :272-278): evaluated only when q passed (&& short circuit)
-            StrongParams F{(uint32_t)idx.size(), d_idx, d_p, p_bits, 2, 1, d_state};
+            StrongParams F{(uint32_t)idx.size(), d_idx, d_p, p_bits, 2, nullptr, 0, 1, d_state};
             PCU(strong_launch(S, F, sms, st)); ++nl;
             PCU(cudaMemcpyAsync(state.data(), d_state, count, cudaMemcpyDeviceToHost, st));
             PCU(cudaStreamSynchronize(st));
