@@ -326,6 +326,24 @@ def main() -> None:
             barrier()
         breakdown["dot_u64_terms_per_s"] = world * dcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         breakdown["dot_u64_terms"] = dcount
+        # AltEncryptWithR (paillier.go:221-238): fixed base h_1, comb table, no squarings
+        from paillier_b200.api import PublicKey
+        hr = int.from_bytes(synth.randomness(1, n, w_n, seed).tobytes(), "little")
+        apk = PublicKey(n, device=local, H=hr * hr % n, K=1 << (n.bit_length() // 2))
+        check(lib.pgpu_ctx_set_stream(apk._ctx, C.c_void_p(stream.cuda_stream)), apk._ctx)
+        acount = max(1, count // 4)
+        a_host_m, a_host_r = m_host[:acount * w_n], r_host[:acount * w_n]
+        a_host_c = torch.empty(acount * w_n2, dtype=torch.uint8).pin_memory()
+        hp2 = lambda t: C.c_void_p(t.data_ptr())
+        for timed in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            check(lib.pgpu_alt_encrypt_with_r_at_level(apk._ctx, 1, acount, hp2(a_host_m), hp2(a_host_r), hp2(a_host_c)), apk._ctx)
+            barrier()
+            adt = time.perf_counter() - t0
+        breakdown["alt_enc_e2e_per_s"] = world * acount / max_over_ranks(adt)
+        breakdown["alt_enc_items"] = acount
+        apk.close()
         # BASELINE configs[4]: safe-prime candidate procedure (sieve + Miller-Rabin + Fermat) at 1024-bit p
         if rank == 0:
             from paillier_b200.keygen import safe_prime_scan

@@ -40,6 +40,13 @@ int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_le
     ctx->sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(ctx, PGPU_ERR_CUDA, "cudaStreamCreate failed"));
     ctx->stream = ctx->own_stream;
+    {   // keep the stream-ordered pool warm: the temporaries of the composite operations come from it
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     ctx->n = BigU::from_be(n_be, n_len);
     if (!ctx->n.is_odd() || ctx->n.bitlen() < 2) return bail(fail(ctx, PGPU_ERR_ARG, "n must be an odd integer >= 3"));

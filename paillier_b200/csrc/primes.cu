@@ -154,18 +154,17 @@ __global__ void __launch_bounds__(128) strong_kernel(StrongParams P) {
 #pragma unroll
         for (int k = 0; k < L; ++k) zero[k] = 0;
         M.sub(minus1, zero, one);
+        // aR = a * one by double-and-add over a fixed number of bit positions: groups of one warp may hold different bases
+        // and every Mont operation is a warp-wide collective, so the trip count must not depend on the base (a < 2^8)
 #pragma unroll
-        for (int k = 0; k < L; ++k) aR[k] = one[k];
-        {
-            int hb = 31 - __clz(base);
-            for (int bpos = hb - 1; bpos >= 0; --bpos) {
-                M.add(aR, aR, aR);
-                uint32_t t[L];
-                M.add(t, aR, one);
-                const bool take = (base >> bpos) & 1u;
+        for (int k = 0; k < L; ++k) aR[k] = 0;
+        for (int bpos = 7; bpos >= 0; --bpos) {
+            M.add(aR, aR, aR);
+            uint32_t t[L];
+            M.add(t, aR, one);
+            const bool take = (base >> bpos) & 1u;
 #pragma unroll
-                for (int k = 0; k < L; ++k) aR[k] = take ? t[k] : aR[k];
-            }
+            for (int k = 0; k < L; ++k) aR[k] = take ? t[k] : aR[k];
         }
         // exponent e = m - 1 (m odd: clear bit 0); s = trailing zeros of e (group-uniform)
         uint32_t e[L];
@@ -254,6 +253,23 @@ int pfail(int code, const std::string& m) { g_perr = m; return code; }
 
 const uint32_t MR_BASES[20] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71};
 
+// one stream per device, created once; scratch comes from the stream-ordered pool (kept warm across calls)
+cudaError_t scratch_stream(int device, cudaStream_t* st) {
+    static cudaStream_t streams[64] = {};
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (!streams[device]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    *st = streams[device];
+    return cudaSuccess;
+}
+
 int shape_for_bits(unsigned bits) { return bits <= 1024 ? 32 : bits <= 1536 ? 48 : bits <= 2048 ? 64 : 0; }
 
 }  // namespace
@@ -312,11 +328,11 @@ int pgpu_miller_rabin(int device, unsigned bits, size_t count, const void* cand,
         if (b != bits || !(c[0] & 1)) return pfail(PGPU_ERR_ARG, "pgpu_miller_rabin: candidate " + std::to_string(i) + " is even or not of the stated bit length");
     }
     uint32_t *d_cand = nullptr, *d_idx = nullptr, *d_bases = nullptr; uint8_t* d_flags = nullptr; cudaStream_t st = nullptr;
-    auto cleanup = [&]() { if (d_cand) cudaFree(d_cand); if (d_idx) cudaFree(d_idx); if (d_bases) cudaFree(d_bases); if (d_flags) cudaFree(d_flags); if (st) cudaStreamDestroy(st); };
+    auto cleanup = [&]() { for (void* x : {(void*)d_cand, (void*)d_idx, (void*)d_bases, (void*)d_flags}) if (x) cudaFreeAsync(x, st); if (st) cudaStreamSynchronize(st); };
     PCU(cudaSetDevice(device));
     int sms_attr = 0; PCU(cudaDeviceGetAttribute(&sms_attr, cudaDevAttrMultiProcessorCount, device));
-    PCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    PCU(cudaMalloc(&d_cand, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4)); PCU(cudaMalloc(&d_flags, count)); PCU(cudaMalloc(&d_bases, sizeof MR_BASES));
+    PCU(scratch_stream(device, &st));
+    PCU(cudaMallocAsync(&d_cand, count * S * 4, st)); PCU(cudaMallocAsync(&d_idx, count * 4, st)); PCU(cudaMallocAsync(&d_flags, count, st)); PCU(cudaMallocAsync(&d_bases, sizeof MR_BASES, st));
     PCU(cudaMemcpyAsync(d_bases, MR_BASES, sizeof MR_BASES, cudaMemcpyHostToDevice, st));
     PCU(cudaMemcpyAsync(d_cand, cand, count * S * 4, cudaMemcpyHostToDevice, st));
     PCU(cudaMemsetAsync(d_flags, 1, count, st));
@@ -338,14 +354,14 @@ int pgpu_safe_prime_scan(int device, unsigned p_bits, size_t count, const uint8_
     const unsigned q_bits = p_bits - 1, raw_bytes = (q_bits + 7) / 8;
     uint8_t *d_raw = nullptr, *d_state = nullptr, *d_pf = nullptr; uint32_t *d_q = nullptr, *d_p = nullptr, *d_idx = nullptr, *d_bases = nullptr; cudaStream_t st = nullptr;
     auto cleanup = [&]() {
-        for (void* x : {(void*)d_raw, (void*)d_state, (void*)d_pf, (void*)d_q, (void*)d_p, (void*)d_idx, (void*)d_bases}) if (x) cudaFree(x);
-        if (st) cudaStreamDestroy(st);
+        for (void* x : {(void*)d_raw, (void*)d_state, (void*)d_pf, (void*)d_q, (void*)d_p, (void*)d_idx, (void*)d_bases}) if (x) cudaFreeAsync(x, st);
+        if (st) cudaStreamSynchronize(st);
     };
     PCU(cudaSetDevice(device));
     int sms = 0; PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    PCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    PCU(cudaMalloc(&d_raw, count * raw_bytes)); PCU(cudaMalloc(&d_state, count)); PCU(cudaMalloc(&d_pf, count));
-    PCU(cudaMalloc(&d_q, count * S * 4)); PCU(cudaMalloc(&d_p, count * S * 4)); PCU(cudaMalloc(&d_idx, count * 4)); PCU(cudaMalloc(&d_bases, sizeof MR_BASES));
+    PCU(scratch_stream(device, &st));
+    PCU(cudaMallocAsync(&d_raw, count * raw_bytes, st)); PCU(cudaMallocAsync(&d_state, count, st)); PCU(cudaMallocAsync(&d_pf, count, st));
+    PCU(cudaMallocAsync(&d_q, count * S * 4, st)); PCU(cudaMallocAsync(&d_p, count * S * 4, st)); PCU(cudaMallocAsync(&d_idx, count * 4, st)); PCU(cudaMallocAsync(&d_bases, sizeof MR_BASES, st));
     PCU(cudaMemcpyAsync(d_bases, MR_BASES, sizeof MR_BASES, cudaMemcpyHostToDevice, st));
     PCU(cudaMemcpyAsync(d_raw, raw, count * raw_bytes, cudaMemcpyHostToDevice, st));
     uint64_t nl = 0;

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Generates tests/golden/vectors.json: fixed-input / expected-output vectors for every entry point of the hot path,
+computed by the Python oracle (oracle/paillier_ref.py) and cross-checked against the libgmp oracle where both apply.
+The reference ships no vectors at these sizes and cannot be run in this image (no Go toolchain), so
+these pin the oracle's and the engine's behaviour against regressions rather than against the Go binary.
+
+    python tools/gen_golden.py            # rewrites tests/golden/vectors.json
+"""
+import hashlib
+import json
+import os
+import random
+import sys
+from math import gcd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import paillier_ref as R          # noqa: E402
+
+KEYS = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
+H = lambda x: hex(x)
+
+
+def units(rnd, n, k):
+    out = []
+    while len(out) < k:
+        r = rnd.randrange(1, n)
+        if gcd(r, n) == 1:
+            out.append(r)
+    return out
+
+
+def main():
+    out = {"generator": "tools/gen_golden.py", "oracle": "oracle/paillier_ref.py", "cases": {}}
+    for name in ("paillier_64", "paillier_1024", "paillier_2048"):
+        rnd = random.Random("golden:" + name)
+        p, q = int(KEYS[name]["p"], 16), int(KEYS[name]["q"], 16)
+        n, n2 = p * q, (p * q) ** 2
+        hs = units(rnd, n, 1)[0]
+        sk, pk = R.keygen_from_primes(p, q, h_seed_r=hs)
+        ms = [0, 1, n - 1] + [rnd.randrange(n) for _ in range(3)]
+        rs = [1, n - 1] + units(rnd, n, 4)
+        c1 = [R.encrypt_with_r(pk, m, r).C for m, r in zip(ms, rs)]
+        m2 = [0, n2 - 1] + [rnd.randrange(n2) for _ in range(2)]
+        c2 = [R.encrypt_with_r_at_level(pk, m, r, R.ENC_LEVEL_TWO).C for m, r in zip(m2, rs)]
+        alt_r = [rnd.randrange(n) for _ in range(3)]
+        alt1 = [R.alt_encrypt_with_r_at_level(pk, m, r, R.ENC_LEVEL_ONE)[0].C for m, r in zip(ms, alt_r)]
+        alt2 = [R.alt_encrypt_with_r_at_level(pk, m, r, R.ENC_LEVEL_TWO)[0].C for m, r in zip(m2, alt_r)]
+        ks = [0, 1, 2 ** 64 - 1, rnd.getrandbits(64)]
+        cm = [R.const_mult(pk, R.Ciphertext(c), k).C for c, k in zip(c1, ks)]
+        case = {
+            "p": H(p), "q": H(q), "H": H(pk.H), "K": H(pk.K),
+            "encrypt": {"m": [H(x) for x in ms], "r": [H(x) for x in rs], "c": [H(x) for x in c1]},
+            "encrypt_level2": {"m": [H(x) for x in m2], "r": [H(x) for x in rs[:4]], "c": [H(x) for x in c2]},
+            "alt_encrypt": {"r": [H(x) for x in alt_r], "c_level1": [H(x) for x in alt1], "c_level2": [H(x) for x in alt2]},
+            "const_mult": {"k": [H(x) for x in ks], "c": [H(x) for x in cm]},
+            "add_all": H(R.add(pk, *[R.Ciphertext(c) for c in c1]).C),
+            "sub_pairs": [H(R.sub(pk, R.Ciphertext(a), R.Ciphertext(b)).C) for a, b in zip(c1[:3], c1[3:])],
+            "extract_randomness_level2": [H(R.extract_randomness(sk, R.Ciphertext(c, R.ENC_LEVEL_TWO))) for c in c2[:2]],
+        }
+        # one DDLEQ statement with two instances (both challenge values if the draw allows)
+        inner = R.encrypt_with_r(pk, ms[3], rs[2])
+        ct1 = R.encrypt_with_r_at_level(pk, inner.C, rs[3], R.ENC_LEVEL_TWO)
+        a, b = units(rnd, n, 2)
+        ct2 = R.nested_randomize_with(pk, ct1, a, b)
+        xs, ys = units(rnd, n, 4), units(rnd, n, 4)
+        proof = R.prove_ddleq(sk, 4, ct1, ct2, a, b, xs, ys)
+        assert R.verify_ddleq(pk, ct1, ct2, proof)
+        case["ddleq"] = {"ct1": H(ct1.C), "ct2": H(ct2.C), "a": H(a), "b": H(b), "x": [H(v) for v in xs], "y": [H(v) for v in ys],
+                         "alpha": [H(i.Alpha) for i in proof], "e": [H(i.E) for i in proof], "f": [H(i.F) for i in proof]}
+        out["cases"][name] = case
+    for name, l, w in (("threshold_512", 5, 3), ("threshold_2048", 8, 5), ("threshold_3072", 8, 5)):
+        rnd = random.Random("golden:" + name)
+        p, q = int(KEYS[name]["p"], 16), int(KEYS[name]["q"], 16)
+        n = p * q
+        nm = n * ((p - 1) // 2) * ((q - 1) // 2)
+        keys = R.threshold_keys_from(p, q, l, w, v_seed=rnd.randrange(2, n * n), coeffs=[rnd.randrange(nm) for _ in range(w - 1)])
+        pk = R.PublicKey(N=n)
+        ms = [0, n - 1, rnd.randrange(n)]
+        cs = [R.encrypt_with_r(pk, m, r).C for m, r in zip(ms, units(rnd, n, 3))]
+        zr = [0, rnd.randrange(n * n), rnd.randrange(n * n)]
+        k = keys[1]
+        zk = [R.partial_decryption_with_zkp(k, c, r) for c, r in zip(cs, zr)]
+        assert all(R.verify_proof(z) for z in zk)
+        shares = [[R.partial_decrypt(kk, c) for c in cs] for kk in keys[:w]]
+        tk = R.threshold_public_key(keys[0])
+        assert [R.combine_partial_decryptions(tk, [s[i] for s in shares]) for i in range(3)] == ms
+        out["cases"][name] = {
+            "p": H(p), "q": H(q), "l": l, "w": w, "V": H(k.VerificationKey), "vi": [H(v) for v in k.VerificationKeys],
+            "shares": [H(kk.Share) for kk in keys], "m": [H(x) for x in ms], "c": [H(x) for x in cs],
+            "partial_decrypt_id2": [H(z.Decryption) for z in zk], "zkp_r": [H(x) for x in zr],
+            "zkp_e": [H(z.E) for z in zk], "zkp_z": [H(z.Z) for z in zk],
+        }
+    # safe-prime candidate procedure (safe_prime.go:170-263): byte strings -> (p, q, accepted)
+    sp = {}
+    for p_bits, count in ((16, 40), (64, 400), (1024, 24)):
+        nb = (p_bits - 1 + 7) // 8
+        raws, res = [], []
+        ctr = 0
+        while len(raws) < count:
+            raw = hashlib.sha256(f"golden-sp:{p_bits}:{ctr}".encode()).digest() * ((nb + 31) // 32)
+            raw = raw[:nb]
+            ctr += 1
+            pp, qq, ok = R.safe_prime_candidate(raw, p_bits)
+            if p_bits == 64 and not ok and len(raws) >= 20 and sum(r[2] for r in res) < 2:
+                continue                  # keep the 64-bit file short but make sure it holds accepted candidates
+            raws.append(raw.hex())
+            res.append((H(pp), H(qq), ok))
+        sp[str(p_bits)] = {"raw": raws, "p": [r[0] for r in res], "q": [r[1] for r in res], "ok": [r[2] for r in res]}
+    out["safe_prime"] = sp
+    path = os.path.join(ROOT, "tests", "golden", "vectors.json")
+    json.dump(out, open(path, "w"), indent=0)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
