@@ -201,6 +201,11 @@ int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const v
  * all-gathered [share][ciphertext] buffer in place (one share-holder per GPU) */
 int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, void* m);
 int pgpu_pdec_zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok);
+/* VerifyProof for the proofs of k servers in one batch: n_per_id proofs per server, grouped by server in the order of
+ * ids[0..k) (record i belongs to server ids[i / n_per_id]); c, dec, e, z, ok hold k * n_per_id records.  Used by the
+ * combiner of a threshold round, which checks every share-holder's proofs of its ciphertext slice at once. */
+int pgpu_pdec_zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const void* c, const void* dec, const void* e,
+                                   const void* z, uint8_t* ok);
 
 /* ---- introspection used by bench.py ------------------------------------ */
 /* number of kernels this context has launched so far */

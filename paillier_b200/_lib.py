@@ -79,6 +79,7 @@ SIGNATURES = {
     "pgpu_primes_last_error": (C.c_char_p, []),
     "pgpu_combine_strided_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _sz, _p]),
     "pgpu_pdec_zkp_verify_dev": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
+    "pgpu_pdec_zkp_verify_multi_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p, _p]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),

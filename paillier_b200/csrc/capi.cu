@@ -727,6 +727,16 @@ int pgpu_pdec_zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const void* c,
     GUARD_END(ctx)
 }
 
+int pgpu_pdec_zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const void* c, const void* dec, const void* e,
+                                   const void* z, uint8_t* ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids) && (n_per_id == 0 || k == 0 || (c && dec && e && z && ok)), "pgpu_pdec_zkp_verify_multi_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return zkp_verify_multi_dev(ctx, n_per_id, k, ids, (const uint32_t*)c, (const uint32_t*)dec, (const uint32_t*)e, (const uint32_t*)z, ok);
+    GUARD_END(ctx)
+}
+
 int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches) {
     if (!ctx || !launches) return fail(nullptr, PGPU_ERR_ARG, "null argument");
     *launches = ctx->launches;

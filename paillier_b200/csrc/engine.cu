@@ -598,16 +598,26 @@ int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t
 }
 
 // VerifyProof (thresholdkey.go:278-311)
-int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok) {
+// proofs of k servers, n_per_id each, grouped by server: item i belongs to ids[i / n_per_id].  c, dec, e, z, ok hold
+// k * n_per_id records in that order.
+int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
+                         const uint32_t* z, uint8_t* ok) {
     if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "VerifyProof: no threshold key loaded");
-    if (id < 1 || (size_t)id > ctx->tk_vi.size()) return fail(ctx, PGPU_ERR_ARG, "VerifyProof: no verification key for this server id");   // VerificationKeys[ID-1] :305
+    for (int j = 0; j < k; ++j)
+        if (ids[j] < 1 || (size_t)ids[j] > ctx->tk_vi.size())
+            return fail(ctx, PGPU_ERR_ARG, "VerifyProof: no verification key for this server id");   // VerificationKeys[ID-1] :305
+    const size_t count = n_per_id * (size_t)k;
+    if (count == 0) return PGPU_OK;
     ModCtx& M = ctx->m_n2;
     const uint32_t S = M.sh.S, ZL = z_limbs(ctx);
     int rc;
     DEVBUF(t0, ctx, count * S); DEVBUF(t1, ctx, count * S); DEVBUF(t2, ctx, count * S);
-    DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(kv, ctx, S); DEVBUF(kvi, ctx, S); DEVBUF(bad, ctx, 1); DEVBUF(e2, ctx, count * 8);
-    if ((rc = upload(ctx, kv.p, ctx->tk_v.limbs(S)))) return rc;
-    if ((rc = upload(ctx, kvi.p, ctx->tk_vi[id - 1].limbs(S)))) return rc;
+    DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(kvi, ctx, (size_t)k * S); DEVBUF(bad, ctx, 1); DEVBUF(e2, ctx, count * 8);
+    {
+        std::vector<uint32_t> vk;
+        for (int j = 0; j < k; ++j) { auto l = ctx->tk_vi[ids[j] - 1].limbs(S); vk.insert(vk.end(), l.begin(), l.end()); }
+        if ((rc = upload(ctx, kvi.p, vk))) return rc;
+    }
     // a = (c^4)^Z * ((c_i^2)^E)^-1 mod n^2        verifyPart1 :293-302
     if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), t0.p))) return rc;
     if ((rc = modexp_items_dev(ctx, M, count, t0.p, z, ZL, t1.p))) return rc;
@@ -618,13 +628,18 @@ int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const
     // b = V^Z * (v_i^E)^-1 mod n^2                verifyPart2 :304-311
     if ((rc = ensure_fix_v(ctx))) return rc;
     if ((rc = modexp_fixed_dev(ctx, M, ctx->fix_v, count, ExpDesc{z, ZL, 32 * ZL, nullptr}, t1.p))) return rc;   // V^Z (fixed base)
-    if ((rc = modexp_items_dev(ctx, M, count, kvi.p, e, 8, t2.p, true))) return rc;
+    if ((rc = modexp_items_io(ctx, M, count, IoDesc{kvi.p, S, S, (uint32_t)n_per_id}, ExpDesc{e, 8, 256, nullptr}, t2.p))) return rc;
     if ((rc = modinv_batch_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
     if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, b.p))) return rc;
     if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e2.p))) return rc;
     CU(ctx, equal_launch(e, e2.p, 8, (uint32_t)count, ok, ctx->stream));
     ctx->launches++;
     return PGPU_OK;
+}
+
+// VerifyProof (thresholdkey.go:278-311) for proofs of one server
+int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok) {
+    return zkp_verify_multi_dev(ctx, count, 1, &id, c, dec, e, z, ok);
 }
 
 // CombinePartialDecryptions (thresholdkey.go:149-161); decs = k batches of `count` n^2-width records, one per share

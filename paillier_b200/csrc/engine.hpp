@@ -193,6 +193,8 @@ uint32_t z_limbs(const pgpu_ctx* ctx);
 int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z);
 int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok);
 // share j's batch starts at record j*share_stride (0 = count: tightly packed)
+int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
+                         const uint32_t* z, uint8_t* ok);
 int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out, size_t share_stride = 0);
 int set_device(pgpu_ctx* ctx);
 

@@ -30,7 +30,8 @@ def shard_range(count: int, world: int, rank: int) -> Tuple[int, int]:
 def threshold_round(dist, rank: int, world: int, count: int, record_width: int,
                     partial_decrypt: Callable[[], "torch.Tensor"],
                     combine: Callable[["torch.Tensor", Sequence[int], int, int], "torch.Tensor"],
-                    verify: Optional[Callable[["torch.Tensor", int], bool]] = None):
+                    verify: Optional[Callable[["torch.Tensor", int], bool]] = None,
+                    verify_all: Optional[Callable[["torch.Tensor"], Sequence[bool]]] = None):
     """One threshold-decryption round.
 
     partial_decrypt() -> uint8 tensor [count * record_width]: this rank's share applied to every ciphertext.
@@ -38,6 +39,7 @@ def threshold_round(dist, rank: int, world: int, count: int, record_width: int,
         [world][count][record_width] buffer using the shares `ids` (server ids, rank r holds id r+1).
     verify(gathered, r) (optional) -> whether rank r's partials are to be used (CombinePartialDecryptionsZKP,
         thresholdkey.go:164-172 drops shares whose proof fails).
+    verify_all(gathered) (optional) -> one verdict per rank, all shares checked in one batch (takes precedence).
     Returns (plaintext slice tensor, (lo, hi))."""
     import torch
     mine = partial_decrypt()
@@ -48,7 +50,11 @@ def threshold_round(dist, rank: int, world: int, count: int, record_width: int,
         dist.all_gather_into_tensor(gathered, mine.contiguous())
     else:
         gathered.copy_(mine)
-    ids = [r + 1 for r in range(world) if verify is None or verify(gathered, r)]
+    if verify_all is not None:
+        verdicts = list(verify_all(gathered))
+        ids = [r + 1 for r in range(world) if verdicts[r]]
+    else:
+        ids = [r + 1 for r in range(world) if verify is None or verify(gathered, r)]
     lo, hi = shard_range(count, world, rank)
     return combine(gathered, ids, lo, hi), (lo, hi)
 
@@ -115,6 +121,19 @@ def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, wit
         stream.synchronize()
         return bool(ok[:n].all().item()) if n else True
 
+    def verify_all(gathered):
+        n = hi - lo
+        if n == 0:
+            return [True] * world
+        rows = lambda buf, w: torch.cat([buf[(r * count + lo) * w:(r * count + hi) * w] for r in range(world)])
+        dec, e, z = rows(gathered, w2), rows(proofs["e"], 32), rows(proofs["z"], tsk.w_z)
+        c_rep = c_dev[lo * w2:hi * w2].repeat(world)
+        ok = torch.zeros(world * n, dtype=torch.uint8, device=c_dev.device)
+        idarr = (C.c_int * world)(*range(1, world + 1))
+        check(lib.pgpu_pdec_zkp_verify_multi_dev(tsk._ctx, n, world, idarr, vp(c_rep), vp(dec), vp(e), vp(z), vp(ok)), tsk._ctx)
+        stream.synchronize()
+        return [bool(v) for v in ok.view(world, n).all(dim=1).cpu()]
+
     def combine(gathered, ids, lo, hi):
         n = hi - lo
         out = torch.empty(max(n, 1) * wn, dtype=torch.uint8, device=c_dev.device)
@@ -130,7 +149,7 @@ def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, wit
         return out[:n * wn]
 
     with torch.cuda.stream(stream):
-        res = threshold_round(dist, rank, world, count, w2, partial_decrypt, combine, verify if with_zkp_r is not None else None)
+        res = threshold_round(dist, rank, world, count, w2, partial_decrypt, combine, None, verify_all if with_zkp_r is not None else None)
     stream.synchronize()
     check(lib.pgpu_ctx_set_stream(tsk._ctx, None), tsk._ctx)
     return res

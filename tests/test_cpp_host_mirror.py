@@ -1,0 +1,56 @@
+"""The C++ host mirror (include/paillier_b200.hpp): it must compile and link against libpaillier_b200.so on any box
+(CPU test) and reproduce the golden vectors through the GPU (gpu test)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
+V = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))
+I = lambda s: int(s, 16)
+
+
+def _build():
+    libdir = os.path.join(ROOT, "paillier_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"),
+           "-o", EXE, "-L", libdir, "-lpaillier_b200", f"-Wl,-rpath,{libdir}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+
+
+def test_host_mirror_compiles_and_links():
+    _build()
+    assert os.path.exists(EXE)
+
+
+def _input():
+    lines = []
+    for name in ("paillier_64", "paillier_2048"):
+        c = V["cases"][name]
+        p, q = I(c["p"]), I(c["q"])
+        e = c["encrypt"]
+        lines += ["paillier", hex(p * q), hex((p - 1) * (q - 1)), "4"]
+        for i in range(4):
+            lines += [e["m"][i], e["r"][i], e["c"][i], c["const_mult"]["k"][i], c["const_mult"]["c"][i]]
+        # add_all over the first 4 ciphertexts
+        acc = 1
+        for x in e["c"][:4]:
+            acc = acc * I(x) % (p * q) ** 2
+        lines.append(hex(acc))
+    for name in ("threshold_512",):
+        c = V["cases"][name]
+        n = I(c["p"]) * I(c["q"])
+        lines += ["threshold", hex(n), str(c["l"]), str(c["w"]), c["V"]] + c["vi"]
+        for i in range(c["w"]):
+            lines += [str(i + 1), c["shares"][i]]
+        lines += [str(len(c["c"]))] + c["c"] + c["m"] + c["zkp_r"]
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.gpu
+def test_host_mirror_reproduces_golden_vectors():
+    _build()
+    r = subprocess.run([EXE], input=_input(), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "host mirror ok" in r.stdout
