@@ -312,6 +312,17 @@ def main() -> None:
             barrier()
         breakdown["pdec_zkp_prove_per_s"] = world * zcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         breakdown["pdec_zkp_items"] = zcount
+        # VerifyProof (thresholdkey.go:278-311) of those proofs
+        zok = torch.zeros(zcount, dtype=torch.uint8, device=dev)
+        for timed in (False, True):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            check(lib.pgpu_pdec_zkp_verify_dev(tsk._ctx, zcount, tsk.ID, vp(zin), vp(zout), vp(ze), vp(zz), vp(zok)), tsk._ctx)
+            e1.record(stream)
+            barrier()
+        assert bool(zok.all().item()), "ZKP verification rejected an honest proof"
+        breakdown["pdec_zkp_verify_per_s"] = world * zcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         tsk.close()
         # BASELINE config 3: encrypted dot product with 64-bit scalars (ConstMult + Add) over the ciphertexts of this step
         dcount = max(1, count // 4)
@@ -344,6 +355,28 @@ def main() -> None:
         breakdown["alt_enc_e2e_per_s"] = world * acount / max_over_ranks(adt)
         breakdown["alt_enc_items"] = acount
         apk.close()
+        # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI
+        if rank == 0:
+            from paillier_b200.api import ENC_LEVEL_TWO
+            dn, dsecpar = 256, 8
+            ints = lambda a, w: [int.from_bytes(a[i * w:(i + 1) * w].tobytes(), "little") for i in range(len(a) // w)]
+            rr = ints(synth.randomness(dn * (4 + 2 * dsecpar), n, w_n, seed + 7), w_n)
+            inner = sk.EncryptWithRBatch(ints(synth.plaintexts(dn, n, w_n, seed + 7), w_n), rr[:dn])
+            ct1 = sk.EncryptWithRAtLevelBatch([c.C for c in inner], rr[dn:2 * dn], ENC_LEVEL_TWO)
+            As, Bs = rr[2 * dn:3 * dn], rr[3 * dn:4 * dn]
+            ct2 = sk.NestedRandomizeWithBatch(ct1, As, Bs)
+            xs = [rr[4 * dn + i * dsecpar:4 * dn + (i + 1) * dsecpar] for i in range(dn)]
+            ys = [rr[(4 + dsecpar) * dn + i * dsecpar:(4 + dsecpar) * dn + (i + 1) * dsecpar] for i in range(dn)]
+            sk.ProveDDLEQBatch(dsecpar, ct1[:2], ct2[:2], As[:2], Bs[:2], xs[:2], ys[:2])
+            t0 = time.perf_counter()
+            proofs = sk.ProveDDLEQBatch(dsecpar, ct1, ct2, As, Bs, xs, ys)
+            t1 = time.perf_counter()
+            okd = sk.VerifyDDLEQProofBatch(ct1, ct2, proofs)
+            t2 = time.perf_counter()
+            assert all(okd), "DDLEQ verification rejected an honest proof"
+            breakdown["ddleq_prove_instances_per_s"] = dn * dsecpar / (t1 - t0)
+            breakdown["ddleq_verify_instances_per_s"] = dn * dsecpar / (t2 - t1)
+            breakdown["ddleq_instances"] = dn * dsecpar
         # BASELINE configs[4]: safe-prime candidate procedure (sieve + Miller-Rabin + Fermat) at 1024-bit p
         if rank == 0:
             from paillier_b200.keygen import safe_prime_scan
@@ -392,6 +425,15 @@ def main() -> None:
                     "peak_gbs": mp.get("hbm_gbs"), "frac": (alg_bytes / (enc_ms * 1e-3) / 1e9 / mp["hbm_gbs"]) if mp.get("hbm_gbs") else None},
             "traffic": traffic,
             "imad_peak": peak,
+            "other_kernels": {
+                "crt_decrypt (2 x powm_vm<4,16> + crt_combine)": {
+                    "achieved": dec_macs * count / (dec_ms * 1e-3) / 1e12,
+                    "frac": (dec_macs * count / (dec_ms * 1e-3) / 1e12 / peak_t) if peak_t else None},
+                **({"partial_decrypt (powm_vm<4,32>)": {
+                    "achieved": breakdown["pdec_program"]["mac32_per_item"] * breakdown["pdec_per_s"] / world / 1e12,
+                    "frac": (breakdown["pdec_program"]["mac32_per_item"] * breakdown["pdec_per_s"] / world / 1e12 / peak_t) if peak_t else None}}
+                   if "pdec_per_s" in breakdown else {}),
+            },
         }
         cpu = None
         if not args.no_extras:
