@@ -31,6 +31,8 @@ class ThresholdKeyGenerator:
     rng: random.Random = field(default_factory=lambda: random.Random(20260101))
     p: int = 0
     q: int = 0
+    batch: int = 1 << 15          # safe-prime candidates per GPU call
+    max_batches: int = 4096
 
     def __post_init__(self):
         if self.PublicKeyBitLength % 2 == 1:
@@ -43,8 +45,25 @@ class ThresholdKeyGenerator:
         self.p, self.q = p, q
         return self
 
+    def generateSafePrimes(self, device: int = 0):
+        """thresholdkey_generator.go:88-99: a safe prime of PublicKeyBitLength/2 bits, candidates tested on the GPU in
+        stream order of this generator's randomness"""
+        reader = lambda nbytes: self.rng.randbytes(nbytes)
+        return GenerateSafePrime(self.PublicKeyBitLength // 2, reader, batch=self.batch, max_batches=self.max_batches, device=device)
+
+    def initPsAndQs(self, device: int = 0) -> None:
+        """thresholdkey_generator.go:133-144 (retry until p, q, p1, q1 are pairwise usable, :120-131)"""
+        while True:
+            self.p, _ = self.generateSafePrimes(device)
+            self.q, _ = self.generateSafePrimes(device)
+            p1, q1 = (self.p - 1) // 2, (self.q - 1) // 2
+            if self.p != self.q and self.p != q1 and p1 != self.q:
+                return
+
     def GenerateKeys(self, device: int = 0) -> List[ThresholdSecretKey]:
         """thresholdkey_generator.go:47-55"""
+        if not self.p or not self.q:
+            self.initPsAndQs(device)
         p, q = self.p, self.q
         p1, q1 = (p - 1) // 2, (q - 1) // 2
         if p == q or p == q1 or p1 == q:                                           # :120-131
@@ -134,3 +153,45 @@ def GenerateSafePrime(bitLen: int, random_reader, batch: int = 1 << 14, max_batc
             if good:
                 return p, q
     raise TimeoutError(f"generator gave up after {max_batches} batches of {batch} candidates")   # :101-103
+
+
+# ---- paillier.go KeyGen ----------------------------------------------------------------------------------
+
+def _random_prime_3mod4(bits: int, rng, device: int, batch: int = 4096) -> int:
+    """Stand-in for crypto/rand.Prime(bits) followed by KeyGen's `= 3 (mod 4)` filter (paillier.go:122-139): random odd
+    candidates with the two top bits set (as rand.Prime does) and the low two bits set, Miller-Rabin (20 rounds) for the
+    whole batch on the GPU, first survivor in stream order wins."""
+    while True:
+        cands = [rng.getrandbits(bits) | (3 << (bits - 2)) | 3 for _ in range(batch)]
+        small = (3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53)
+        keep = [c for c in cands if all(c % s for s in small)]
+        for c, ok in zip(keep, miller_rabin(bits, keep, 20, device)):
+            if ok:
+                return c
+
+
+def KeyGen(secparam: int, rng: Optional[random.Random] = None, device: int = 0):
+    """paillier.go:106-179: returns (SecretKey, PublicKey) mirrors bound to `device`; p, q = 3 (mod 4), distinct;
+    g = n+1; K = 2^(secparam/2); H = r^2 mod n for a random unit r (utils.go:36-59)."""
+    from math import gcd
+    from .api import PublicKey as _PK, SecretKey as _SK
+    if secparam % 2 != 0:
+        raise ValueError("KeyGen: secparam must be divisible by 2")           # :108-110
+    if secparam < 64:
+        raise ValueError("KeyGen: secparam must be at least 64 bits")         # :112-114
+    rng = rng or random.Random()
+    while True:
+        p = _random_prime_3mod4(secparam // 2, rng, device)
+        q = _random_prime_3mod4(secparam // 2, rng, device)
+        if p != q:                                                             # :135-137
+            break
+    n = p * q
+    k = 1 << (secparam // 2)                                                   # :151
+    while True:                                                                # utils.go:36-49
+        r = rng.randrange(n)
+        if r != 0 and gcd(r, n) == 1:
+            break
+    h = r * r % n                                                              # utils.go:53-59
+    sk = _SK(n, p=p, q=q, device=device, H=h, K=k)
+    pk = _PK(n, device=device, H=h, K=k)
+    return sk, pk

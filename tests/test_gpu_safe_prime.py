@@ -91,3 +91,31 @@ def test_generate_safe_prime_first_in_stream_order():
         assert (p, q) == first[:2]
     with pytest.raises(ValueError):
         GenerateSafePrime(5, reader)
+
+
+def test_keygen_and_threshold_keygen_end_to_end():
+    # paillier.go:106-179 and thresholdkey_generator.go:47-55 with the prime searches on the GPU
+    from paillier_b200.api import ENC_LEVEL_ONE
+    from paillier_b200.keygen import KeyGen, ThresholdKeyGenerator
+    rnd = random.Random(12)
+    sk, pk = KeyGen(128, rnd)
+    assert sk.N.bit_length() in (127, 128) and sk.Lambda % 4 == 0 and sk.K == 1 << 64
+    ms = [0, 1, sk.N - 1, 12345]
+    cts = pk.EncryptWithRBatch(ms, [3, 5, 7, 11])
+    assert sk.DecryptBatch(cts) == ms
+    alt = pk.AltEncryptWithRAtLevelBatch(ms, [rnd.randrange(sk.N) for _ in ms], ENC_LEVEL_ONE)
+    assert sk.DecryptBatch(alt) == ms
+    sk.close(); pk.close()
+    with pytest.raises(ValueError):
+        KeyGen(63)
+    with pytest.raises(ValueError):
+        KeyGen(62)
+    # threshold keys of a 64-bit n: two 32-bit safe primes found on the GPU (thresholdkey_test.go uses 32-bit keys)
+    keys = ThresholdKeyGenerator(64, 4, 3, rng=random.Random(8), batch=2048).GenerateKeys()
+    n = keys[0].N
+    assert n.bit_length() in (63, 64)
+    cs = [c.C for c in keys[0].EncryptWithRBatch([42, 0, n - 1], [5, 7, 9])]
+    parts = [k.PartialDecryptBatch(cs) for k in keys[:3]]
+    assert keys[0].CombinePartialDecryptionsBatch(parts) == [42, 0, n - 1]
+    for k in keys:
+        k.close()
