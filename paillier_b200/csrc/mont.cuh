@@ -22,9 +22,6 @@
 #pragma once
 #include <cstdint>
 
-#ifndef PGPU_SQR_MAXL
-#define PGPU_SQR_MAXL 16   // largest limbs-per-lane that uses the dedicated squaring
-#endif
 #ifndef PGPU_FENCE
 #define PGPU_FENCE 3   // rows of a block product in flight (see Mont::prod_row)
 #endif
@@ -74,12 +71,7 @@ __device__ __forceinline__ uint64_t lookahead(uint32_t g, uint32_t p) {
 // only 2 warps per scheduler fit, every warp instruction then costs ~6.5 cycles of issue latency, and a loop needs
 // >= 81 % IMAD.WIDE in its instruction mix to saturate the multiplier pipe -- mul() has 84 %, the squaring's reduction
 // loop (half the multiplies per row, same per-row bookkeeping) 73 % -- so mul(a, a) stays faster there.
-template <int TPI_, int L_> struct SqrShape { static constexpr bool value = (TPI_ == 4) && (L_ % 8 == 0) && (L_ <= PGPU_SQR_MAXL); };
-// 0: plain (modulus in registers, no shared memory).  1: dedicated squaring, modulus and both slot accumulators in shared
-// memory.  2: "lean" -- for L = 32, where registers and shared memory must allow a third block per SM: modulus re-read from
-// global memory (L1/L2 hits), multiplier operand b of mul() broadcast from shared memory instead of shuffles, one slot
-// accumulator stays in registers during the block products.
-template <int TPI_, int L_> struct MontMode { static constexpr int value = !SqrShape<TPI_, L_>::value ? 0 : (L_ >= 24 ? 2 : 1); };
+template <int TPI_, int L_> struct SqrShape { static constexpr bool value = (TPI_ == 4) && (L_ % 8 == 0) && (L_ <= 16); };
 
 __device__ __forceinline__ uint4 lds_v4_volatile(const uint4* p) {
     uint4 v;
@@ -90,10 +82,8 @@ __device__ __forceinline__ uint4 lds_v4_volatile(const uint4* p) {
 
 // NSM: the modulus limbs are kept in shared memory and fetched at every use instead of occupying L registers
 // for the whole kernel (needed by the dedicated squaring, whose product phase has no use for them).
-template <int TPI, int L, int MODE = 0>
+template <int TPI, int L, bool NSM = false>
 struct Mont {
-    static constexpr bool NSM = MODE != 0;
-    static constexpr bool LEAN = MODE == 2;
     static_assert((L % 2) == 0, "L must be even");
     static_assert(TPI >= 1 && TPI <= 32 && (TPI & (TPI - 1)) == 0, "TPI must be a power of two");
     static constexpr int S = TPI * L;
@@ -101,7 +91,6 @@ struct Mont {
 
     uint32_t n[L];   // this lane's limbs of the modulus
     uint32_t np0;    // -n^-1 mod 2^32
-    const uint32_t* nptr;   // this lane's limbs of the modulus in global memory
     uint64_t np64;   // -n^-1 mod 2^64 (two quotient digits at a time in the squaring's reduction)
     int t;           // lane index inside the group
     int gshift;      // bit position of the group's lane 0 inside the warp
@@ -111,7 +100,6 @@ struct Mont {
         t = lane & (TPI - 1);
         gshift = lane & ~(TPI - 1);
         np0 = np0_;
-        nptr = nmod + t * L;
         {
             const uint64_t n64 = (uint64_t)nmod[0] | ((uint64_t)nmod[1] << 32);
             uint64_t inv = (uint64_t)(0u - np0_);          // n^-1 mod 2^32
@@ -124,14 +112,7 @@ struct Mont {
 
     // this lane's limbs of the modulus
     __device__ __forceinline__ void fetch_n(uint32_t (&nn)[L]) const {
-        if constexpr (LEAN) {
-#pragma unroll
-            for (int k4 = 0; k4 < L / 4; ++k4) {
-                uint4 q;
-                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(nptr + 4 * k4) : "memory");
-                nn[4 * k4] = q.x; nn[4 * k4 + 1] = q.y; nn[4 * k4 + 2] = q.z; nn[4 * k4 + 3] = q.w;
-            }
-        } else if constexpr (NSM) {
+        if constexpr (NSM) {
 #pragma unroll
             for (int k4 = 0; k4 < L / 4; ++k4) {
                 const uint4 q = lds_v4_volatile(sn + k4 * 32 + wl);
@@ -200,31 +181,15 @@ struct Mont {
     // r = a * b * R^-1 mod n,  R = 2^(32*S).  Requires a < R, b < n (or a*b < n*R).
     __device__ __forceinline__ void mul(uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
         uint32_t E[L], O[L], Ec = 0, Oc = 0, nn[L];
-        if constexpr (LEAN) {
-            // b goes to shared memory and is broadcast from there: 32 registers and one shuffle per row less
-#pragma unroll
-            for (int k4 = 0; k4 < L / 4; ++k4) sa[k4 * 32 + wl] = make_uint4(b[4 * k4], b[4 * k4 + 1], b[4 * k4 + 2], b[4 * k4 + 3]);
-            __syncwarp();
-        }
         fetch_n(nn);
 #pragma unroll
         for (int k = 0; k < L; ++k) { E[k] = 0; O[k] = 0; }
 
 #pragma unroll 1
         for (int u = 0; u < TPI; ++u) {
-            uint32_t bq[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int k = 0; k < L; ++k) {
-                uint32_t bj;
-                if constexpr (LEAN) {
-                    if ((k & 3) == 0) {
-                        const uint4 q4 = sa[(k >> 2) * 32 + gb + u];
-                        bq[0] = q4.x; bq[1] = q4.y; bq[2] = q4.z; bq[3] = q4.w;
-                    }
-                    bj = bq[k & 3];
-                } else {
-                    bj = __shfl_sync(FULL_MASK, b[k], u, TPI);
-                }
+                const uint32_t bj = __shfl_sync(FULL_MASK, b[k], u, TPI);
                 // --- one-limb shift of the previous state, fused into a*bj ---
                 uint32_t recv = __shfl_down_sync(FULL_MASK, E[0], 1, TPI);
                 if (t == TPI - 1) recv = 0;
@@ -286,9 +251,9 @@ struct Mont {
         for (int k = 1; k < L - 1; ++k) addc_cc(r[k], O[k], E[k + 1]);
         addc_cc(r[L - 1], O[L - 1], top_lo);
         addc(ov, Oc, top_hi);
-        if constexpr (LEAN) __syncwarp();     // every lane is done reading b before the operand rows are reused
         resolve_reduce(r, ov);
     }
+
 
     // ------------------------------------------------------------------------------------------------
     // Dedicated Montgomery squaring (TPI == 4): r = a * a * R^-1 mod n with ~19 % fewer multiply-accumulates
@@ -307,8 +272,7 @@ struct Mont {
     static constexpr bool HAS_SQR = NSM && SqrShape<TPI, L>::value;
     static constexpr int SQR_A4 = L / 4;            // uint4 rows holding one operand per lane
     static constexpr int SQR_X4 = 2 * L / 4;        // uint4 rows of one exchange buffer per lane
-    // operand + exchange + one row of zeros + (mode 1: modulus + stash of both accumulators | mode 2: stash of one)
-    static constexpr int SQR_ROWS = SQR_A4 + SQR_X4 + 1 + (LEAN ? SQR_A4 : SQR_A4 + SQR_X4);
+    static constexpr int SQR_ROWS = SQR_A4 + SQR_X4 + 1 + SQR_A4 + SQR_X4;   // + one row of zeros + the modulus + accumulator stash
     static constexpr size_t SQR_SMEM_PER_WARP = (size_t)SQR_ROWS * 32 * 16;
 
     uint4* sa;      // [SQR_A4][32] operand rows of this warp
@@ -325,16 +289,11 @@ struct Mont {
         sa = warp_smem;
         sx = warp_smem + SQR_A4 * 32;
         sz = warp_smem + (SQR_A4 + SQR_X4) * 32;
+        sn = sz + 32;
+        ss = sn + SQR_A4 * 32;
         sz[wl] = make_uint4(0, 0, 0, 0);
-        if constexpr (LEAN) {
-            sn = nullptr;
-            ss = sz + 32;
-        } else {
-            sn = sz + 32;
-            ss = sn + SQR_A4 * 32;
 #pragma unroll
-            for (int k4 = 0; k4 < L / 4; ++k4) sn[k4 * 32 + wl] = make_uint4(n[4 * k4], n[4 * k4 + 1], n[4 * k4 + 2], n[4 * k4 + 3]);
-        }
+        for (int k4 = 0; k4 < L / 4; ++k4) sn[k4 * 32 + wl] = make_uint4(n[4 * k4], n[4 * k4 + 1], n[4 * k4 + 2], n[4 * k4 + 3]);
         __syncwarp();
     }
 
@@ -428,29 +387,19 @@ struct Mont {
     }
 
     // the two slot accumulators leave the register file while a block product needs it
-    // (lean mode: only q moves, p stays in registers)
     __device__ __forceinline__ void stash(const uint32_t (&p)[L], const uint32_t (&q)[L]) {
 #pragma unroll
         for (int k4 = 0; k4 < L / 4; ++k4) {
-            if constexpr (LEAN) {
-                ss[k4 * 32 + wl] = make_uint4(q[4 * k4], q[4 * k4 + 1], q[4 * k4 + 2], q[4 * k4 + 3]);
-            } else {
-                ss[k4 * 32 + wl] = make_uint4(p[4 * k4], p[4 * k4 + 1], p[4 * k4 + 2], p[4 * k4 + 3]);
-                ss[(L / 4 + k4) * 32 + wl] = make_uint4(q[4 * k4], q[4 * k4 + 1], q[4 * k4 + 2], q[4 * k4 + 3]);
-            }
+            ss[k4 * 32 + wl] = make_uint4(p[4 * k4], p[4 * k4 + 1], p[4 * k4 + 2], p[4 * k4 + 3]);
+            ss[(L / 4 + k4) * 32 + wl] = make_uint4(q[4 * k4], q[4 * k4 + 1], q[4 * k4 + 2], q[4 * k4 + 3]);
         }
     }
     __device__ __forceinline__ void unstash(uint32_t (&p)[L], uint32_t (&q)[L]) {
 #pragma unroll
         for (int k4 = 0; k4 < L / 4; ++k4) {
-            if constexpr (LEAN) {
-                const uint4 v = lds_v4_volatile(ss + k4 * 32 + wl);
-                q[4 * k4] = v.x; q[4 * k4 + 1] = v.y; q[4 * k4 + 2] = v.z; q[4 * k4 + 3] = v.w;
-            } else {
-                const uint4 u = lds_v4_volatile(ss + k4 * 32 + wl), v = lds_v4_volatile(ss + (L / 4 + k4) * 32 + wl);
-                p[4 * k4] = u.x; p[4 * k4 + 1] = u.y; p[4 * k4 + 2] = u.z; p[4 * k4 + 3] = u.w;
-                q[4 * k4] = v.x; q[4 * k4 + 1] = v.y; q[4 * k4 + 2] = v.z; q[4 * k4 + 3] = v.w;
-            }
+            const uint4 u = lds_v4_volatile(ss + k4 * 32 + wl), v = lds_v4_volatile(ss + (L / 4 + k4) * 32 + wl);
+            p[4 * k4] = u.x; p[4 * k4 + 1] = u.y; p[4 * k4 + 2] = u.z; p[4 * k4 + 3] = u.w;
+            q[4 * k4] = v.x; q[4 * k4 + 1] = v.y; q[4 * k4 + 2] = v.z; q[4 * k4 + 3] = v.w;
         }
     }
 
@@ -470,15 +419,18 @@ struct Mont {
             // is D_t (P = low slot X^t, Q = high slot X^(t+4)).  One loop body serves both full-size products, which keeps
             // the code of the whole squaring within reach of the instruction cache.
             uint32_t p_ov = 0, q_ov = 0;
-            uint32_t P[L], Q[L];
+            {
+                uint32_t Z[L];
 #pragma unroll
-            for (int k = 0; k < L; ++k) { P[k] = 0; Q[k] = 0; }
-            stash(P, Q);
+                for (int k = 0; k < L; ++k) Z[k] = 0;
+                stash(Z, Z);
+            }
 #pragma unroll 1
             for (int round = 0; round < 2; ++round) {
                 // O_t = A_t * A_(t+1 mod 4), base slot t + (t+1 mod 4)   |   D_t = A_t^2, base slot 2t
                 block_product_to_smem<L>(a, sa, round == 0 ? gb + ((t + 1) & 3) : wl, 0);
                 __syncwarp();
+                uint32_t P[L], Q[L];
                 unstash(P, Q);
                 if (round == 0) {
                     const int s1 = (t == 0) ? 1 : (t == 1) ? 2 : (t == 2) ? 0 : 1;
@@ -534,9 +486,8 @@ struct Mont {
                 stash(P, Q);
                 __syncwarp();
             }
-            unstash(P, Q);
-            uint32_t (&lo)[L] = P;
-            uint32_t (&hi)[L] = Q;
+            uint32_t lo[L], hi[L];
+            unstash(lo, hi);
             const uint32_t lo_ov = p_ov, hi_ov = q_ov;
             // ---- phase 2: Montgomery reduction of the low half (lane t: lo + lo_ov * X), sliding window as in mul()
             uint32_t E[L], O[L], Ec = 0, Oc = lo_ov, nn[L];

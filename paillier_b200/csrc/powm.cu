@@ -58,9 +58,9 @@ __device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uin
 }
 
 template <int TPI, int L>
-__global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? (MontMode<TPI, L>::value == 2 ? 3 : 2) : 1)) powm_vm(const VmParams P) {
+__global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 : 1)) powm_vm(const VmParams P) {
     constexpr int S = TPI * L;
-    using MontT = Mont<TPI, L, MontMode<TPI, L>::value>;
+    using MontT = Mont<TPI, L, SqrShape<TPI, L>::value>;
     MontT M;
     const uint32_t n_groups = P.n_groups;
     const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? (Mo
 
 template <int TPI, int L>
 constexpr size_t vm_smem_bytes() {
-    using MontT = Mont<TPI, L, MontMode<TPI, L>::value>;
+    using MontT = Mont<TPI, L, SqrShape<TPI, L>::value>;
     return MontT::HAS_SQR ? MontT::SQR_SMEM_PER_WARP * (VM_BLOCK_THREADS / 32) : 0;
 }
 
