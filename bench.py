@@ -325,7 +325,7 @@ def main() -> None:
         breakdown["pdec_zkp_verify_per_s"] = world * zcount / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         tsk.close()
         # BASELINE config 3: encrypted dot product with 64-bit scalars (ConstMult + Add) over the ciphertexts of this step
-        dcount = max(1, count // 4)
+        dcount = count
         k64 = torch.from_numpy(synth.scalars_u64(dcount, seed).view(np.int64).copy()).to(dev)
         dot = torch.empty(w_n2, dtype=torch.uint8, device=dev)
         for timed in (False, True):

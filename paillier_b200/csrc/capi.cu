@@ -211,6 +211,10 @@ int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t*
     REQUIRE(ctx, ctx && out && (count == 0 || (c && k)), "pgpu_dot_u64: null argument");
     int rc; if ((rc = set_device(ctx))) return rc;
     TimedScope ts(ctx);
+    // large batches: Pippenger's bucket method (17 multiplications per term instead of ~94); small ones: ConstMult + Add
+    const size_t resident = (size_t)vm_full_blocks(ctx, ctx->m_n2) * (VM_BLOCK_THREADS / ctx->m_n2.sh.tpi);
+    if (count >= 16 * resident && !getenv("PGPU_DOT_SIMPLE"))
+        return dot_pippenger_dev(ctx, count, (const uint32_t*)c, (const uint32_t*)k, 2, (uint32_t*)out);
     void* tmp;
     if ((rc = stage(ctx, 2, std::max<size_t>(count, 1) * ctx->m_n2.sh.S * 4, &tmp))) return rc;
     if ((rc = modexp_items_dev(ctx, ctx->m_n2, count, (const uint32_t*)c, (const uint32_t*)k, 2, (uint32_t*)tmp))) return rc;

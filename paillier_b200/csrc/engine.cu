@@ -162,13 +162,13 @@ int ensure_table(pgpu_ctx* ctx, size_t limbs) {
 
 int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
-           const ExpDesc& ex, uint32_t* out2, uint32_t out2_stride) {
+           const ExpDesc& ex, uint32_t* out2, uint32_t out2_stride, int force_blocks) {
     if (count == 0) return PGPU_OK;
     if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
     const int gpb = VM_BLOCK_THREADS / m.sh.tpi;
     const size_t max_blocks = (size_t)ctx->sms * m.blocks_per_sm;
     const size_t want = (count + gpb - 1) / gpb;
-    const int blocks = (int)std::min(max_blocks, want);
+    const int blocks = force_blocks > 0 ? force_blocks : (int)std::min(max_blocks, want);
     VmParams P{};
     P.prog = prog.d_ops;
     P.n_items = (uint32_t)count;
@@ -189,6 +189,8 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     ctx->launches++;
     return PGPU_OK;
 }
+
+int vm_full_blocks(const pgpu_ctx* ctx, const ModCtx& m) { return ctx->sms * m.blocks_per_sm; }
 
 int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out) {
     if (ctx->stage_bytes[slot] < bytes) {
@@ -688,6 +690,74 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
     CombineParams C{(uint32_t)count, (int)h, kd.p, mont_np0(ctx->n.v[0]), cprime, S, m_out};
     CU(ctx, combine_final_launch(C, ctx->stream));
     ctx->launches++;
+    return PGPU_OK;
+}
+
+// Encrypted dot product prod c[i]^k[i] (ConstMult + Add, operations.go:11-29,58-64) by Pippenger's bucket method: per
+// window of w bits every ciphertext is multiplied into the bucket of its digit (ONE multiplication per item and window,
+// no squarings); the buckets are private to a resident group, so the pass is race free and uniform.  Per pass the group
+// folds its buckets into prod_d T[d]^d with the running-product trick, the groups' values are multiplied together, and
+// the windows are combined by Horner's rule.  ~ (bits/w + 1) multiplications per item instead of bits squarings.
+int dot_pippenger_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* k, uint32_t k_limbs, uint32_t* out) {
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S, w = 4, nb = 1u << w, bits = 32 * k_limbs, nwin = (bits + w - 1) / w;
+    const int blocks = vm_full_blocks(ctx, M);
+    const int gpb = VM_BLOCK_THREADS / M.sh.tpi;
+    const size_t n_groups = (size_t)blocks * gpb;
+    int rc;
+    auto program = [&](const std::string& key, auto&& build) -> Program* {
+        Program* P = cached_program(ctx, key);
+        if (P) return P;
+        Program np;
+        build(np);
+        if (program_upload(ctx, np)) return nullptr;
+        return &(ctx->prog_cache[key] = np);
+    };
+    Program* p_tom = program("tom:" + std::to_string(S), [&](Program& p) {
+        p.emit(OP_LDI, 0); p.emit(OP_MULC, K_R2); p.n_mul++; p.emit(OP_STO, 0);
+    });
+    Program* p_init = program("bkt-init:" + std::to_string(S), [&](Program& p) {
+        p.emit(OP_LDC, K_R1);
+        for (uint32_t d = 0; d <= nb; ++d) p.emit(OP_STT, d);
+        p.use_slot(nb + 2);      // same table layout as the two programs below: the buckets must survive between launches
+    });
+    Program* p_agg = program("bkt-agg:" + std::to_string(S), [&](Program& p) {
+        // run = T[nb-1]; acc = run; for d = nb-2 .. 1: run *= T[d]; acc *= run    (acc = prod_d T[d]^d)
+        const uint32_t RUN = nb + 1, ACC = nb + 2;
+        p.use_slot(ACC);
+        p.emit(OP_LDT, nb - 1); p.emit(OP_STT, RUN); p.emit(OP_STT, ACC);
+        for (uint32_t d = nb - 2; d >= 1; --d) {
+            p.emit(OP_LDT, RUN); p.emit(OP_MULT, d); p.n_mul++; p.emit(OP_STT, RUN);
+            p.emit(OP_MULT, ACC); p.n_mul++; p.emit(OP_STT, ACC);
+        }
+        p.emit(OP_MULC, K_ONE); p.n_mul++;
+        p.emit(OP_STO, 0);
+    });
+    if (!p_tom || !p_init || !p_agg) return fail(ctx, PGPU_ERR_CUDA, "dot product: program upload failed");
+    DEVBUF(cM, ctx, count * S); DEVBUF(accs, ctx, n_groups * S); DEVBUF(W, ctx, (size_t)nwin * S); DEVBUF(res, ctx, 2 * S);
+    IoDesc in_c[1] = {{c, S, S}};
+    if ((rc = run_vm(ctx, M, *p_tom, count, in_c, 1, cM.p, S, S))) return rc;                     // c -> Montgomery form, once
+    for (uint32_t j = 0; j < nwin; ++j) {
+        Program* p_bkt = program("bkt:" + std::to_string(S) + ":" + std::to_string(j * w), [&](Program& p) {
+            p.emit(OP_LDI, 0);
+            p.emit(OP_BKT, (j * w) | (w << 20)); p.n_mul++;
+            p.use_slot(nb + 2);
+        });
+        if (!p_bkt) return fail(ctx, PGPU_ERR_CUDA, "dot product: program upload failed");
+        // all three launches use the same resident grid: the buckets live in the groups' table slots
+        if ((rc = run_vm(ctx, M, *p_init, n_groups, nullptr, 0, accs.p, S, S, ExpDesc(), nullptr, 0, blocks))) return rc;
+        IoDesc in_m[1] = {{cM.p, S, S}};
+        if ((rc = run_vm(ctx, M, *p_bkt, count, in_m, 1, accs.p, S, S, ExpDesc{k, k_limbs, bits, nullptr}, nullptr, 0, blocks))) return rc;
+        if ((rc = run_vm(ctx, M, *p_agg, n_groups, nullptr, 0, accs.p, S, S, ExpDesc(), nullptr, 0, blocks))) return rc;
+        if ((rc = prod_dev(ctx, M, n_groups, accs.p, W.p + (size_t)j * S))) return rc;               // window value, plain
+    }
+    // Horner over the windows: res = (...(W[nwin-1]^(2^w) * W[nwin-2])^(2^w) ... ) * W[0]
+    CU(ctx, cudaMemcpyAsync(res.p, W.p + (size_t)(nwin - 1) * S, S * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (uint32_t j = nwin - 1; j-- > 0;) {
+        if ((rc = modexp_shared_dev(ctx, M, 1, res.p, BigU((uint64_t)nb), res.p + S))) return rc;
+        if ((rc = modmul_dev(ctx, M, 1, res.p + S, W.p + (size_t)j * S, res.p))) return rc;
+    }
+    CU(ctx, cudaMemcpyAsync(out, res.p, S * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     return PGPU_OK;
 }
 

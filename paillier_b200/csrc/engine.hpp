@@ -165,7 +165,9 @@ void program_free(Program& P);
 int ensure_table(pgpu_ctx* ctx, size_t limbs);
 int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
-           const ExpDesc& ex = ExpDesc(), uint32_t* out2 = nullptr, uint32_t out2_stride = 0);
+           const ExpDesc& ex = ExpDesc(), uint32_t* out2 = nullptr, uint32_t out2_stride = 0, int force_blocks = 0);
+int vm_full_blocks(const pgpu_ctx* ctx, const ModCtx& m);
+int dot_pippenger_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* k, uint32_t k_limbs, uint32_t* out);
 int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out);
 ModCtx* select_mod(pgpu_ctx* ctx, int modsel);
 int build_encrypt(pgpu_ctx* ctx);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
             const uint32_t op = __ldg(pc);
             const uint32_t code = op >> 27, arg = op & 0x07ffffffu;
             if (code == OP_END) break;
-            uint32_t nsq = 0, nmul = 0;
+            uint32_t nsq = 0, nmul = 0, bkt = 0xffffffffu;
             switch (code) {
                 case OP_LDI: {
                     const uint32_t* p = P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg];
@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
                     uint32_t* p = active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump;
                     store_vec<L>(p + lane_t * L, x);
                 } break;
+                case OP_BKT: {
+                    const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu;
+                    // idle groups must not touch the buckets: they multiply into the spare entry 2^w
+                    bkt = active ? exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w) : (1u << w);
+                    load_vec<L>(y, tbl + bkt * tbl_entry_stride);
+                    nmul = 1;
+                } break;
                 case OP_SUBT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
                 case OP_SQMT: {
                     const uint32_t idx = arg >> 12;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
                     M.mul(x, x, b);
                 }
             }
+            if (bkt != 0xffffffffu) store_vec<L>(tbl + bkt * tbl_entry_stride, x);
         }
     }
 }

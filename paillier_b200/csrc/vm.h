@@ -34,6 +34,9 @@ enum VmOp : uint32_t {
     OP_LDIO  = 16, // x = in[arg & 3][item, off = arg >> 2]
     OP_MULIO = 17, // x = mont(x, in[arg & 3][item, off = arg >> 2])
     OP_STOO  = 18, // out[arg & 1][item, off = arg >> 2] = x
+    // bucket accumulation (Pippenger multi-exponentiation of the encrypted dot product): the group's table is state
+    // that persists from item to item
+    OP_BKT   = 19, // d = bits(exp[item], pos, w); T[d] = x = mont(x, T[d]), arg = pos | w<<20
 };
 
 // 5-bit opcode, 27-bit argument

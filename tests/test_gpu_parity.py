@@ -334,3 +334,29 @@ def test_zkp_large_batch_fixed_base_and_batch_inverse():
     assert res[99] is False and sum(res) == count - 1
     for k in keys:
         k.close()
+
+
+def test_dot_product_pippenger_large_batch(sk2048):
+    # >= 16 items per resident group take the bucket method; it must equal ConstMult + Add bit for bit
+    import os
+    sk, _ = sk2048
+    n = sk.N
+    count = 170_001
+    m = synth.plaintexts(count, n, sk.w_n)
+    c = sk.encrypt_with_r_records(m, synth.randomness(count, n, sk.w_n))
+    k = synth.scalars_u64(count)
+    k[0], k[1], k[2], k[-1] = 0, 1, 2 ** 64 - 1, 0
+    fast = sk.dot_u64_records(c, k)
+    os.environ["PGPU_DOT_SIMPLE"] = "1"
+    try:
+        simple = sk.dot_u64_records(c, k)
+    finally:
+        del os.environ["PGPU_DOT_SIMPLE"]
+    assert np.array_equal(fast, simple)
+    ms = from_records(m, sk.w_n)
+    expect = sum(int(ki) * mi for ki, mi in zip(k, ms)) % n
+    assert sk.DecryptBatch([Ciphertext(from_records(fast, sk.w_n2)[0])]) == [expect]
+    # a subset against the libgmp oracle
+    sub = 2048
+    ref = G.add_reduce(n * n, G.modexp(n * n, c[:sub * sk.w_n2], sk.w_n2, k[:sub].view(np.uint8), 8), sk.w_n2)
+    assert np.array_equal(sk.dot_u64_records(c[:sub * sk.w_n2], k[:sub]), ref)
