@@ -355,6 +355,25 @@ def main() -> None:
         breakdown["alt_enc_e2e_per_s"] = world * acount / max_over_ranks(adt)
         breakdown["alt_enc_items"] = acount
         apk.close()
+        # level 2 (mod n^3): EncryptWithRAtLevel + Decrypt (CRT over p^3, q^3) through the host-buffer ABI
+        lcount = max(1, min(count, 1 << 15))
+        l2m = torch.from_numpy(synth.random_records(lcount, w_n2, (n * n).bit_length() - 1, seed, stream=51)).pin_memory()
+        l2c = torch.empty(lcount * sk.w_n3, dtype=torch.uint8).pin_memory()
+        l2d = torch.empty(lcount * w_n2, dtype=torch.uint8).pin_memory()
+        hp3 = lambda t: C.c_void_p(t.data_ptr())
+        for timed in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            check(lib.pgpu_encrypt_with_r_at_level(sk._ctx, 2, lcount, hp3(l2m), hp3(r_host[:lcount * w_n]), hp3(l2c)), sk._ctx)
+            barrier()
+            t1 = time.perf_counter()
+            check(lib.pgpu_decrypt_at_level(sk._ctx, 2, lcount, hp3(l2c), hp3(l2d)), sk._ctx)
+            barrier()
+            t2 = time.perf_counter()
+        assert torch.equal(l2d, l2m), "level 2: Decrypt(Encrypt(m)) != m"
+        breakdown["level2_enc_e2e_per_s"] = world * lcount / max_over_ranks(t1 - t0)
+        breakdown["level2_dec_e2e_per_s"] = world * lcount / max_over_ranks(t2 - t1)
+        breakdown["level2_items"] = lcount
         # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI
         if rank == 0:
             from paillier_b200.api import ENC_LEVEL_TWO

@@ -62,6 +62,26 @@ struct Recover2Params {
 };
 cudaError_t recover2_launch(const Recover2Params& P, cudaStream_t stream);
 
+// Decrypt at level 2 by CRT over p^3 and q^3.  xp = c^(p-1) mod p^3, xq = c^(q-1) mod q^3 (records of x_stride limbs).
+// With e = m(p-1) mod p^2:  (xp - 1)/p = e q + C(e,2) p q^2 (mod p^2); e mod p comes from the residue mod p, the binomial
+// term is then known, and m mod p^2 = (L1 - p (C(e0,2) q^2 mod p)) (q (p-1))^-1 mod p^2.  Garner over p^2, q^2 gives m mod n^2
+// (= recoveryAlgorithm(c^lambda mod n^3, 2) * lambda^-1 mod n^2, paillier.go:292-340).
+// consts per prime (h = limbs of the prime, H = 2h): P2 (H), p^-1 mod 2^(32H) (H), Cm*R mod p^2 (H), p (h), R_h^2 mod p (h),
+// R_h^3 mod p (h), q^-1 R_h mod p (h), inv2 q^2 R_h mod p (h), R_h mod p (h); then for Garner: (q^2)^-1 R mod p^2 (H), q^2 (H).
+struct Crt2Params {
+    uint32_t n_items;
+    int h;
+    const uint32_t* cp;      // constants of p (other prime q)
+    const uint32_t* cq;      // constants of q (other prime p)
+    const uint32_t* garner;  // (q^2)^-1 * R mod p^2, q^2
+    uint32_t np0_p, np0_p2, np0_q, np0_q2;
+    const uint32_t* xp; const uint32_t* xq; uint32_t x_stride;
+    uint32_t* out;           // out_limbs (<= 2H) limbs per item
+    uint32_t out_limbs;
+    uint32_t* mp; uint32_t* mq;   // scratch: m mod p^2, m mod q^2 (2h limbs per item each)
+};
+cudaError_t crt2_launch(const Crt2Params& P, cudaStream_t stream);
+
 // ---- bigops.cu ----
 constexpr int BIG_MAXS = 192;
 

@@ -211,6 +211,85 @@ cudaError_t recover2_launch(const Recover2Params& P, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+
+// m mod P^2 for one prime P of the level-2 CRT decryption (see Crt2Params)
+__device__ void crt2_half(uint32_t* mP, const uint32_t* x, const uint32_t* K, uint32_t np0_p, uint32_t np0_p2, int h) {
+    const int H = 2 * h;
+    const uint32_t* P2 = K;            const uint32_t* pinvH = K + H;     const uint32_t* CmM = K + 2 * H;
+    const uint32_t* p = K + 3 * H;     const uint32_t* R2h = p + h;       const uint32_t* R3h = p + 2 * h;
+    const uint32_t* CqM = p + 3 * h;   const uint32_t* C2M = p + 4 * h;   const uint32_t* oneM = p + 5 * h;
+    uint32_t L1[CRT_MAXH], a[CRT_MAXH], b[CRT_MAXH], w[CRT_MAXH];
+    st_L(L1, x, pinvH, H);                              // (x - 1) / p, exact, < p^2
+    // e0 = (L1 mod p) * q^-1 mod p, Montgomery form (R_h)
+    st_mont(a, L1, R2h, p, np0_p, h);                   // l0 * R_h
+    st_mont(b, L1 + h, R3h, p, np0_p, h);               // l1 * R_h^2
+    st_addmod(a, a, b, p, h);                           // (L1 mod p) * R_h
+    st_mont(a, a, CqM, p, np0_p, h);                    // e0 * R_h
+    // w = C(e0, 2) * q^2 mod p, plain
+    st_submod(b, a, oneM, p, h);                        // (e0 - 1) * R_h
+    st_mont(b, a, b, p, np0_p, h);                      // e0 (e0 - 1) * R_h
+    st_mont(b, b, C2M, p, np0_p, h);                    // * inv2 * q^2
+    for (int j = 0; j < h; ++j) a[j] = j == 0;
+    st_mont(w, b, a, p, np0_p, h);                      // out of Montgomery form
+    // V = L1 - p * w mod p^2
+    for (int j = 0; j < H; ++j) a[j] = 0;
+    for (int i = 0; i < h; ++i) {
+        uint64_t c = 0;
+        const uint32_t wi = w[i];
+        for (int j = 0; j < h; ++j) { c += (uint64_t)wi * p[j] + a[i + j]; a[i + j] = (uint32_t)c; c >>= 32; }
+        for (int j = i + h; c != 0 && j < H; ++j) { c += a[j]; a[j] = (uint32_t)c; c >>= 32; }
+    }
+    st_submod(b, L1, a, P2, H);
+    st_mont(mP, b, CmM, P2, np0_p2, H);                 // * (q (p-1))^-1 mod p^2
+}
+
+// one prime per launch: m mod P^2 into mhalf (H limbs per item)
+__global__ void crt2_half_kernel(uint32_t n_items, int h, const uint32_t* consts, uint32_t np0_p, uint32_t np0_p2,
+                                 const uint32_t* x, uint32_t x_stride, uint32_t* mhalf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    uint32_t m[CRT_MAXH];
+    crt2_half(m, x + (size_t)i * x_stride, consts, np0_p, np0_p2, h);
+    uint32_t* out = mhalf + (size_t)i * 2 * h;
+    for (int j = 0; j < 2 * h; ++j) out[j] = m[j];
+}
+
+// Garner over the moduli p^2, q^2: m = mq + q^2 * ((mp - mq) * (q^2)^-1 mod p^2)
+__global__ void crt2_garner_kernel(Crt2Params P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_items) return;
+    const int H = 2 * P.h;
+    const uint32_t* mp = P.mp + (size_t)i * H;
+    const uint32_t* mq = P.mq + (size_t)i * H;
+    const uint32_t* P2 = P.cp;
+    const uint32_t* CgM = P.garner;
+    const uint32_t* Q2 = P.garner + H;
+    uint32_t a[CRT_MAXH], b[CRT_MAXH];
+    st_mont(a, mp, CgM, P2, P.np0_p2, H);
+    st_mont(b, mq, CgM, P2, P.np0_p2, H);
+    st_submod(a, a, b, P2, H);
+    uint32_t* out = P.out + (size_t)i * P.out_limbs;
+    uint32_t r[2 * CRT_MAXH];
+    for (int j = 0; j < 2 * H; ++j) r[j] = j < H ? mq[j] : 0;
+    for (int ii = 0; ii < H; ++ii) {
+        uint64_t c = 0;
+        const uint32_t ti = a[ii];
+        for (int j = 0; j < H; ++j) { c += (uint64_t)ti * Q2[j] + r[ii + j]; r[ii + j] = (uint32_t)c; c >>= 32; }
+        for (int j = ii + H; c != 0 && j < 2 * H; ++j) { c += r[j]; r[j] = (uint32_t)c; c >>= 32; }
+    }
+    for (uint32_t j = 0; j < P.out_limbs; ++j) out[j] = r[j];
+}
+
+cudaError_t crt2_launch(const Crt2Params& P, cudaStream_t stream) {
+    if (P.n_items == 0) return cudaSuccess;
+    const int threads = 32;
+    const unsigned blocks = (P.n_items + threads - 1) / threads;
+    crt2_half_kernel<<<blocks, threads, 0, stream>>>(P.n_items, P.h, P.cp, P.np0_p, P.np0_p2, P.xp, P.x_stride, P.mp);
+    crt2_half_kernel<<<blocks, threads, 0, stream>>>(P.n_items, P.h, P.cq, P.np0_q, P.np0_q2, P.xq, P.x_stride, P.mq);
+    crt2_garner_kernel<<<blocks, threads, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // PublicKey.Add over a batch (operations.go:11-29): one running Montgomery
 // product per group, then a shared-memory tree across the block's groups.

@@ -90,6 +90,11 @@ struct pgpu_ctx {
     bool level2_ready = false;
     pgpu::Program prog_enc2, prog_rand;
     uint32_t* d_rec2 = nullptr;             // constants of recover2_kernel
+    pgpu::ModCtx m_p3, m_q3;                // CRT moduli of level-2 Decrypt
+    pgpu::Program prog_dec2_p, prog_dec2_q;
+    uint32_t* d_crt2 = nullptr; size_t crt2_cq_off = 0, crt2_g_off = 0;
+    uint32_t crt2_np0[4] = {0, 0, 0, 0};
+    bool crt2_ready = false;
     bool has_alt = false;
     pgpu::BigU alt_h; uint32_t alt_kbits = 0;
     pgpu::FixedTable fix_h1, fix_h2, fix_v;
@@ -172,6 +177,7 @@ int stage(pgpu_ctx* ctx, int slot, size_t bytes, void** out);
 ModCtx* select_mod(pgpu_ctx* ctx, int modsel);
 int build_encrypt(pgpu_ctx* ctx);
 int build_pdec(pgpu_ctx* ctx);
+int build_decrypt_half(pgpu_ctx* ctx, Program& P, const BigU& pm1);
 int setup_crt(pgpu_ctx* ctx);
 int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
@@ -208,6 +214,7 @@ int modexp_fixed_dev(pgpu_ctx* ctx, const ModCtx& M, const FixedTable& T, size_t
 int ensure_fix_v(pgpu_ctx* ctx);
 int setup_level2(pgpu_ctx* ctx);
 int setup_level2_secret(pgpu_ctx* ctx);
+int setup_level2_crt(pgpu_ctx* ctx);
 int setup_alt(pgpu_ctx* ctx);
 int encrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int decrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);

@@ -102,6 +102,10 @@ void protocols_free(pgpu_ctx* ctx) {
     program_free(ctx->prog_enc2); program_free(ctx->prog_rand); program_free(ctx->prog_alt1); program_free(ctx->prog_alt2);
     fixed_table_free(ctx->fix_h1); fixed_table_free(ctx->fix_h2); fixed_table_free(ctx->fix_v);
     if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
+    if (ctx->d_crt2) { cudaFree(ctx->d_crt2); ctx->d_crt2 = nullptr; }
+    program_free(ctx->prog_dec2_p); program_free(ctx->prog_dec2_q);
+    modctx_free(ctx->m_p3); modctx_free(ctx->m_q3);
+    ctx->crt2_ready = false;
 }
 
 // Public-key constants of the level-1 / level-2 shortcuts and the programs that need no secret.
@@ -183,12 +187,86 @@ int setup_level2_secret(pgpu_ctx* ctx) {
     }
     if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
     CU(ctx, cudaMalloc(&ctx->d_rec2, K.size() * 4));
-    return upload(ctx, ctx->d_rec2, K);
+    int rc;
+    if ((rc = upload(ctx, ctx->d_rec2, K))) return rc;
+    return setup_level2_crt(ctx);
+}
+
+// CRT constants of level-2 Decrypt (Crt2Params in aux.h).  Optional: without them decrypt2_dev takes the direct route.
+static void crt2_prime_consts(std::vector<uint32_t>& K, const BigU& p, const BigU& q, size_t h) {
+    const size_t H = 2 * h;
+    const BigU p2 = p * p, R = BigU::pow2(32 * H), Rh = BigU::pow2(32 * h);
+    BigU pinvH, cm, qinv, inv2;
+    BigU::modinv(p, R, pinvH);
+    BigU::modinv((q * (p - BigU(1))) % p2, p2, cm);
+    BigU::modinv(q % p, p, qinv);
+    BigU::modinv(BigU(2), p, inv2);
+    auto push = [&](const BigU& x, size_t w) { auto l = x.limbs(w); K.insert(K.end(), l.begin(), l.end()); };
+    push(p2, H); push(pinvH, H); push((cm * (R % p2)) % p2, H);
+    const BigU rh = Rh % p;
+    push(p, h); push((rh * rh) % p, h); push((((rh * rh) % p) * rh) % p, h);
+    push((qinv * rh) % p, h); push(((((inv2 * q) % p) * q) % p * rh) % p, h); push(rh, h);
+}
+
+int setup_level2_crt(pgpu_ctx* ctx) {
+    ctx->crt2_ready = false;
+    const BigU &p = ctx->p, &q = ctx->q;
+    const BigU p3 = p * p * p, q3 = q * q * q;
+    Shape s1, s2;
+    if (!pick_shape(p3.v.size(), s1) || !pick_shape(q3.v.size(), s2) || s1.S != s2.S) return PGPU_OK;
+    const size_t h = ctx->crt_h, H = 2 * h;
+    const uint32_t S3 = ctx->m_n3.sh.S, Sp = s1.S;
+    if (H > (size_t)CRT_MAXH || H > Sp || S3 > 2 * Sp || p.v.size() > h || q.v.size() > h || 2 * H < 2 * ctx->wn) return PGPU_OK;
+    int rc;
+    modctx_free(ctx->m_p3); modctx_free(ctx->m_q3);
+    if ((rc = modctx_init(ctx, ctx->m_p3, p3))) return rc;
+    if ((rc = modctx_init(ctx, ctx->m_q3, q3))) return rc;
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec2_p, p - BigU(1)))) return rc;
+    if ((rc = build_decrypt_half(ctx, ctx->prog_dec2_q, q - BigU(1)))) return rc;
+    std::vector<uint32_t> K;
+    crt2_prime_consts(K, p, q, h);
+    ctx->crt2_cq_off = K.size();
+    crt2_prime_consts(K, q, p, h);
+    ctx->crt2_g_off = K.size();
+    const BigU p2 = p * p, q2 = q * q, R = BigU::pow2(32 * H);
+    BigU q2inv;
+    if (!BigU::modinv(q2 % p2, p2, q2inv)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
+    for (const BigU& x : {(q2inv * (R % p2)) % p2, q2}) { auto l = x.limbs(H); K.insert(K.end(), l.begin(), l.end()); }
+    if (ctx->d_crt2) { cudaFree(ctx->d_crt2); ctx->d_crt2 = nullptr; }
+    CU(ctx, cudaMalloc(&ctx->d_crt2, K.size() * 4));
+    if ((rc = upload(ctx, ctx->d_crt2, K))) return rc;
+    ctx->crt2_np0[0] = mont_np0(p.v[0]); ctx->crt2_np0[1] = mont_np0(p2.v[0]);
+    ctx->crt2_np0[2] = mont_np0(q.v[0]); ctx->crt2_np0[3] = mont_np0(q2.v[0]);
+    ctx->crt2_ready = true;
+    return PGPU_OK;
+}
+
+static int decrypt2_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
+    const ModCtx &P3 = ctx->m_p3, &Q3 = ctx->m_q3;
+    const uint32_t S3 = ctx->m_n3.sh.S, Sp = P3.sh.S;
+    const uint32_t hi_limbs = S3 > Sp ? S3 - Sp : 0;
+    DEVBUF(xp, ctx, count * Sp); DEVBUF(xq, ctx, count * Sp);
+    DEVBUF(mhp, ctx, count * 2 * ctx->crt_h); DEVBUF(mhq, ctx, count * 2 * ctx->crt_h);
+    int rc;
+    IoDesc ins[2] = {{c, S3, std::min(S3, Sp)}, {c + Sp, S3, hi_limbs}};
+    if ((rc = run_vm(ctx, P3, ctx->prog_dec2_p, count, ins, 2, xp.p, Sp, Sp))) return rc;          // c^(p-1) mod p^3
+    if ((rc = run_vm(ctx, Q3, ctx->prog_dec2_q, count, ins, 2, xq.p, Sp, Sp))) return rc;          // c^(q-1) mod q^3
+    Crt2Params C{};
+    C.n_items = (uint32_t)count; C.h = ctx->crt_h;
+    C.cp = ctx->d_crt2; C.cq = ctx->d_crt2 + ctx->crt2_cq_off; C.garner = ctx->d_crt2 + ctx->crt2_g_off;
+    C.np0_p = ctx->crt2_np0[0]; C.np0_p2 = ctx->crt2_np0[1]; C.np0_q = ctx->crt2_np0[2]; C.np0_q2 = ctx->crt2_np0[3];
+    C.xp = xp.p; C.xq = xq.p; C.x_stride = Sp;
+    C.out = m; C.out_limbs = 2 * (uint32_t)ctx->wn;
+    C.mp = mhp.p; C.mq = mhq.p;
+    CU(ctx, crt2_launch(C, ctx->stream));
+    ctx->launches += 3;
+    return PGPU_OK;
 }
 
 int decrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
     if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "Decrypt: no secret key loaded");
     if (!ctx->level2_ready || !ctx->d_rec2) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level-2 Decrypt is not available at this key size");
+    if (ctx->crt2_ready && !getenv("PGPU_NO_CRT2")) return decrypt2_crt_dev(ctx, count, c, m);
     const ModCtx& M = ctx->m_n3;
     const uint32_t S = M.sh.S;
     const BigU lambda = (ctx->p - BigU(1)) * (ctx->q - BigU(1));
