@@ -516,6 +516,17 @@ class ThresholdPublicKey(PublicKey):
         return self.CombinePartialDecryptionsBatch([[PartialDecryption(p.ID, p.Decryption) for p in s] for s in good])
 
 
+    def VerifyDecryptionBatch(self, encryptedMessages: Sequence[int], decryptedMessages: Sequence[int],
+                              shares: Sequence[Sequence[PartialDecryptionZKP]]) -> None:
+        """N x ThresholdPublicKey.VerifyDecryption (thresholdkey.go:175-189); raises ValueError with the reference's
+        error strings, or the combine error (PgpuError) when too few valid shares remain."""
+        for s in shares:
+            if [p.C for p in s] != list(encryptedMessages):
+                raise ValueError("The encrypted message is not the same than the one in the shares")
+        if self.CombinePartialDecryptionsZKPBatch(shares) != list(decryptedMessages):
+            raise ValueError("The decrypted message is not the same than the one in the shares")
+
+
 class ThresholdSecretKey(ThresholdPublicKey):
     """thresholdkey.go:38-42"""
 

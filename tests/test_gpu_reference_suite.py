@@ -1,0 +1,128 @@
+"""The reference's own randomized tests, run through the batch engine: fresh random keys per iteration, the same
+sizes and assertions (paillier_test.go:52-138, operations_test.go:11-163, thresholdkey_test.go:192-394,
+ddleq_test.go:9-72), with key generation on the GPU as well.  Every result is also compared with the oracle."""
+import random
+
+import pytest
+
+from oracle import paillier_ref as R
+from paillier_b200._lib import PgpuError, PGPU_ERR_THRESHOLD
+from paillier_b200.api import (Ciphertext, ENC_LEVEL_ONE, ENC_LEVEL_TWO, PartialDecryption, PartialDecryptionZKP)
+from paillier_b200.keygen import KeyGen, ThresholdKeyGenerator
+
+pytestmark = pytest.mark.gpu
+
+
+def _units(rnd, n, k):
+    from math import gcd
+    out = []
+    while len(out) < k:
+        r = rnd.randrange(1, n)
+        if gcd(r, n) == 1:
+            out.append(r)
+    return out
+
+
+def test_encrypt_decrypt_and_operations_random_keys():
+    # TestEncryptDecrypt / TestEncryptDecryptLevel2 / TestAdd / TestSub / TestMult with 64..128-bit keys
+    rnd = random.Random(2026)
+    for it in range(12):
+        bits = rnd.choice([64, 80, 96, 128])
+        sk, pk = KeyGen(bits, rnd)
+        n = sk.N
+        opk = R.PublicKey(N=n)
+        osk = R.SecretKey(N=n, Lambda=sk.Lambda)
+        ms = [rnd.randrange(n) for _ in range(8)]
+        rs = _units(rnd, n, 8)
+        cts = pk.EncryptWithRBatch(ms, rs)
+        assert [c.C for c in cts] == [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms, rs)]
+        assert sk.DecryptBatch(cts) == ms == [R.decrypt(osk, R.Ciphertext(c.C)) for c in cts]
+        m2 = [rnd.randrange(n * n) for _ in range(4)]
+        ct2 = pk.EncryptWithRAtLevelBatch(m2, rs[:4], ENC_LEVEL_TWO)
+        assert sk.DecryptBatch(ct2) == m2
+        assert sk.DecryptBatch(pk.AddPairs(cts[:4], cts[4:])) == [(a + b) % n for a, b in zip(ms[:4], ms[4:])]
+        assert sk.DecryptBatch(pk.SubPairs(cts[:4], cts[4:])) == [(a - b) % n for a, b in zip(ms[:4], ms[4:])]
+        ks = [rnd.randrange(1, 2 ** 32) for _ in range(8)]
+        assert sk.DecryptBatch(pk.ConstMultBatch(cts, ks)) == [m * k % n for m, k in zip(ms, ks)]
+        assert sk.DecryptBatch([pk.AddBatch(cts)]) == [sum(ms) % n]
+        # TestExtractRandomnessWithRegularEncryption (operations_test.go:130-163): r = i^2
+        sq = [(i + 2) ** 2 for i in range(4)]
+        assert sk.ExtractRandonnessBatch(pk.EncryptWithRBatch(ms[:4], sq)) == sq
+        sk.close(); pk.close()
+
+
+def test_threshold_round_trips_with_generated_keys():
+    # TestEncryptingDecryptingSimple / TestEncryptingDecrypting / TestHomomorphicThresholdEncryption (32-bit keys)
+    rnd = random.Random(7)
+    for l, w in ((2, 1), (2, 2), (5, 3)):
+        keys = ThresholdKeyGenerator(32, l, w, rng=rnd, batch=512).GenerateKeys()
+        n = keys[0].N
+        c1, c2 = keys[0].EncryptWithRBatch([13 % n, 19 % n], _units(rnd, n, 2))
+        c3 = keys[0].AddPairs([c1], [c2])[0]
+        parts = [k.PartialDecryptBatch([c1.C, c3.C]) for k in keys[:w]]
+        assert keys[0].CombinePartialDecryptionsBatch(parts) == [13 % n, 32 % n]
+        for k in keys:
+            k.close()
+
+
+def test_combine_with_100_servers():
+    # TestCombinePartialDecryptionsWith100Shares (thresholdkey_test.go:329-355): 100 servers, threshold 50, 75 shares
+    rnd = random.Random(100)
+    keys = ThresholdKeyGenerator(32, 100, 50, rng=rnd, batch=512).GenerateKeys()
+    n = keys[0].N
+    msgs = [100 % n, 0, n - 1]
+    cs = [c.C for c in keys[1].EncryptWithRBatch(msgs, _units(rnd, n, 3))]
+    shares = [keys[i].PartialDecryptBatch(cs) for i in range(75)]
+    assert keys[0].CombinePartialDecryptionsBatch(shares) == msgs
+    okeys = [R.ThresholdSecretKey(N=n, TotalNumberOfDecryptionServers=100, Threshold=50, VerificationKey=k.VerificationKey,
+                                  VerificationKeys=k.VerificationKeys, ID=k.ID, Share=k.Share) for k in keys[:75]]
+    otk = R.threshold_public_key(okeys[0])
+    assert R.combine_partial_decryptions(otk, [R.partial_decrypt(k, cs[0]) for k in okeys]) == msgs[0]
+    with pytest.raises(PgpuError) as ei:
+        keys[0].CombinePartialDecryptionsBatch(shares[:49])
+    assert ei.value.code == PGPU_ERR_THRESHOLD
+    for k in keys:
+        k.close()
+
+
+def test_zkp_and_verify_decryption():
+    # TestCombinePartialDecryptionsZKP / TestVerifyDecryption (thresholdkey_test.go:294-394)
+    rnd = random.Random(31)
+    keys = ThresholdKeyGenerator(32, 2, 2, rng=rnd, batch=512).GenerateKeys()
+    n = keys[0].N
+    c = keys[1].EncryptWithRBatch([100 % n, 101 % n], _units(rnd, n, 2))
+    cs = [x.C for x in c]
+    zr = [rnd.randrange(n * n) for _ in cs]
+    s1, s2 = keys[0].PartialDecryptionWithZKPBatch(cs, zr), keys[1].PartialDecryptionWithZKPBatch(cs, zr[::-1])
+    assert keys[0].CombinePartialDecryptionsZKPBatch([s1, s2]) == [100 % n, 101 % n]
+    keys[0].VerifyDecryptionBatch(cs, [100 % n, 101 % n], [s1, s2])
+    with pytest.raises(ValueError):
+        keys[0].VerifyDecryptionBatch(cs, [100 % n, 100 % n], [s1, s2])
+    with pytest.raises(ValueError):
+        keys[0].VerifyDecryptionBatch([cs[0] + 1, cs[1]], [100 % n, 101 % n], [s1, s2])
+    bad = [PartialDecryptionZKP(p.ID, p.Decryption, 687687678, p.Z, p.C) for p in s1]       # share1.E = 687687678
+    with pytest.raises(PgpuError) as ei:
+        keys[0].CombinePartialDecryptionsZKPBatch([bad, s2])                                   # too few valid shares
+    assert ei.value.code == PGPU_ERR_THRESHOLD
+    for k in keys:
+        k.close()
+
+
+def test_ddleq_random_keys():
+    # ddleq_test.go:9-72: 128-bit keys, secpar 10, completeness and soundness
+    rnd = random.Random(5)
+    for it in range(3):
+        sk, pk = KeyGen(128, rnd)
+        n = sk.N
+        count, secpar = 4, 10
+        inner = pk.EncryptWithRBatch([rnd.randrange(n) for _ in range(count)], _units(rnd, n, count))
+        ct1 = pk.EncryptWithRAtLevelBatch([c.C for c in inner], _units(rnd, n, count), ENC_LEVEL_TWO)
+        As, Bs = _units(rnd, n, count), _units(rnd, n, count)
+        ct2 = pk.NestedRandomizeWithBatch(ct1, As, Bs)
+        xs = [_units(rnd, n, secpar) for _ in range(count)]
+        ys = [_units(rnd, n, secpar) for _ in range(count)]
+        proofs = sk.ProveDDLEQBatch(secpar, ct1, ct2, As, Bs, xs, ys)
+        assert pk.VerifyDDLEQProofBatch(ct1, ct2, proofs) == [True] * count
+        other = pk.NestedRandomizeWithBatch(ct1, Bs, As)
+        assert pk.VerifyDDLEQProofBatch(ct1, other, proofs) == [False] * count
+        sk.close(); pk.close()
