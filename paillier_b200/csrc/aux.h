@@ -130,6 +130,10 @@ cudaError_t first_zero_launch(const uint8_t* flags, uint32_t n_items, uint32_t* 
 cudaError_t select_launch(const uint32_t* digest, const uint32_t* a, uint32_t a_div, const uint32_t* b, uint32_t b_div, uint32_t limbs, uint32_t n_items, uint32_t* out, cudaStream_t stream);
 // out[i] = in[i / rep] (records of `limbs` limbs): a statement value repeated for each of its proof instances
 cudaError_t repeat_launch(const uint32_t* in, uint32_t limbs, uint32_t rep, uint32_t* out, uint32_t n_out, cudaStream_t stream);
+// out[i] = in[idx[i] / div] and out[idx[i]] = in[i] over records of `limbs` limbs (compaction of the DDLEQ instances whose
+// challenge bit is 1)
+cudaError_t gather_launch(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t div, uint32_t* out, uint32_t n, cudaStream_t stream);
+cudaError_t scatter_launch(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t* out, uint32_t n, cudaStream_t stream);
 cudaError_t resize_launch(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items, cudaStream_t stream);
 
 }  // namespace pgpu

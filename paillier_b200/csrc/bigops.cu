@@ -422,6 +422,29 @@ cudaError_t repeat_launch(const uint32_t* in, uint32_t limbs, uint32_t rep, uint
     return cudaGetLastError();
 }
 
+__global__ void gather_kernel(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t div, uint32_t* out, uint32_t n) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint32_t* src = in + (size_t)(idx[i] / div) * limbs;
+    for (uint32_t k = lane; k < limbs; k += 32) out[(size_t)i * limbs + k] = src[k];
+}
+__global__ void scatter_kernel(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t* out, uint32_t n) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    uint32_t* dst = out + (size_t)idx[i] * limbs;
+    for (uint32_t k = lane; k < limbs; k += 32) dst[k] = in[(size_t)i * limbs + k];
+}
+cudaError_t gather_launch(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t div, uint32_t* out, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    gather_kernel<<<(n + 3) / 4, 128, 0, stream>>>(in, limbs, idx, div ? div : 1, out, n);
+    return cudaGetLastError();
+}
+cudaError_t scatter_launch(const uint32_t* in, uint32_t limbs, const uint32_t* idx, uint32_t* out, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    scatter_kernel<<<(n + 3) / 4, 128, 0, stream>>>(in, limbs, idx, out, n);
+    return cudaGetLastError();
+}
+
 // widen / narrow records: out (out_limbs) = in (in_limbs), zero padded or truncated; stride 0 broadcasts one record
 __global__ void resize_kernel(const uint32_t* in, uint32_t in_stride, uint32_t in_limbs, uint32_t* out, uint32_t out_limbs, uint32_t n_items) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -458,26 +458,44 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     if ((rc = modinv_batch_dev(ctx, M2, count, a2.p, ainv.p, badinv.p))) return rc;                                                // a^-1 mod n^2 :96
     // ---- per instance
     DEVBUF(xn, ctx, total * S2); DEVBUF(yn2, ctx, total * S3); DEVBUF(u3, ctx, total * S3); DEVBUF(dig, ctx, total * 8);
-    DEVBUF(e1, ctx, total * S2); DEVBUF(en, ctx, total * S2); DEVBUF(v3, ctx, total * S3); DEVBUF(f1, ctx, total * S3);
     if ((rc = modexp_shared_io(ctx, M2, total, IoDesc{x, wn, wn}, ctx->n, xn.p))) return rc;                                 // x^n        :81
     if ((rc = modexp_shared_io(ctx, M3, total, IoDesc{y, wn, wn}, ctx->n2, yn2.p))) return rc;                               // y^(n^2)    :82
     if ((rc = modexp_items_io(ctx, M3, total, IoDesc{ct1, S3, S3, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // ct1^xn :85
     if ((rc = modmul_dev(ctx, M3, total, u3.p, yn2.p, alpha))) return rc;                                                    // alpha      :86-87
     if ((rc = ddleq_hash(ctx, total, secpar, ct2, x, y, alpha, dig.p))) return rc;                                           // challenge  :91
-    if ((rc = modmul_io(ctx, M2, total, IoDesc{x, wn, wn}, IoDesc{ainv.p, S2, S2, secpar}, e1.p))) return rc;                // e = x*a^-1 mod n^2 :94-99
-    if ((rc = modexp_shared_dev(ctx, M2, total, e1.p, ctx->n, en.p))) return rc;                                             // e^n        :105
-    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{c0.p, S3, S3, secpar}, ExpDesc{en.p, S2, e2bits, nullptr}, u3.p))) return rc;  // (s^an*b)^en :109
-    if ((rc = modinv_batch_dev(ctx, M3, total, u3.p, v3.p, badinv.p))) return rc;                                                  // ^-1        :110
-    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{s.p, wn, wn, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // s^xn  :112
-    if ((rc = modmul_dev(ctx, M3, total, v3.p, u3.p, v3.p))) return rc;                                                      // c          :112
-    if ((rc = modmul_io(ctx, M3, total, IoDesc{y, wn, wn}, IoDesc{v3.p, S3, S3}, f1.p))) return rc;                          // f = y*c    :113-114
-    // challenge bit selects (e, f) = (x*a^-1, y*c) or (x, y)
-    DEVBUF(xw, ctx, total * S2); DEVBUF(yw, ctx, total * S3);
-    CU(ctx, resize_launch(x, wn, wn, xw.p, S2, (uint32_t)total, ctx->stream));
-    CU(ctx, resize_launch(y, wn, wn, yw.p, S3, (uint32_t)total, ctx->stream));
-    CU(ctx, select_launch(dig.p, e1.p, 1, xw.p, 1, S2, (uint32_t)total, e, ctx->stream));
-    CU(ctx, select_launch(dig.p, f1.p, 1, yw.p, 1, S3, (uint32_t)total, f, ctx->stream));
-    ctx->launches += 4;
+    // (e, f) = (x, y) where the challenge bit is 0 ...
+    CU(ctx, resize_launch(x, wn, wn, e, S2, (uint32_t)total, ctx->stream));
+    CU(ctx, resize_launch(y, wn, wn, f, S3, (uint32_t)total, ctx->stream));
+    ctx->launches += 2;
+    // ... and only the instances whose bit is 1 pay for the second half (:94-114): compact them
+    std::vector<uint32_t> hd(total * 8), idx;
+    CU(ctx, cudaMemcpyAsync(hd.data(), dig.p, total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < total; ++i) if (hd[i * 8] & 1u) idx.push_back((uint32_t)i);
+    const size_t n1 = idx.size();
+    if (n1 == 0) return PGPU_OK;
+    DEVBUF(didx, ctx, n1); DEVBUF(xg, ctx, n1 * wn); DEVBUF(yg, ctx, n1 * wn); DEVBUF(xng, ctx, n1 * S2); DEVBUF(ainvg, ctx, n1 * S2);
+    DEVBUF(c0g, ctx, n1 * S3); DEVBUF(sg, ctx, n1 * wn);
+    DEVBUF(e1, ctx, n1 * S2); DEVBUF(en, ctx, n1 * S2); DEVBUF(v3, ctx, n1 * S3); DEVBUF(f1, ctx, n1 * S3);
+    if ((rc = upload(ctx, didx.p, idx))) return rc;
+    const uint32_t N1 = (uint32_t)n1;
+    CU(ctx, gather_launch(x, wn, didx.p, 1, xg.p, N1, ctx->stream));
+    CU(ctx, gather_launch(y, wn, didx.p, 1, yg.p, N1, ctx->stream));
+    CU(ctx, gather_launch(xn.p, S2, didx.p, 1, xng.p, N1, ctx->stream));
+    CU(ctx, gather_launch(ainv.p, S2, didx.p, secpar, ainvg.p, N1, ctx->stream));
+    CU(ctx, gather_launch(c0.p, S3, didx.p, secpar, c0g.p, N1, ctx->stream));
+    CU(ctx, gather_launch(s.p, wn, didx.p, secpar, sg.p, N1, ctx->stream));
+    ctx->launches += 6;
+    if ((rc = modmul_io(ctx, M2, n1, IoDesc{xg.p, wn, wn}, IoDesc{ainvg.p, S2, S2}, e1.p))) return rc;                       // e = x*a^-1 mod n^2 :94-99
+    if ((rc = modexp_shared_dev(ctx, M2, n1, e1.p, ctx->n, en.p))) return rc;                                                // e^n        :105
+    if ((rc = modexp_items_io(ctx, M3, n1, IoDesc{c0g.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, u3.p))) return rc;     // (s^an*b)^en :109
+    if ((rc = modinv_batch_dev(ctx, M3, n1, u3.p, v3.p, badinv.p))) return rc;                                               // ^-1        :110
+    if ((rc = modexp_items_io(ctx, M3, n1, IoDesc{sg.p, wn, wn}, ExpDesc{xng.p, S2, e2bits, nullptr}, u3.p))) return rc;     // s^xn       :112
+    if ((rc = modmul_dev(ctx, M3, n1, v3.p, u3.p, v3.p))) return rc;                                                         // c          :112
+    if ((rc = modmul_io(ctx, M3, n1, IoDesc{yg.p, wn, wn}, IoDesc{v3.p, S3, S3}, f1.p))) return rc;                          // f = y*c    :113-114
+    CU(ctx, scatter_launch(e1.p, S2, didx.p, e, N1, ctx->stream));
+    CU(ctx, scatter_launch(f1.p, S3, didx.p, f, N1, ctx->stream));
+    ctx->launches += 2;
     return PGPU_OK;
 }
 
