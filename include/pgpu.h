@@ -62,6 +62,9 @@ int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_le
 int pgpu_ctx_destroy(pgpu_ctx* ctx);
 /* record widths in bytes (any pointer may be NULL) */
 int pgpu_ctx_widths(const pgpu_ctx* ctx, size_t* w_n, size_t* w_n2, size_t* w_n3);
+/* record width in bytes of the generic entry points (pgpu_modexp, pgpu_modmul, pgpu_modinv ...) for one modulus selector;
+ * equals the n2- / n3-width above for PGPU_MOD_N2 / PGPU_MOD_N3, 0 if that modulus is not available */
+int pgpu_ctx_mod_width(const pgpu_ctx* ctx, int modsel, size_t* width);
 /* run subsequent *_dev calls on this cudaStream_t (default: a stream owned by the context) */
 int pgpu_ctx_set_stream(pgpu_ctx* ctx, void* cuda_stream);
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "pgpu_ctx_create": (C.c_int, [C.POINTER(_p), C.c_int, _u8p, _sz]),
     "pgpu_ctx_destroy": (C.c_int, [_p]),
     "pgpu_ctx_widths": (C.c_int, [_p, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "pgpu_ctx_mod_width": (C.c_int, [_p, C.c_int, C.POINTER(_sz)]),
     "pgpu_ctx_set_stream": (C.c_int, [_p, _p]),
     "pgpu_ctx_set_secret_pq": (C.c_int, [_p, _u8p, _sz, _u8p, _sz]),
     "pgpu_ctx_set_secret_lambda": (C.c_int, [_p, _u8p, _sz]),

@@ -113,6 +113,9 @@ class PublicKey:
         wn, w2, w3 = C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(lib.pgpu_ctx_widths(self._ctx, C.byref(wn), C.byref(w2), C.byref(w3)), self._ctx)
         self.w_n, self.w_n2, self.w_n3 = wn.value, w2.value, w3.value
+        wm = C.c_size_t()
+        check(lib.pgpu_ctx_mod_width(self._ctx, MOD_N, C.byref(wm)), self._ctx)
+        self.w_n_rec = wm.value              # record width of the generic mod-n entry points (the n kernel shape)
         if H is not None:
             if K is None or K < 2 or K & (K - 1):
                 raise ValueError("K must be a power of two (paillier.go:151)")
@@ -221,6 +224,28 @@ class PublicKey:
         out = self.encrypt_with_r_records(to_records(ms, self.w_n), to_records(rs, self.w_n))
         return [Ciphertext(c, ENC_LEVEL_ONE, REGULAR) for c in from_records(out, self.w_n2)]
 
+    def EncryptBatch(self, ms: Sequence[int], rand=None) -> List[Ciphertext]:
+        """N x PublicKey.Encrypt (paillier.go:192, :258-269): draws r as GetRandomNumberInMultiplicativeGroup does
+        (utils.go:36-49: uniform below n, retry on 0 or gcd(n, r) != 1) -- the draws come from the host CSPRNG (`secrets`,
+        or `rand.randrange` if given), the unit test of the whole batch is one batched ModInverse mod n on the GPU."""
+        import secrets
+        draw = (lambda: rand.randrange(self.N)) if rand is not None else (lambda: secrets.randbelow(self.N))
+        rs = [draw() for _ in ms]
+        while True:
+            bad = [i for i, r in enumerate(rs) if r == 0]
+            if not bad:
+                try:
+                    self.ModInverseBatch(rs, MOD_N)
+                    break
+                except PgpuError as e:
+                    if e.code != _lib.PGPU_ERR_NOT_INVERTIBLE:
+                        raise
+                    from math import gcd
+                    bad = [i for i, r in enumerate(rs) if gcd(r, self.N) != 1]
+            for i in bad:
+                rs[i] = draw()
+        return self.EncryptWithRBatch(ms, rs)
+
     def ConstMultBatch(self, cts: Sequence[Ciphertext], ks: Sequence[int]) -> List[Ciphertext]:
         """N x PublicKey.ConstMult (operations.go:58-64); k <= 0 gives 1 like gmp's Exp"""
         if len(cts) != len(ks):
@@ -250,7 +275,7 @@ class PublicKey:
 
     def ModInverseBatch(self, xs: Sequence[int], modsel: int = MOD_N2) -> List[int]:
         """N x gmp.Int.ModInverse(x, mod); raises PgpuError(PGPU_ERR_NOT_INVERTIBLE) for a non-unit"""
-        width = {MOD_N2: self.w_n2, MOD_N3: self.w_n3}[modsel]
+        width = {MOD_N: self.w_n_rec, MOD_N2: self.w_n2, MOD_N3: self.w_n3}[modsel]
         xr = to_records(xs, width)
         out = np.empty(len(xs) * width, dtype=np.uint8)
         check(lib.pgpu_modinv(self._ctx, modsel, len(xs), _ptr(xr), _ptr(out)), self._ctx)

@@ -95,6 +95,13 @@ int pgpu_ctx_widths(const pgpu_ctx* ctx, size_t* w_n, size_t* w_n2, size_t* w_n3
     return PGPU_OK;
 }
 
+int pgpu_ctx_mod_width(const pgpu_ctx* ctx, int modsel, size_t* width) {
+    if (!ctx || !width) return fail(nullptr, PGPU_ERR_ARG, "null argument");
+    const ModCtx* M = modsel == PGPU_MOD_N ? &ctx->m_n : modsel == PGPU_MOD_N2 ? &ctx->m_n2 : modsel == PGPU_MOD_N3 ? &ctx->m_n3 : nullptr;
+    *width = (M && M->ready) ? (size_t)M->sh.S * 4 : 0;
+    return PGPU_OK;
+}
+
 int pgpu_ctx_set_stream(pgpu_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;

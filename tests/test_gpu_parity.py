@@ -7,7 +7,7 @@ from oracle import gmp_ref as G
 from oracle import paillier_ref as R
 from paillier_b200 import synth
 from paillier_b200.api import (Ciphertext, PublicKey, SecretKey, ThresholdSecretKey, from_records, to_records,
-                               MOD_N2, MOD_N3)
+                               MOD_N, MOD_N2, MOD_N3)
 
 pytestmark = pytest.mark.gpu
 
@@ -360,3 +360,45 @@ def test_dot_product_pippenger_large_batch(sk2048):
     sub = 2048
     ref = G.add_reduce(n * n, G.modexp(n * n, c[:sub * sk.w_n2], sk.w_n2, k[:sub].view(np.uint8), 8), sk.w_n2)
     assert np.array_equal(sk.dot_u64_records(c[:sub * sk.w_n2], k[:sub]), ref)
+
+
+def test_encrypt_batch_draws_units(sk2048):
+    # PublicKey.Encrypt (paillier.go:192,258-269): r drawn on the host, unit check batched on the GPU
+    import random
+    sk, _ = sk2048
+    ms = [0, 1, sk.N - 1, 424242]
+    cts = sk.EncryptBatch(ms, rand=random.Random(3))
+    assert sk.DecryptBatch(cts) == ms
+    assert len({c.C for c in cts}) == 4
+    assert sk.ModInverseBatch([3, sk.N - 1], MOD_N) == [pow(3, -1, sk.N), sk.N - 1]
+
+
+def test_carry_chain_edge_values():
+    # operands made of all-ones / all-zero limbs and values next to the modulus, through every multiplier shape
+    # (32, 64, 96, 128, 192 limbs): squarings (dedicated kernel for the 32- and 64-limb shapes) and multiplications
+    import random
+    rnd = random.Random(99)
+    for name in ("paillier_64", "paillier_1024", "paillier_2048", "threshold_3072"):
+        p, q, n = _key(name)
+        pk = PublicKey(n)
+        for modsel, mod, width in ((MOD_N2, n * n, pk.w_n2), (MOD_N3, n ** 3, pk.w_n3)):
+            if not width:
+                continue
+            limbs = width // 4
+            vals = [0, 1, 2, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1, (1 << (32 * (limbs - 1))) % mod]
+            vals += [((1 << b) - 1) % mod for b in (31, 32, 33, 64, 32 * limbs // 2, 32 * limbs // 2 + 1, mod.bit_length() - 1)]
+            vals += [int("ffffffff00000000" * (limbs // 2), 16) % mod, int("00000000ffffffff" * (limbs // 2), 16) % mod]
+            vals += [(mod - (1 << b)) % mod for b in (0, 32, 64, 32 * limbs // 4)]
+            vals += [rnd.randrange(mod) for _ in range(6)]
+            assert pk.ExpSharedBatch(vals, 2, modsel) == [v * v % mod for v in vals]
+            assert pk.ExpSharedBatch(vals, 65537, modsel) == [pow(v, 65537, mod) for v in vals]
+            rev = vals[::-1]
+            assert pk.MulModBatch(vals, rev, modsel) == [a * b % mod for a, b in zip(vals, rev)]
+        pk.close()
+    # the CRT halves of Decrypt run the 64-limb squaring kernel: plaintexts and ciphertexts at the extremes
+    p, q, n = _key("paillier_2048")
+    sk = SecretKey(n, p=p, q=q)
+    ms = [0, 1, n - 1, (1 << 2047) % n, (1 << 1024) - 1, n >> 1]
+    for r in (1, n - 1, 2):
+        assert sk.DecryptBatch(sk.EncryptWithRBatch(ms, [r] * len(ms))) == ms
+    sk.close()
