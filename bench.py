@@ -442,10 +442,10 @@ def main() -> None:
             pass
         alg_bytes = count * (2 * w_n + w_n2)
         # DRAM bytes of the EncryptWithR launch: per-item traffic of the committed `ncu --set full` capture of the same
-        # kernel (profiles/r01_ncu_powm_vm_summary_v2.json, 18944 items) scaled to this launch's item count
+        # kernel (profiles/r01_ncu_powm_vm_summary_v4.json, 18944 items) scaled to this launch's item count
         traffic = None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_powm_vm_summary_v2.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_powm_vm_summary_v4.json")))
             k0 = prof["kernels"][0]
             unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             def _b(sv):
