@@ -197,6 +197,10 @@ int pgpu_partial_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* o
 int pgpu_const_mult_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out);
 int pgpu_add_reduce_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out);
 int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t* k, void* out);
+int pgpu_add_pairs_dev(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out);
+/* first_bad: device word set to 0xffffffff, or to the index of the first b[i] that is not a unit */
+int pgpu_sub_pairs_dev(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out, uint32_t* first_bad);
+int pgpu_randomize_with_r_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* out);
 
 int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z);
 int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);

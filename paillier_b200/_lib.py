@@ -56,6 +56,9 @@ SIGNATURES = {
     "pgpu_const_mult_dev": (C.c_int, [_p, _sz, _p, _p, _sz, _p]),
     "pgpu_add_reduce_dev": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_dot_u64_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_add_pairs_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_sub_pairs_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p]),
+    "pgpu_randomize_with_r_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_sub_pairs": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_modinv": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
     "pgpu_pdec_zkp_prove": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),

@@ -229,6 +229,36 @@ int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t*
     GUARD_END(ctx)
 }
 
+int pgpu_add_pairs_dev(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (a && b && out)), "pgpu_add_pairs_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return modmul_dev(ctx, ctx->m_n2, count, (const uint32_t*)a, (const uint32_t*)b, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+/* first_bad: device word, 0xffffffff when every b[i] is a unit, else the index of the first one that is not */
+int pgpu_sub_pairs_dev(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out, uint32_t* first_bad) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && first_bad && (count == 0 || (a && b && out)), "pgpu_sub_pairs_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    DEVBUF(inv, ctx, count * ctx->m_n2.sh.S);        // out may alias a or b
+    if ((rc = modinv_batch_dev(ctx, ctx->m_n2, count, (const uint32_t*)b, inv.p, first_bad))) return rc;
+    return modmul_dev(ctx, ctx->m_n2, count, (const uint32_t*)a, inv.p, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
+int pgpu_randomize_with_r_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && r && out)), "pgpu_randomize_with_r_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return randomize_dev(ctx, count, (const uint32_t*)c, (const uint32_t*)r, (uint32_t*)out);
+    GUARD_END(ctx)
+}
+
 // ---- host-buffer entry points
 int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
     GUARD_BEGIN

@@ -28,3 +28,45 @@ def test_threshold_round_world1(zkp):
     assert (lo, hi) == (0, count)
     assert from_records(plain.cpu().numpy(), tsk.w_n) == from_records(m, tsk.w_n)
     tsk.close()
+
+
+def test_device_resident_chain():
+    # Encrypt -> Randomize -> ConstMult -> Add/Sub pairs -> Add over the batch -> Decrypt without leaving the GPU
+    import ctypes as C
+    import numpy as np
+    from paillier_b200._lib import check, lib
+    from paillier_b200.api import SecretKey
+    p, q = synth.load_key("paillier_2048")
+    n = p * q
+    sk = SecretKey(n, p=p, q=q)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    check(lib.pgpu_ctx_set_stream(sk._ctx, C.c_void_p(stream.cuda_stream)), sk._ctx)
+    count = 2000
+    m = synth.plaintexts(count, n, sk.w_n)
+    k = synth.scalars_u64(count)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.stream(stream):
+        md = torch.from_numpy(m).to(dev)
+        rd = torch.from_numpy(synth.randomness(count, n, sk.w_n)).to(dev)
+        r2 = torch.from_numpy(synth.randomness(count, n, sk.w_n, synth.SEED + 1)).to(dev)
+        kd = torch.from_numpy(k.view(np.int64).copy()).to(dev)
+        c = torch.empty(count * sk.w_n2, dtype=torch.uint8, device=dev)
+        c2, c3, c4 = torch.empty_like(c), torch.empty_like(c), torch.empty_like(c)
+        tot = torch.empty(sk.w_n2, dtype=torch.uint8, device=dev)
+        out = torch.empty(sk.w_n, dtype=torch.uint8, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.pgpu_encrypt_with_r_dev(sk._ctx, count, vp(md), vp(rd), vp(c)), sk._ctx)
+        check(lib.pgpu_randomize_with_r_dev(sk._ctx, count, vp(c), vp(r2), vp(c2)), sk._ctx)          # same plaintexts, fresh randomness
+        check(lib.pgpu_const_mult_dev(sk._ctx, count, vp(c2), vp(kd), 8, vp(c3)), sk._ctx)            # k_i * m_i
+        check(lib.pgpu_add_pairs_dev(sk._ctx, count, vp(c3), vp(c), vp(c4)), sk._ctx)                 # + m_i
+        check(lib.pgpu_sub_pairs_dev(sk._ctx, count, vp(c4), vp(c2), vp(c4), vp(bad)), sk._ctx)       # - m_i
+        check(lib.pgpu_add_reduce_dev(sk._ctx, count, vp(c4), vp(tot)), sk._ctx)
+        check(lib.pgpu_decrypt_dev(sk._ctx, 1, vp(tot), vp(out)), sk._ctx)
+    stream.synchronize()
+    assert int(bad.item()) == -1
+    ms = from_records(m, sk.w_n)
+    expect = sum(int(ki) * mi for ki, mi in zip(k, ms)) % n
+    assert from_records(out.cpu().numpy(), sk.w_n) == [expect]
+    check(lib.pgpu_ctx_set_stream(sk._ctx, None), sk._ctx)
+    sk.close()
