@@ -411,7 +411,7 @@ def main() -> None:
         # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI
         if rank == 0:
             from paillier_b200.api import ENC_LEVEL_TWO
-            dn, dsecpar = 256, 8
+            dn, dsecpar = 2048, 8
             ints = lambda a, w: [int.from_bytes(a[i * w:(i + 1) * w].tobytes(), "little") for i in range(len(a) // w)]
             rr = ints(synth.randomness(dn * (4 + 2 * dsecpar), n, w_n, seed + 7), w_n)
             inner = sk.EncryptWithRBatch(ints(synth.plaintexts(dn, n, w_n, seed + 7), w_n), rr[:dn])
