@@ -73,7 +73,8 @@ void modctx_free(ModCtx& m) {
 // ------------------------------------------------------- program compiler
 int choose_window(size_t bits) {
     int best = 1; double best_cost = 1e300;
-    for (int w = 1; w <= 7; ++w) {
+    static const int wmax = [] { const char* e = getenv("PGPU_WINDOW_MAX"); const int v = e ? atoi(e) : 7; return v < 1 ? 1 : v > 7 ? 7 : v; }();
+    for (int w = 1; w <= wmax; ++w) {
         double cost = (w == 1 ? 0.0 : (double)(1u << (w - 1))) + (double)bits / (w + 1);
         if (cost < best_cost) { best_cost = cost; best = w; }
     }
