@@ -285,6 +285,21 @@ def main() -> None:
                  "dec_program": {"limbs": Sd, "sqr": d_sqr, "mul": d_mul, "mac32_per_item": dec_macs}}
 
     if not args.no_extras:
+        # EncryptWithR by the key holder (r^n over p^2 and q^2, pgpu_encrypt_with_r_sk): same ciphertexts, outside the timed steps
+        c2_dev = torch.empty_like(c_dev)
+        check(lib.pgpu_encrypt_with_r_sk_dev(sk._ctx, count, vp(m_dev), vp(r_dev), vp(c2_dev)), sk._ctx)
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        es[0].record(stream)
+        check(lib.pgpu_encrypt_with_r_sk_dev(sk._ctx, count, vp(m_dev), vp(r_dev), vp(c2_dev)), sk._ctx)
+        es[1].record(stream)
+        barrier()
+        assert torch.equal(c2_dev, c_dev), "secret-key EncryptWithR differs from the public-key path"
+        breakdown["enc_sk_per_s"] = world * count / (max_over_ranks(es[0].elapsed_time(es[1])) * 1e-3)
+        Sk, k_sqr, k_mul = sk.program_cost(3)
+        breakdown["enc_sk_program"] = {"limbs": Sk, "sqr": k_sqr, "mul": k_mul, "mac32_per_item": mont_macs(Sk, k_sqr, k_mul)}
+        del c2_dev
+
         # threshold PartialDecrypt at 2048-bit n (BASELINE metric's partial-dec/s), outside the timed steps
         from paillier_b200.keygen import ThresholdKeyGenerator
         tp, tq = synth.load_key("threshold_2048")

@@ -28,6 +28,7 @@ type GPUContext struct {
 	ctx            *C.pgpu_ctx
 	wN, wN2, wN3   int
 	wZ             int
+	secret         bool // p, q are loaded: EncryptWithRBatch may use them
 }
 
 func gpuErr(ctx *C.pgpu_ctx, rc C.int) error {
@@ -69,6 +70,7 @@ func (sk *SecretKey) NewGPUContext(device int) (*GPUContext, error) {
 		g.Close()
 		return nil, err
 	}
+	g.secret = true
 	return g, nil
 }
 
@@ -122,7 +124,13 @@ func (g *GPUContext) EncryptWithRBatch(ms, rs []*gmp.Int) ([]*Ciphertext, error)
 	}
 	m, r := toRecords(ms, g.wN), toRecords(rs, g.wN)
 	c := make([]byte, len(ms)*g.wN2)
-	if err := gpuErr(g.ctx, C.pgpu_encrypt_with_r(g.ctx, C.size_t(len(ms)), ptr(m), ptr(r), ptr(c))); err != nil {
+	var rc C.int
+	if g.secret { // context made from a SecretKey: r^n over p^2 and q^2, the same ciphertexts at about twice the rate
+		rc = C.pgpu_encrypt_with_r_sk(g.ctx, C.size_t(len(ms)), ptr(m), ptr(r), ptr(c))
+	} else {
+		rc = C.pgpu_encrypt_with_r(g.ctx, C.size_t(len(ms)), ptr(m), ptr(r), ptr(c))
+	}
+	if err := gpuErr(g.ctx, rc); err != nil {
 		return nil, err
 	}
 	out := make([]*Ciphertext, len(ms))

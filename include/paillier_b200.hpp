@@ -4,6 +4,7 @@
 //
 //   paillier::PublicKey::EncryptWithRBatch        <- PublicKey.EncryptWithR            paillier.go:185-187,206-218
 //   paillier::SecretKey::DecryptBatch             <- SecretKey.Decrypt                 paillier.go:292-303
+//   paillier::SecretKey::EncryptWithRBatch        <- EncryptWithR on a SecretKey (CRT)  paillier.go:29-34,206-218
 //   paillier::PublicKey::ConstMultBatch / AddBatch / SubPairs  <- operations.go:11-64
 //   paillier::ThresholdSecretKey::PartialDecryptBatch / PartialDecryptionWithZKPBatch  <- thresholdkey.go:192-255
 //   paillier::ThresholdPublicKey::VerifyProofBatch / CombinePartialDecryptionsBatch    <- thresholdkey.go:149-172,278-311
@@ -159,6 +160,15 @@ public:
     }
     SecretKey(const Int& n, const Int& p, const Int& q, int device) : PublicKey(n, device) {
         check(pgpu_ctx_set_secret_pq(ctx_, p.data(), p.size(), q.data(), q.size()));
+    }
+    // N x EncryptWithR through the embedded PublicKey (paillier.go:29-34): the same ciphertexts as
+    // PublicKey::EncryptWithRBatch, computed over p^2 and q^2 (pgpu_encrypt_with_r_sk)
+    std::vector<Ciphertext> EncryptWithRBatch(const std::vector<Int>& ms, const std::vector<Int>& rs) {
+        if (ms.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per plaintext");
+        auto m = detail::to_records(ms, w_n), r = detail::to_records(rs, w_n);
+        std::vector<uint8_t> c(ms.size() * w_n2);
+        check(pgpu_encrypt_with_r_sk(ctx_, ms.size(), m.data(), r.data(), c.data()));
+        return wrap(detail::from_records(c, w_n2), EncLevelOne, RegularEncryption);
     }
     // N x SecretKey.Decrypt (paillier.go:292-303), level 1
     std::vector<Int> DecryptBatch(const std::vector<Ciphertext>& cts) {

@@ -51,6 +51,8 @@ SIGNATURES = {
     "pgpu_modexp_shared": (C.c_int, [_p, C.c_int, _sz, _p, _u8p, _sz, _p]),
     "pgpu_modmul": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_r_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_encrypt_with_r_sk": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_encrypt_with_r_sk_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_decrypt_dev": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_partial_decrypt_dev": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_const_mult_dev": (C.c_int, [_p, _sz, _p, _p, _sz, _p]),

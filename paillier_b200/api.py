@@ -404,6 +404,17 @@ class SecretKey(PublicKey):
         else:
             raise ValueError("SecretKey needs Lambda or (p, q)")
 
+    def encrypt_with_r_records(self, m, r) -> np.ndarray:
+        """EncryptWithR reached through the embedded PublicKey (paillier.go:29-34): same ciphertexts as
+        PublicKey.encrypt_with_r_records, computed over p^2 and q^2 (pgpu_encrypt_with_r_sk)."""
+        m = np.ascontiguousarray(m).view(np.uint8).reshape(-1)
+        count = m.size // self.w_n
+        m = _as_u8(m, count * self.w_n, "m")
+        r = _as_u8(r, count * self.w_n, "r")
+        out = np.empty(count * self.w_n2, dtype=np.uint8)
+        check(lib.pgpu_encrypt_with_r_sk(self._ctx, count, _ptr(m), _ptr(r), _ptr(out)), self._ctx)
+        return out
+
     def decrypt_records(self, c) -> np.ndarray:
         c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)
         count = c.size // self.w_n2

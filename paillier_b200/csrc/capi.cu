@@ -75,6 +75,7 @@ int pgpu_ctx_destroy(pgpu_ctx* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     modctx_free(ctx->m_n); modctx_free(ctx->m_n2); modctx_free(ctx->m_n3); modctx_free(ctx->m_p2); modctx_free(ctx->m_q2);
     program_free(ctx->prog_enc); program_free(ctx->prog_dec_p); program_free(ctx->prog_dec_q); program_free(ctx->prog_pdec);
+    program_free(ctx->prog_encq); program_free(ctx->prog_encp); program_free(ctx->prog_encf);
     for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
     protocols_free(ctx);
     if (ctx->d_crt) cudaFree(ctx->d_crt);
@@ -176,6 +177,15 @@ int pgpu_encrypt_with_r_dev(pgpu_ctx* ctx, size_t count, const void* m, const vo
     GUARD_END(ctx)
 }
 
+int pgpu_encrypt_with_r_sk_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r_sk: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return encrypt_crt_dev(ctx, count, (const uint32_t*)m, (const uint32_t*)r, (uint32_t*)c);
+    GUARD_END(ctx)
+}
+
 int pgpu_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* m) {
     GUARD_BEGIN
     REQUIRE(ctx, ctx && (count == 0 || (m && c)), "pgpu_decrypt: null argument");
@@ -272,6 +282,23 @@ int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* 
     uint32_t* dc = io.out(2, count * w2);
     if (io.rc) return io.rc;
     { TimedScope ts(ctx); if ((rc = encrypt_dev(ctx, count, dm, dr, dc))) return rc; }
+    return io.finish(c, dc, count * w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_encrypt_with_r_sk(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r_sk: null argument");
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "EncryptWithR (secret key): no secret key loaded");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dm = io.in(0, m, count * wn);
+    uint32_t* dr = io.in(1, r, count * wn);
+    uint32_t* dc = io.out(2, count * w2);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = encrypt_crt_dev(ctx, count, dm, dr, dc))) return rc; }
     return io.finish(c, dc, count * w2);
     GUARD_END(ctx)
 }
@@ -795,6 +822,9 @@ int pgpu_ctx_program_cost(const pgpu_ctx* ctx, int what, uint32_t* limbs, uint32
         case 2:
             if (!ctx->has_share) return fail(nullptr, PGPU_ERR_STATE, "no share");
             S = ctx->m_n2.sh.S; sq = ctx->prog_pdec.n_sqr; mu = ctx->prog_pdec.n_mul; break;
+        case 3:
+            if (!ctx->has_enc_crt) return fail(nullptr, PGPU_ERR_STATE, "no secret-key encryption programs");
+            S = ctx->m_p2.sh.S; sq = ctx->prog_encq.n_sqr + ctx->prog_encp.n_sqr; mu = ctx->prog_encq.n_mul + ctx->prog_encp.n_mul; break;
         default: return fail(nullptr, PGPU_ERR_ARG, "bad selector");
     }
     if (limbs) *limbs = S;

@@ -261,6 +261,69 @@ int build_pdec(pgpu_ctx* ctx) {
     return program_upload(ctx, P);
 }
 
+// EncryptWithR for the holder of p, q (paillier.go:206-218 gives the same c for every caller; SecretKey embeds
+// PublicKey, paillier.go:29-34): r^n is computed mod q^2 and mod p^2 (two half-width exponentiations, 1/4 of the
+// n^2 cost each), recombined with Garner's formula x = x_q + q^2 * ((x_p - x_q) * q^-2 mod p^2), and multiplied
+// by g^m = 1 + m*n mod n^2.  No coprimality assumption: the exponent n is used unreduced.
+int setup_encrypt_crt(pgpu_ctx* ctx) {
+    ctx->has_enc_crt = false;
+    ModCtx &P2 = ctx->m_p2, &N2 = ctx->m_n2;
+    if (ctx->wn > (size_t)P2.sh.S || (size_t)P2.sh.S > (size_t)N2.sh.S) return PGPU_OK;   // r does not fit a p^2 record: general path
+    const BigU p2 = ctx->p * ctx->p, q2 = ctx->q * ctx->q;
+    BigU q2inv;
+    if (!BigU::modinv(q2 % p2, p2, q2inv)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
+    int rc;
+    if ((rc = set_kconst(ctx, P2, K_CRT, q2inv))) return rc;
+    if ((rc = set_kconst(ctx, N2, K_CRT, (q2 * N2.R2) % N2.N))) return rc;
+    {   // x_q = r^n mod q^2.  in0 = r
+        Program& P = ctx->prog_encq;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;       // r < n may exceed q^2: the Montgomery product reduces it
+        emit_pow_shared(P, ctx->n, 0);
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    {   // t = (r^n - x_q) * q^-2 mod p^2.  in0 = r, in1 = x_q
+        Program& P = ctx->prog_encp;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_pow_shared(P, ctx->n, 0);
+        const uint32_t XP = P.tbl_entries, XQ = XP + 1;
+        P.emit(OP_STT, XP); P.use_slot(XP);
+        P.emit(OP_LDI, 1);
+        P.emit(OP_MULC, K_R2); P.n_mul++;       // x_q mod p^2, Montgomery form
+        P.emit(OP_STT, XQ); P.use_slot(XQ);
+        P.emit(OP_LDT, XP);
+        P.emit(OP_SUBT, XQ);
+        P.emit(OP_MULC, K_CRT); P.n_mul++;      // times the plain constant: leaves Montgomery form
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    {   // c = (x_q + q^2*t) * (1 + m*n) mod n^2.  in0 = t, in1 = x_q, in2 = m
+        Program& P = ctx->prog_encf;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_CRT); P.n_mul++;      // q^2*t, Montgomery form
+        P.emit(OP_STT, 0); P.use_slot(0);
+        P.emit(OP_LDI, 1);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        P.emit(OP_ADDT, 0);                     // r^n mod n^2 (x_q + q^2*t < n^2: the modular add is exact)
+        P.emit(OP_STT, 0);
+        P.emit(OP_LDI, 2);
+        P.emit(OP_MULC, K_NR2); P.n_mul++;
+        P.emit(OP_ADDC, K_R1);                  // g^m = 1 + m*n
+        P.emit(OP_MULT, 0); P.n_mul++;
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    ctx->has_enc_crt = true;
+    return PGPU_OK;
+}
+
 int setup_crt(pgpu_ctx* ctx) {
     const BigU &p = ctx->p, &q = ctx->q;
     int rc;
@@ -291,6 +354,7 @@ int setup_crt(pgpu_ctx* ctx) {
     if ((rc = upload(ctx, ctx->d_crt, K))) return rc;
     ctx->crt_np0_p = mont_np0(p.v[0]); ctx->crt_np0_q = mont_np0(q.v[0]);
     ctx->has_secret = true;
+    if ((rc = setup_encrypt_crt(ctx))) return rc;
     return setup_level2_secret(ctx);
 }
 
@@ -321,6 +385,22 @@ int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
     CU(ctx, crt_combine_launch(C, ctx->stream));
     ctx->launches++;
     return PGPU_OK;
+}
+
+int encrypt_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "EncryptWithR (secret key): no secret key loaded");
+    if (!ctx->has_enc_crt) return encrypt_dev(ctx, count, m, r, c);
+    const ModCtx &P2 = ctx->m_p2, &Q2 = ctx->m_q2, &N2 = ctx->m_n2;
+    const uint32_t Sp = P2.sh.S, wn = (uint32_t)ctx->wn;
+    void *xq, *t; int rc;
+    if ((rc = stage(ctx, 4, count * Sp * 4, &xq))) return rc;
+    if ((rc = stage(ctx, 5, count * Sp * 4, &t))) return rc;
+    IoDesc iq[1] = {{r, wn, wn}};
+    if ((rc = run_vm(ctx, Q2, ctx->prog_encq, count, iq, 1, (uint32_t*)xq, Sp, Sp))) return rc;
+    IoDesc ip[2] = {{r, wn, wn}, {(const uint32_t*)xq, Sp, Sp}};
+    if ((rc = run_vm(ctx, P2, ctx->prog_encp, count, ip, 2, (uint32_t*)t, Sp, Sp))) return rc;
+    IoDesc fin[3] = {{(const uint32_t*)t, Sp, Sp}, {(const uint32_t*)xq, Sp, Sp}, {m, wn, wn}};
+    return run_vm(ctx, N2, ctx->prog_encf, count, fin, 3, c, N2.sh.S, N2.sh.S);
 }
 
 int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out) {

@@ -30,6 +30,7 @@ enum : uint32_t {
     K_NM = 8,     // n                          (Montgomery form)
     K_NSM = 9,    // n^s for the modulus n^(s+1) (Montgomery form; g^(-v) = g^(n^s - v))
     K_R4 = 10,    // R^4 mod N
+    K_CRT = 11,   // secret-key EncryptWithR: q^-2 mod p^2 (plain) in the p^2 context, q^2 * R^2 mod n^2 in the n^2 context
     K_SLOTS = 16
 };
 
@@ -85,6 +86,8 @@ struct pgpu_ctx {
     std::vector<pgpu::BigU> tk_vi;
 
     pgpu::Program prog_enc, prog_dec_p, prog_dec_q, prog_pdec;
+    pgpu::Program prog_encq, prog_encp, prog_encf;   // secret-key EncryptWithR over p^2, q^2 (encrypt_crt_dev)
+    bool has_enc_crt = false;
 
     // level 2 (mod n^3), alternative encryption, randomness extraction (protocols.cu)
     bool level2_ready = false;
@@ -181,6 +184,7 @@ int build_decrypt_half(pgpu_ctx* ctx, Program& P, const BigU& pm1);
 int setup_crt(pgpu_ctx* ctx);
 int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
+int encrypt_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out);
 Program* cached_program(pgpu_ctx* ctx, const std::string& key);
 int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,

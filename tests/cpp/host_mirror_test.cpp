@@ -27,7 +27,9 @@ int main() {
             Int add_all = rd();
             SecretKey sk(N, lambda);
             auto cts = sk.EncryptWithRBatch(ms, rs);
-            for (size_t i = 0; i < count; ++i) expect(cts[i].C == cs[i], "EncryptWithRBatch");
+            for (size_t i = 0; i < count; ++i) expect(cts[i].C == cs[i], "SecretKey::EncryptWithRBatch");
+            auto pub = static_cast<PublicKey&>(sk).EncryptWithRBatch(ms, rs);
+            for (size_t i = 0; i < count; ++i) expect(pub[i].C == cs[i], "PublicKey::EncryptWithRBatch");
             expect(sk.DecryptBatch(cts) == ms, "DecryptBatch");
             auto cm = sk.ConstMultBatch(cts, ks);
             for (size_t i = 0; i < count; ++i) expect(cm[i].C == cks[i], "ConstMultBatch");

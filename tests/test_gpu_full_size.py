@@ -6,7 +6,7 @@ import pytest
 
 from oracle import gmp_ref as G
 from paillier_b200 import synth
-from paillier_b200.api import Ciphertext, SecretKey, from_records
+from paillier_b200.api import Ciphertext, PublicKey, SecretKey, from_records
 
 pytestmark = pytest.mark.gpu
 
@@ -18,7 +18,8 @@ def test_config2_full_batch_properties():
     count = 1 << 20
     m = synth.plaintexts(count, n, sk.w_n)
     r = synth.randomness(count, n, sk.w_n)
-    c = sk.encrypt_with_r_records(m, r)
+    c = PublicKey.encrypt_with_r_records(sk, m, r)               # public-key path: r^n mod n^2
+    assert np.array_equal(sk.encrypt_with_r_records(m, r), c)    # secret-key path (CRT over p^2, q^2): same 2^20 ciphertexts
     for lo in (0, 9472 * 55 - 16, count - 128):                  # head, a round boundary of the persistent grid, tail
         sl = slice(lo * sk.w_n, (lo + 128) * sk.w_n)
         assert np.array_equal(c[lo * sk.w_n2:(lo + 128) * sk.w_n2], G.encrypt_with_r(n, m[sl], r[sl], sk.w_n))

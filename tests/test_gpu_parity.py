@@ -58,9 +58,32 @@ def test_encrypt_decrypt_parity_python_oracle(name):
     ms = from_records(synth.plaintexts(12, n, sk.w_n), sk.w_n)
     rs = from_records(synth.randomness(12, n, sk.w_n), sk.w_n)
     ms[0], ms[1], ms[2], rs[3], rs[4] = 0, n - 1, 1, 1, n - 1
-    cts = sk.EncryptWithRBatch(ms, rs)
+    cts = sk.EncryptWithRBatch(ms, rs)                               # secret-key path (CRT over p^2, q^2)
     assert [c.C for c in cts] == [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms, rs)]
+    pub = from_records(PublicKey.encrypt_with_r_records(sk, to_records(ms, sk.w_n), to_records(rs, sk.w_n)), sk.w_n2)
+    assert pub == [c.C for c in cts]                                 # public-key path (r^n mod n^2)
     assert sk.DecryptBatch(cts) == ms == [R.decrypt(osk, R.Ciphertext(c.C)) for c in cts]
+    sk.close()
+
+
+@pytest.mark.parametrize("name", ["paillier_64", "paillier_1024", "paillier_2048", "threshold_512", "threshold_3072"])
+def test_secret_key_encrypt_edge_randomness(name):
+    """EncryptWithR over p^2, q^2 with r values that stress the recombination: multiples of p and q (r^n = 0 mod p^2),
+    r on either side of p^2 and q^2, r = 0 (the reference does not reject it: c = 0), against both oracles and the
+    public-key path."""
+    p, q, n = _key(name)
+    osk, opk = R.keygen_from_primes(p, q)
+    sk = SecretKey(n, p=p, q=q)
+    lo2, hi2 = min(p * p, q * q), max(p * p, q * q)
+    rs = [0, 1, 2, p, q, 2 * p, 3 * q, p * (q - 1), q * (p - 1), n - 1, n - 2,
+          lo2 % n, (lo2 - 1) % n, (lo2 + 1) % n, hi2 % n, (hi2 - 1) % n, (hi2 + 1) % n, n // 2, n // 3]
+    ms = [(i * 0x9E3779B97F4A7C15 + 7) % n for i in range(len(rs))]
+    ms[0], ms[1], ms[2] = 0, n - 1, 1
+    mrec, rrec = to_records(ms, sk.w_n), to_records(rs, sk.w_n)
+    got = from_records(sk.encrypt_with_r_records(mrec, rrec), sk.w_n2)
+    assert got == [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms, rs)]
+    assert got == from_records(PublicKey.encrypt_with_r_records(sk, mrec, rrec), sk.w_n2)
+    assert got == from_records(G.encrypt_with_r(n, mrec, rrec, sk.w_n), sk.w_n2)
     sk.close()
 
 
@@ -78,7 +101,8 @@ def test_encrypt_decrypt_2048_large_batch_vs_libgmp(sk2048):
     n, count = sk.N, 20011
     m = synth.plaintexts(count, n, sk.w_n)
     r = synth.randomness(count, n, sk.w_n)
-    c = sk.encrypt_with_r_records(m, r)
+    c = PublicKey.encrypt_with_r_records(sk, m, r)
+    assert np.array_equal(sk.encrypt_with_r_records(m, r), c)        # secret-key path over the same ragged batch
     nref = 4096
     ref = G.encrypt_with_r(n, m[:nref * sk.w_n], r[:nref * sk.w_n], sk.w_n)
     assert np.array_equal(c[:nref * sk.w_n2], ref)
