@@ -58,7 +58,10 @@ struct Error : std::runtime_error {
 enum EncryptionLevel { EncLevelOne = 0, EncLevelTwo = 1 };                               // paillier.go:17-23
 enum EncryptionMethod { RegularEncryption = 0, AlternativeEncryption = 1, MixedEncryption = 2 };   // paillier.go:29-39
 
-struct Ciphertext { Int C; int Level = EncLevelOne; int EncMethod = RegularEncryption; };          // paillier.go:65-69
+struct Ciphertext {                                                                                 // paillier.go:65-69
+    Int C; int Level = EncLevelOne; int EncMethod = RegularEncryption;
+    std::vector<uint8_t> Bytes() const;                  // Ciphertext.Bytes, paillier.go:392-401 (encoding/gob stream)
+};
 struct PartialDecryption { int ID = 0; Int Decryption; };                                           // thresholdkey.go:45-48
 struct PartialDecryptionZKP { int ID = 0; Int Decryption, E, Z, C; };                               // thresholdkey.go:52-58
 
@@ -85,6 +88,154 @@ inline std::vector<Int> from_records(const std::vector<uint8_t>& buf, size_t wid
 }
 }  // namespace detail
 
+// Wire format of a Ciphertext: Go's encoding/gob stream of struct{C *gmp.Int; Level, EncMethod int} written by a fresh
+// encoder (paillier.go:374-401).  Restated from the encoding/gob specification and ncw/gmp's Int.GobEncode
+// (version<<1|sign, big-endian magnitude); host-side marshalling only.  Same layout as paillier_b200/gobwire.py.
+namespace gob {
+inline void put_uint(std::vector<uint8_t>& o, uint64_t u) {
+    if (u < 128) { o.push_back((uint8_t)u); return; }
+    int n = 0;
+    for (uint64_t t = u; t; t >>= 8) ++n;
+    o.push_back((uint8_t)(256 - n));
+    for (int i = n - 1; i >= 0; --i) o.push_back((uint8_t)(u >> (8 * i)));
+}
+inline void put_int(std::vector<uint8_t>& o, int64_t i) { put_uint(o, i < 0 ? ((uint64_t)~i << 1) | 1 : (uint64_t)i << 1); }
+inline void put_string(std::vector<uint8_t>& o, const std::string& s) { put_uint(o, s.size()); o.insert(o.end(), s.begin(), s.end()); }
+inline void put_named_id(std::vector<uint8_t>& o, const std::string& name, int64_t id) {   // {Name, Id} + end of struct
+    o.push_back(1); put_string(o, name); o.push_back(1); put_int(o, id); o.push_back(0);
+}
+inline void put_message(std::vector<uint8_t>& o, const std::vector<uint8_t>& body) { put_uint(o, body.size()); o.insert(o.end(), body.begin(), body.end()); }
+
+struct Reader {
+    const uint8_t* d; size_t p, end;
+    size_t left() const { return end - p; }
+    const uint8_t* take(size_t n) { if (n > left()) throw Error(PGPU_ERR_ARG, "unexpected EOF"); const uint8_t* r = d + p; p += n; return r; }
+    uint64_t uint() {
+        uint8_t b = *take(1);
+        if (b < 128) return b;
+        size_t n = 256 - b;
+        if (n > 8) throw Error(PGPU_ERR_ARG, "encoded unsigned integer out of range");
+        const uint8_t* q = take(n);
+        uint64_t v = 0;
+        for (size_t i = 0; i < n; ++i) v = v << 8 | q[i];
+        return v;
+    }
+    int64_t sint() { uint64_t u = uint(); return (u & 1) ? ~(int64_t)(u >> 1) : (int64_t)(u >> 1); }
+    std::string string() { size_t n = (size_t)uint(); const uint8_t* q = take(n); return std::string(q, q + n); }
+    std::pair<std::string, int64_t> named_id() {           // CommonType / fieldType: {Name string; Id typeId}
+        std::string name; int64_t id = 0; int f = -1;
+        for (;;) {
+            uint64_t dl = uint();
+            if (dl == 0) return {name, id};
+            f += (int)dl;
+            if (f == 0) name = string(); else if (f == 1) id = sint(); else throw Error(PGPU_ERR_ARG, "gob: unknown field in a type description");
+        }
+    }
+};
+
+inline std::vector<uint8_t> encode(const Ciphertext& ct, int64_t struct_id = 65) {
+    const int64_t int_id = struct_id + 1;
+    std::vector<uint8_t> out, b;
+    put_int(b, -struct_id); b.push_back(3);                 // wireType.StructT
+    b.push_back(1); put_named_id(b, "Ciphertext", struct_id);
+    b.push_back(1); put_uint(b, 3);
+    put_named_id(b, "C", int_id); put_named_id(b, "Level", 2); put_named_id(b, "EncMethod", 2);
+    b.push_back(0); b.push_back(0);
+    put_message(out, b); b.clear();
+    put_int(b, -int_id); b.push_back(5);                    // wireType.GobEncoderT
+    b.push_back(1); put_named_id(b, "Int", int_id);
+    b.push_back(0); b.push_back(0);
+    put_message(out, b); b.clear();
+    put_int(b, struct_id);
+    b.push_back(1); put_uint(b, ct.C.size() + 1); b.push_back(2); b.insert(b.end(), ct.C.begin(), ct.C.end());
+    int last = 0;
+    const int vals[2] = {ct.Level, ct.EncMethod};
+    for (int i = 0; i < 2; ++i)
+        if (vals[i] != 0) { put_uint(b, (uint64_t)(i + 1 - last)); put_int(b, vals[i]); last = i + 1; }
+    b.push_back(0);
+    put_message(out, b);
+    return out;
+}
+
+inline Ciphertext decode(const uint8_t* data, size_t len) {
+    if (len == 0) throw Error(PGPU_ERR_ARG, "no data provided");                         // paillier.go:377-379
+    struct Type { bool is_struct = false; std::vector<std::pair<std::string, int64_t>> fields; };
+    std::vector<std::pair<int64_t, Type>> types;
+    auto find = [&](int64_t id) -> const Type* { for (auto& t : types) if (t.first == id) return &t.second; return nullptr; };
+    Reader top{data, 0, len};
+    while (top.left() > 0) {
+        size_t n = (size_t)top.uint();
+        top.take(n);
+        Reader r{data, top.p - n, top.p};
+        int64_t tid = r.sint();
+        if (tid < 0) {
+            if (find(-tid)) throw Error(PGPU_ERR_ARG, "gob: duplicate type received");
+            Type t;
+            uint64_t kind = r.uint();
+            if (kind == 3) {
+                t.is_struct = true;
+                int f = -1;
+                for (;;) {
+                    uint64_t dl = r.uint();
+                    if (dl == 0) break;
+                    f += (int)dl;
+                    if (f == 0) r.named_id();
+                    else if (f == 1) { for (uint64_t k = r.uint(); k > 0; --k) t.fields.push_back(r.named_id()); }
+                    else throw Error(PGPU_ERR_ARG, "gob: unknown field in structType");
+                }
+            } else if (kind >= 5 && kind <= 7) {
+                uint64_t f = r.uint();
+                if (f == 1) { r.named_id(); if (r.uint() != 0) throw Error(PGPU_ERR_ARG, "gob: unknown field in gobEncoderType"); }
+                else if (f != 0) throw Error(PGPU_ERR_ARG, "gob: unknown field in gobEncoderType");
+            } else throw Error(PGPU_ERR_ARG, "gob: type definition not used by a Ciphertext stream");
+            if (r.uint() != 0) throw Error(PGPU_ERR_ARG, "gob: wireType with more than one kind");
+            types.emplace_back(-tid, t);
+            continue;
+        }
+        const Type* t = find(tid);
+        if (!t || !t->is_struct) throw Error(PGPU_ERR_ARG, "gob: type mismatch: no fields matched compiling decoder for Ciphertext");
+        Ciphertext ct;
+        int f = -1;
+        for (;;) {
+            uint64_t dl = r.uint();
+            if (dl == 0) break;
+            f += (int)dl;
+            if ((size_t)f >= t->fields.size()) throw Error(PGPU_ERR_ARG, "gob: field number out of range");
+            const std::string& name = t->fields[f].first;
+            const int64_t ft = t->fields[f].second;
+            const Type* ftype = ft >= 64 ? find(ft) : nullptr;
+            if ((ftype && !ftype->is_struct) || ft == 5 || ft == 6) {
+                size_t bl = (size_t)r.uint();
+                const uint8_t* q = r.take(bl);
+                if (name == "C") {
+                    if (!ftype) throw Error(PGPU_ERR_ARG, "gob: wrong type for field C");
+                    if (bl > 0) {
+                        if ((q[0] >> 1) != 1) throw Error(PGPU_ERR_ARG, "Int.GobDecode: encoding version not supported");
+                        if (q[0] & 1) throw Error(PGPU_ERR_ARG, "negative ciphertext value");
+                        size_t z = 1;
+                        while (z < bl && q[z] == 0) ++z;
+                        ct.C.assign(q + z, q + bl);
+                    }
+                }
+            } else if (ft == 2) {
+                int64_t v = r.sint();
+                if (name == "Level") ct.Level = (int)v; else if (name == "EncMethod") ct.EncMethod = (int)v;
+            } else if (ft == 1 || ft == 3 || ft == 4) {
+                r.uint();
+                if (name == "Level" || name == "EncMethod") throw Error(PGPU_ERR_ARG, "gob: wrong type for field " + name);
+            } else throw Error(PGPU_ERR_ARG, "gob: cannot skip a field of this type");
+        }
+        if (r.left() != 0) throw Error(PGPU_ERR_ARG, "gob: extra data in message");
+        return ct;
+    }
+    throw Error(PGPU_ERR_ARG, "unexpected EOF");
+}
+}  // namespace gob
+
+inline std::vector<uint8_t> Ciphertext::Bytes() const { return gob::encode(*this); }
+// PublicKey.NewCiphertextFromBytes (paillier.go:374-390); like the reference it needs no key material and does not range-check C
+inline Ciphertext NewCiphertextFromBytes(const std::vector<uint8_t>& data) { return gob::decode(data.data(), data.size()); }
+
 // PublicKey{N} with g = n+1 (paillier.go:46-56,147); owns one engine context on `device`.
 class PublicKey {
 public:
@@ -96,6 +247,8 @@ public:
     virtual ~PublicKey() { if (ctx_) pgpu_ctx_destroy(ctx_); }
     PublicKey(const PublicKey&) = delete;
     PublicKey& operator=(const PublicKey&) = delete;
+
+    Ciphertext NewCiphertextFromBytes(const std::vector<uint8_t>& data) const { return paillier::NewCiphertextFromBytes(data); }
 
     // N x PublicKey.EncryptWithR (paillier.go:185-187)
     std::vector<Ciphertext> EncryptWithRBatch(const std::vector<Int>& ms, const std::vector<Int>& rs) {

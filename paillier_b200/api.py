@@ -64,6 +64,11 @@ class Ciphertext:
     Level: int = ENC_LEVEL_ONE
     EncMethod: int = REGULAR
 
+    def Bytes(self) -> bytes:
+        """Ciphertext.Bytes (paillier.go:392-401): the encoding/gob stream of the struct (gobwire.py)"""
+        from .gobwire import encode_ciphertext
+        return encode_ciphertext(self.C, self.Level, self.EncMethod)
+
 
 @dataclass
 class PartialDecryption:
@@ -140,6 +145,17 @@ class PublicKey:
             self.close()
         except Exception:
             pass
+
+    def NewCiphertextFromBytes(self, data: bytes) -> Ciphertext:
+        """PublicKey.NewCiphertextFromBytes (paillier.go:374-390); like the reference it does not range-check C"""
+        from .gobwire import decode_ciphertext
+        return Ciphertext(*decode_ciphertext(data))
+
+    def CiphertextsToBytes(self, cts: Sequence[Ciphertext]) -> List[bytes]:
+        return [c.Bytes() for c in cts]
+
+    def NewCiphertextsFromBytes(self, blobs: Sequence[bytes]) -> List[Ciphertext]:
+        return [self.NewCiphertextFromBytes(b) for b in blobs]
 
     # -- cached moduli (paillier.go:72-90)
     def GetN2(self) -> int:

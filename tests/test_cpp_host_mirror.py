@@ -54,3 +54,28 @@ def test_host_mirror_reproduces_golden_vectors():
     r = subprocess.run([EXE], input=_input(), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "host mirror ok" in r.stdout
+
+
+def test_cpp_gob_wire_format_matches_python_mirror():
+    """Ciphertext.Bytes / NewCiphertextFromBytes of the C++ mirror against paillier_b200/gobwire.py (no GPU needed)."""
+    import random
+    from paillier_b200 import gobwire as W
+    libdir = os.path.join(ROOT, "paillier_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "gob_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "gob_test.cpp"),
+                    "-o", exe, "-L", libdir, "-lpaillier_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    rnd = random.Random(8)
+    cases = [(0, 0, 0), (1, 0, 0), (0x1234, 1, 1), (127, 0, 2), (128, 1, 0)]
+    cases += [(rnd.getrandbits(b) | 1 << (b - 1), rnd.randrange(2), rnd.randrange(3)) for b in (64, 1016, 1024, 4096, 6144)]
+    lines = [f"enc {c:x} {l} {m}" for c, l, m in cases]
+    lines += ["dec " + W.encode_ciphertext(c, l, m, struct_id=65 + i).hex() for i, (c, l, m) in enumerate(cases)]
+    good = W.encode_ciphertext(2 ** 200 + 5, 0, 0)
+    lines += ["dec -", "dec " + good[:-3].hex(), "dec " + good[good.index(b"\xff\x83") - 1:].hex()]
+    r = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.split("\n")
+    k = len(cases)
+    assert out[:k] == [W.encode_ciphertext(c, l, m).hex() for c, l, m in cases]
+    assert out[k:2 * k] == [f"{hex(c)} {l} {m}" for c, l, m in cases]
+    assert out[2 * k] == "error no data provided"
+    assert out[2 * k + 1].startswith("error ") and out[2 * k + 2].startswith("error ")
