@@ -298,7 +298,18 @@ def main() -> None:
         breakdown["enc_sk_per_s"] = world * count / (max_over_ranks(es[0].elapsed_time(es[1])) * 1e-3)
         Sk, k_sqr, k_mul = sk.program_cost(3)
         breakdown["enc_sk_program"] = {"limbs": Sk, "sqr": k_sqr, "mul": k_mul, "mac32_per_item": mont_macs(Sk, k_sqr, k_mul)}
-        del c2_dev
+        # online half of an offline/online EncryptWithR: c = (1 + m*n) * rn with rn = r^n precomputed (pgpu_encrypt_with_rn)
+        check(lib.pgpu_encrypt_with_r_sk_dev(sk._ctx, count, vp(torch.zeros_like(m_dev)), vp(r_dev), vp(c2_dev)), sk._ctx)   # the pool
+        c3_dev = torch.empty_like(c_dev)
+        check(lib.pgpu_encrypt_with_rn_dev(sk._ctx, count, vp(m_dev), vp(c2_dev), vp(c3_dev)), sk._ctx)
+        barrier()
+        es[0].record(stream)
+        check(lib.pgpu_encrypt_with_rn_dev(sk._ctx, count, vp(m_dev), vp(c2_dev), vp(c3_dev)), sk._ctx)
+        es[1].record(stream)
+        barrier()
+        assert torch.equal(c3_dev, c_dev), "EncryptWithRn(m, r^n) differs from EncryptWithR(m, r)"
+        breakdown["enc_online_per_s"] = world * count / (max_over_ranks(es[0].elapsed_time(es[1])) * 1e-3)
+        del c2_dev, c3_dev
 
         # threshold PartialDecrypt at 2048-bit n (BASELINE metric's partial-dec/s), outside the timed steps
         from paillier_b200.keygen import ThresholdKeyGenerator
@@ -423,6 +434,16 @@ def main() -> None:
         breakdown["level2_enc_e2e_per_s"] = world * lcount / max_over_ranks(t1 - t0)
         breakdown["level2_dec_e2e_per_s"] = world * lcount / max_over_ranks(t2 - t1)
         breakdown["level2_items"] = lcount
+        l2c_sk = torch.empty_like(l2c)                        # the same ciphertexts by the key holder (r^(n^2) over p^3, q^3)
+        for timed in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            check(lib.pgpu_encrypt_with_r_at_level_sk(sk._ctx, 2, lcount, hp3(l2m), hp3(r_host[:lcount * w_n]), hp3(l2c_sk)), sk._ctx)
+            barrier()
+            t1 = time.perf_counter()
+        assert torch.equal(l2c_sk, l2c), "level 2: secret-key EncryptWithRAtLevel differs from the public-key path"
+        breakdown["level2_enc_sk_e2e_per_s"] = world * lcount / max_over_ranks(t1 - t0)
+        del l2c_sk
         # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI
         if rank == 0:
             from paillier_b200.api import ENC_LEVEL_TWO

@@ -93,6 +93,12 @@ int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* 
  * (two half-width exponentiations, about 2x the throughput).  Needs pgpu_ctx_set_secret. */
 int pgpu_encrypt_with_r_sk(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c);
 
+/* Offline/online EncryptWithR (the r^n pool): rn[i] = r[i]^n mod n^2 is prepared ahead of time --
+ * pgpu_encrypt_with_r (or _sk) with m = 0 returns exactly that -- and the online call is two multiplications:
+ * c[i] = (1 + m[i]*n) * rn[i] mod n^2, the same c as EncryptWithR(m[i], r[i]) (paillier.go:206-218).
+ * m: n-width; rn, c: n2-width.  Each rn must be used once (it is the ciphertext's randomness). */
+int pgpu_encrypt_with_rn(pgpu_ctx* ctx, size_t count, const void* m, const void* rn, void* c);
+
 /* SecretKey.Decrypt (paillier.go:292-303), level 1, computed with CRT over
  * p^2 and q^2.   c: n2-width; m: n-width. */
 int pgpu_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* m);
@@ -140,6 +146,9 @@ int pgpu_combine(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void*
 
 /* PublicKey.EncryptWithRAtLevel (paillier.go:206-218): c = (1+n)^m * r^(n^s) mod n^(s+1); r: n-width */
 int pgpu_encrypt_with_r_at_level(pgpu_ctx* ctx, int level, size_t count, const void* m, const void* r, void* c);
+/* the same ciphertexts for the holder of p, q (pgpu_ctx_set_secret): level 1 = pgpu_encrypt_with_r_sk; level 2 computes
+ * r^(n^2) over p^3 and q^3 with the exponent reduced mod phi (+ phi, so that non-units stay exact) */
+int pgpu_encrypt_with_r_at_level_sk(pgpu_ctx* ctx, int level, size_t count, const void* m, const void* r, void* c);
 /* SecretKey.Decrypt at either level (paillier.go:292-340); level 2 runs recoveryAlgorithm(s = 2) */
 int pgpu_decrypt_at_level(pgpu_ctx* ctx, int level, size_t count, const void* c, void* m);
 /* PublicKey.H and K = 2^k_bits (paillier.go:46-56,151,158-161): enables AltEncrypt; precomputes the
@@ -198,6 +207,7 @@ int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const vo
  * the context's stream and NOT synchronised (the caller owns ordering). */
 int pgpu_encrypt_with_r_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c);
 int pgpu_encrypt_with_r_sk_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c);
+int pgpu_encrypt_with_rn_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* rn, void* c);
 int pgpu_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* m);
 int pgpu_partial_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* out);
 int pgpu_const_mult_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* k, size_t k_bytes, void* out);

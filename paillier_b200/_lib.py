@@ -52,6 +52,8 @@ SIGNATURES = {
     "pgpu_modmul": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_r_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_r_sk": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_encrypt_with_rn": (C.c_int, [_p, _sz, _p, _p, _p]),
+    "pgpu_encrypt_with_rn_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_r_sk_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_decrypt_dev": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_partial_decrypt_dev": (C.c_int, [_p, _sz, _p, _p]),
@@ -71,6 +73,7 @@ SIGNATURES = {
     "pgpu_combine_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
     "pgpu_ctx_set_alt_generator": (C.c_int, [_p, _u8p, _sz, C.c_uint]),
     "pgpu_encrypt_with_r_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
+    "pgpu_encrypt_with_r_at_level_sk": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
     "pgpu_alt_encrypt_with_r_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
     "pgpu_decrypt_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
     "pgpu_randomize_with_r": (C.c_int, [_p, _sz, _p, _p, _p]),

@@ -174,6 +174,21 @@ class PublicKey:
         check(lib.pgpu_encrypt_with_r(self._ctx, count, _ptr(m), _ptr(r), _ptr(out)), self._ctx)
         return out
 
+    def precompute_rn_records(self, r) -> np.ndarray:
+        """r^n mod n^2 for a pool of r values (the offline half of EncryptWithR): EncryptWithR with m = 0."""
+        r = np.ascontiguousarray(r).view(np.uint8).reshape(-1)
+        return self.encrypt_with_r_records(np.zeros(r.size, dtype=np.uint8), r)
+
+    def encrypt_with_rn_records(self, m, rn) -> np.ndarray:
+        """online half: c = (1 + m*n) * rn mod n^2 (pgpu_encrypt_with_rn)"""
+        m = np.ascontiguousarray(m).view(np.uint8).reshape(-1)
+        count = m.size // self.w_n
+        m = _as_u8(m, count * self.w_n, "m")
+        rn = _as_u8(rn, count * self.w_n2, "rn")
+        out = np.empty(count * self.w_n2, dtype=np.uint8)
+        check(lib.pgpu_encrypt_with_rn(self._ctx, count, _ptr(m), _ptr(rn), _ptr(out)), self._ctx)
+        return out
+
     def const_mult_records(self, c, k, k_bytes: int) -> np.ndarray:
         c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)
         count = c.size // self.w_n2
@@ -238,6 +253,17 @@ class PublicKey:
         if len(ms) != len(rs):
             raise ValueError("one r per plaintext")
         out = self.encrypt_with_r_records(to_records(ms, self.w_n), to_records(rs, self.w_n))
+        return [Ciphertext(c, ENC_LEVEL_ONE, REGULAR) for c in from_records(out, self.w_n2)]
+
+    def PrecomputeRnBatch(self, rs: Sequence[int]) -> List[int]:
+        """r^n mod n^2 for later EncryptWithRnBatch calls (each value is one ciphertext's randomness: use it once)"""
+        return from_records(self.precompute_rn_records(to_records(rs, self.w_n)), self.w_n2)
+
+    def EncryptWithRnBatch(self, ms: Sequence[int], rns: Sequence[int]) -> List[Ciphertext]:
+        """N x EncryptWithR (paillier.go:206-218) with r^n already computed: two multiplications per item"""
+        if len(ms) != len(rns):
+            raise ValueError("one r^n per plaintext")
+        out = self.encrypt_with_rn_records(to_records(ms, self.w_n), to_records(rns, self.w_n2))
         return [Ciphertext(c, ENC_LEVEL_ONE, REGULAR) for c in from_records(out, self.w_n2)]
 
     def EncryptBatch(self, ms: Sequence[int], rand=None) -> List[Ciphertext]:
@@ -430,6 +456,14 @@ class SecretKey(PublicKey):
         out = np.empty(count * self.w_n2, dtype=np.uint8)
         check(lib.pgpu_encrypt_with_r_sk(self._ctx, count, _ptr(m), _ptr(r), _ptr(out)), self._ctx)
         return out
+
+    def EncryptWithRAtLevelBatch(self, ms: Sequence[int], rs: Sequence[int], level: int) -> List[Ciphertext]:
+        """EncryptWithRAtLevel reached through the embedded PublicKey: same ciphertexts, r^(n^s) over the prime powers"""
+        wm, wc = self._level_widths(level)
+        mr, rr = to_records(ms, wm), to_records(rs, self.w_n)
+        out = np.empty(len(ms) * wc, dtype=np.uint8)
+        check(lib.pgpu_encrypt_with_r_at_level_sk(self._ctx, level + 1, len(ms), _ptr(mr), _ptr(rr), _ptr(out)), self._ctx)
+        return [Ciphertext(c, level, REGULAR) for c in from_records(out, wc)]
 
     def decrypt_records(self, c) -> np.ndarray:
         c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)

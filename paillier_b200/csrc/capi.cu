@@ -186,6 +186,15 @@ int pgpu_encrypt_with_r_sk_dev(pgpu_ctx* ctx, size_t count, const void* m, const
     GUARD_END(ctx)
 }
 
+int pgpu_encrypt_with_rn_dev(pgpu_ctx* ctx, size_t count, const void* m, const void* rn, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && rn && c)), "pgpu_encrypt_with_rn: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return encrypt_rn_dev(ctx, count, (const uint32_t*)m, (const uint32_t*)rn, (uint32_t*)c);
+    GUARD_END(ctx)
+}
+
 int pgpu_decrypt_dev(pgpu_ctx* ctx, size_t count, const void* c, void* m) {
     GUARD_BEGIN
     REQUIRE(ctx, ctx && (count == 0 || (m && c)), "pgpu_decrypt: null argument");
@@ -299,6 +308,22 @@ int pgpu_encrypt_with_r_sk(pgpu_ctx* ctx, size_t count, const void* m, const voi
     uint32_t* dc = io.out(2, count * w2);
     if (io.rc) return io.rc;
     { TimedScope ts(ctx); if ((rc = encrypt_crt_dev(ctx, count, dm, dr, dc))) return rc; }
+    return io.finish(c, dc, count * w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_encrypt_with_rn(pgpu_ctx* ctx, size_t count, const void* m, const void* rn, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && rn && c)), "pgpu_encrypt_with_rn: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
+    uint32_t* dm = io.in(0, m, count * wn);
+    uint32_t* dr = io.in(1, rn, count * w2);
+    uint32_t* dc = io.out(2, count * w2);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = encrypt_rn_dev(ctx, count, dm, dr, dc))) return rc; }
     return io.finish(c, dc, count * w2);
     GUARD_END(ctx)
 }
@@ -588,6 +613,24 @@ int pgpu_encrypt_with_r_at_level(pgpu_ctx* ctx, int level, size_t count, const v
     uint32_t* dc = io.out(2, count * wc);
     if (io.rc) return io.rc;
     { TimedScope ts(ctx); if ((rc = encrypt2_dev(ctx, count, dm, dr, dc))) return rc; }
+    return io.finish(c, dc, count * wc);
+    GUARD_END(ctx)
+}
+
+int pgpu_encrypt_with_r_at_level_sk(pgpu_ctx* ctx, int level, size_t count, const void* m, const void* r, void* c) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r_at_level_sk: null argument");
+    if (level == 1) return pgpu_encrypt_with_r_sk(ctx, count, m, r, c);
+    size_t wm, wc; int rc;
+    if ((rc = level_widths(ctx, level, &wm, &wc))) return rc;
+    if (count == 0) return PGPU_OK;
+    if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    uint32_t* dm = io.in(0, m, count * wm);
+    uint32_t* dr = io.in(1, r, count * ctx->wn * 4);
+    uint32_t* dc = io.out(2, count * wc);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = encrypt2_crt_dev(ctx, count, dm, dr, dc))) return rc; }
     return io.finish(c, dc, count * wc);
     GUARD_END(ctx)
 }

@@ -387,6 +387,27 @@ int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
     return PGPU_OK;
 }
 
+// Online half of an offline/online encryption: c = (1 + m*n) * rn mod n^2 with rn = r^n mod n^2 computed ahead of
+// time (EncryptWithR with m = 0 yields exactly r^n).  Same c as EncryptWithR(m, r), paillier.go:206-218.
+int encrypt_rn_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* rn, uint32_t* c) {
+    const ModCtx& M = ctx->m_n2;
+    const std::string key = "encrn";
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_NR2); np.n_mul++;       // m*n, Montgomery form
+        np.emit(OP_ADDC, K_R1);                    // + 1
+        np.emit(OP_MULI, 1); np.n_mul++;           // times the plain rn: leaves Montgomery form
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[2] = {{m, (uint32_t)ctx->wn, (uint32_t)ctx->wn}, {rn, (uint32_t)M.sh.S, (uint32_t)M.sh.S}};
+    return run_vm(ctx, M, *P, count, ins, 2, c, M.sh.S, M.sh.S);
+}
+
 int encrypt_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
     if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "EncryptWithR (secret key): no secret key loaded");
     if (!ctx->has_enc_crt) return encrypt_dev(ctx, count, m, r, c);

@@ -95,6 +95,8 @@ struct pgpu_ctx {
     uint32_t* d_rec2 = nullptr;             // constants of recover2_kernel
     pgpu::ModCtx m_p3, m_q3;                // CRT moduli of level-2 Decrypt
     pgpu::Program prog_dec2_p, prog_dec2_q;
+    pgpu::Program prog_enc2q, prog_enc2p, prog_enc2f;   // secret-key EncryptWithRAtLevel(2) over p^3, q^3 (encrypt2_crt_dev)
+    bool enc2_crt_ready = false;
     uint32_t* d_crt2 = nullptr; size_t crt2_cq_off = 0, crt2_g_off = 0;
     uint32_t crt2_np0[4] = {0, 0, 0, 0};
     bool crt2_ready = false;
@@ -185,6 +187,7 @@ int setup_crt(pgpu_ctx* ctx);
 int encrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
 int encrypt_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
+int encrypt_rn_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* rn, uint32_t* c);
 int pdec_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* out);
 Program* cached_program(pgpu_ctx* ctx, const std::string& key);
 int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,
@@ -221,6 +224,7 @@ int setup_level2_secret(pgpu_ctx* ctx);
 int setup_level2_crt(pgpu_ctx* ctx);
 int setup_alt(pgpu_ctx* ctx);
 int encrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
+int encrypt2_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int decrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m);
 int alt_encrypt_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c);
 int randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* out);

@@ -104,6 +104,8 @@ void protocols_free(pgpu_ctx* ctx) {
     if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
     if (ctx->d_crt2) { cudaFree(ctx->d_crt2); ctx->d_crt2 = nullptr; }
     program_free(ctx->prog_dec2_p); program_free(ctx->prog_dec2_q);
+    program_free(ctx->prog_enc2q); program_free(ctx->prog_enc2p); program_free(ctx->prog_enc2f);
+    ctx->enc2_crt_ready = false;
     modctx_free(ctx->m_p3); modctx_free(ctx->m_q3);
     ctx->crt2_ready = false;
 }
@@ -208,6 +210,71 @@ static void crt2_prime_consts(std::vector<uint32_t>& K, const BigU& p, const Big
     push((qinv * rh) % p, h); push(((((inv2 * q) % p) * q) % p * rh) % p, h); push(rh, h);
 }
 
+// EncryptWithRAtLevel(level 2) for the holder of p, q (paillier.go:206-218; SecretKey embeds PublicKey, :29-34):
+// r^(n^2) mod n^3 from r^e mod q^3 and mod p^3 with e = (n^2 mod phi) + phi, phi = P^2 (P-1) of that prime --
+// for r coprime to P that is r^(n^2) by Euler, for P | r both sides are 0 since e >= 3 -- then Garner's step and the
+// g^m factor over n^3.  Exponents of ~3k bits over 3k-bit moduli instead of 4096 bits over 6144.
+static int setup_encrypt2_crt(pgpu_ctx* ctx) {
+    ctx->enc2_crt_ready = false;
+    ModCtx &P3 = ctx->m_p3, &Q3 = ctx->m_q3, &N3 = ctx->m_n3;
+    if (!ctx->level2_ready || ctx->wn > (size_t)P3.sh.S || P3.sh.S > N3.sh.S) return PGPU_OK;
+    const BigU &p = ctx->p, &q = ctx->q;
+    const BigU phip = p * p * (p - BigU(1)), phiq = q * q * (q - BigU(1));
+    const BigU ep = (ctx->n2 % phip) + phip, eq = (ctx->n2 % phiq) + phiq;
+    BigU q3inv;
+    if (!BigU::modinv(Q3.N % P3.N, P3.N, q3inv)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
+    int rc;
+    if ((rc = set_kconst(ctx, P3, K_CRT, q3inv))) return rc;
+    if ((rc = set_kconst(ctx, N3, K_CRT, (Q3.N * N3.R2) % N3.N))) return rc;
+    {   // x_q = r^eq mod q^3.  in0 = r
+        Program& P = ctx->prog_enc2q;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_pow_shared(P, eq, 0);
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    {   // t = (r^ep - x_q) * q^-3 mod p^3.  in0 = r, in1 = x_q
+        Program& P = ctx->prog_enc2p;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_pow_shared(P, ep, 0);
+        const uint32_t XP = P.tbl_entries, XQ = XP + 1;
+        P.emit(OP_STT, XP); P.use_slot(XP);
+        P.emit(OP_LDI, 1);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        P.emit(OP_STT, XQ); P.use_slot(XQ);
+        P.emit(OP_LDT, XP);
+        P.emit(OP_SUBT, XQ);
+        P.emit(OP_MULC, K_CRT); P.n_mul++;      // plain constant: leaves Montgomery form
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    {   // c = (x_q + q^3*t) * (1+n)^m mod n^3.  in0 = t, in1 = x_q, in2 = m
+        Program& P = ctx->prog_enc2f;
+        program_free(P);
+        P.emit(OP_LDI, 0);
+        P.emit(OP_MULC, K_CRT); P.n_mul++;
+        P.emit(OP_STT, 0); P.use_slot(0);
+        P.emit(OP_LDI, 1);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        P.emit(OP_ADDT, 0);                     // r^(n^2) mod n^3 (x_q + q^3*t < n^3)
+        P.emit(OP_STT, 0);
+        P.emit(OP_LDI, 2);
+        P.emit(OP_MULC, K_R2); P.n_mul++;
+        emit_g_pow_level2(P, 1);
+        P.emit(OP_MULT, 0); P.n_mul++;
+        P.emit(OP_MULC, K_ONE); P.n_mul++;
+        P.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, P))) return rc;
+    }
+    ctx->enc2_crt_ready = true;
+    return PGPU_OK;
+}
+
 int setup_level2_crt(pgpu_ctx* ctx) {
     ctx->crt2_ready = false;
     const BigU &p = ctx->p, &q = ctx->q;
@@ -238,7 +305,22 @@ int setup_level2_crt(pgpu_ctx* ctx) {
     ctx->crt2_np0[0] = mont_np0(p.v[0]); ctx->crt2_np0[1] = mont_np0(p2.v[0]);
     ctx->crt2_np0[2] = mont_np0(q.v[0]); ctx->crt2_np0[3] = mont_np0(q2.v[0]);
     ctx->crt2_ready = true;
-    return PGPU_OK;
+    return setup_encrypt2_crt(ctx);
+}
+
+int encrypt2_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t* r, uint32_t* c) {
+    if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "EncryptWithRAtLevel (secret key): no secret key loaded");
+    if (!ctx->enc2_crt_ready) return encrypt2_dev(ctx, count, m, r, c);
+    const ModCtx &P3 = ctx->m_p3, &Q3 = ctx->m_q3, &N3 = ctx->m_n3;
+    const uint32_t Sp = P3.sh.S, wn = (uint32_t)ctx->wn;
+    DEVBUF(xq, ctx, count * Sp); DEVBUF(t, ctx, count * Sp);
+    int rc;
+    IoDesc iq[1] = {{r, wn, wn}};
+    if ((rc = run_vm(ctx, Q3, ctx->prog_enc2q, count, iq, 1, xq.p, Sp, Sp))) return rc;
+    IoDesc ip[2] = {{r, wn, wn}, {xq.p, Sp, Sp}};
+    if ((rc = run_vm(ctx, P3, ctx->prog_enc2p, count, ip, 2, t.p, Sp, Sp))) return rc;
+    IoDesc fin[3] = {{t.p, Sp, Sp}, {xq.p, Sp, Sp}, {m, 2 * wn, 2 * wn}};
+    return run_vm(ctx, N3, ctx->prog_enc2f, count, fin, 3, c, N3.sh.S, N3.sh.S);
 }
 
 static int decrypt2_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {

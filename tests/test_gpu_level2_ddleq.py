@@ -9,7 +9,7 @@ from oracle import paillier_ref as R
 from paillier_b200 import synth
 from paillier_b200._lib import PgpuError, PGPU_ERR_ARG
 from paillier_b200.api import (ALTERNATIVE, Ciphertext, DDLEQProof, DDLEQProofInstance, ENC_LEVEL_ONE, ENC_LEVEL_TWO,
-                               SecretKey)
+                               PublicKey, SecretKey)
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,15 @@ def _units(rnd, n, k):
         if gcd(r, n) == 1:
             out.append(r)
     return out
+
+
+def _factors(n, lam):
+    from math import isqrt
+    s = n + 1 - lam                      # p + q
+    d = isqrt(s * s - 4 * n)
+    p, q = (s - d) // 2, (s + d) // 2
+    assert p * q == n
+    return p, q
 
 
 def _keys(name, seed=7):
@@ -47,6 +56,15 @@ def test_level2_encrypt_decrypt(keys):
     cts = sk.EncryptWithRAtLevelBatch(ms, rs, ENC_LEVEL_TWO)
     assert [c.C for c in cts] == [R.encrypt_with_r_at_level(opk, m, r, R.ENC_LEVEL_TWO).C for m, r in zip(ms, rs)]
     assert sk.DecryptBatch(cts) == ms == [R.decrypt(osk, R.Ciphertext(c.C, R.ENC_LEVEL_TWO)) for c in cts]
+    # the public-key path (r^(n^2) mod n^3 directly) gives the same ciphertexts as the secret-key path over p^3, q^3
+    assert [c.C for c in PublicKey.EncryptWithRAtLevelBatch(sk, ms, rs, ENC_LEVEL_TWO)] == [c.C for c in cts]
+    # non-units and r around the prime powers: the reduced exponent must stay exact
+    p, q = _factors(n, osk.Lambda)
+    edge = [0, p, q, 2 * p, q * (p - 1), (p ** 3) % n, (q ** 3 + 1) % n, n // 2]
+    em = [rnd.randrange(n2) for _ in edge]
+    got = [c.C for c in sk.EncryptWithRAtLevelBatch(em, edge, ENC_LEVEL_TWO)]
+    assert got == [R.encrypt_with_r_at_level(opk, m, r, R.ENC_LEVEL_TWO).C for m, r in zip(em, edge)]
+    assert got == [c.C for c in PublicKey.EncryptWithRAtLevelBatch(sk, em, edge, ENC_LEVEL_TWO)]
     # level 1 through the same entry point
     ms1 = [m % n for m in ms]
     cts1 = sk.EncryptWithRAtLevelBatch(ms1, rs, ENC_LEVEL_ONE)

@@ -87,6 +87,26 @@ def test_secret_key_encrypt_edge_randomness(name):
     sk.close()
 
 
+@pytest.mark.parametrize("name", ["paillier_64", "paillier_2048"])
+def test_offline_online_encrypt_matches_encrypt_with_r(name):
+    """r^n pool: EncryptWithRn(m, r^n mod n^2) == EncryptWithR(m, r) (paillier.go:206-218), through the
+    public-key and the secret-key precomputation, against the Python oracle."""
+    p, q, n = _key(name)
+    osk, opk = R.keygen_from_primes(p, q)
+    sk = SecretKey(n, p=p, q=q)
+    pk = PublicKey(n)
+    ms = from_records(synth.plaintexts(40, n, sk.w_n), sk.w_n)
+    rs = from_records(synth.randomness(40, n, sk.w_n), sk.w_n)
+    ms[0], ms[1], rs[2], rs[3] = 0, n - 1, 1, n - 1
+    pool_pk, pool_sk = pk.PrecomputeRnBatch(rs), sk.PrecomputeRnBatch(rs)
+    assert pool_pk == pool_sk == [pow(r, n, n * n) for r in rs]
+    want = [R.encrypt_with_r(opk, m, r).C for m, r in zip(ms, rs)]
+    assert [c.C for c in pk.EncryptWithRnBatch(ms, pool_pk)] == want
+    assert [c.C for c in sk.EncryptWithRnBatch(ms, pool_sk)] == want
+    assert pk.EncryptWithRnBatch([], []) == []
+    sk.close(); pk.close()
+
+
 def test_empty_and_single_batches(sk2048):
     sk, _ = sk2048
     assert sk.EncryptWithRBatch([], []) == []
