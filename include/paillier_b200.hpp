@@ -6,6 +6,11 @@
 //   paillier::SecretKey::DecryptBatch             <- SecretKey.Decrypt                 paillier.go:292-303
 //   paillier::SecretKey::EncryptWithRBatch        <- EncryptWithR on a SecretKey (CRT)  paillier.go:29-34,206-218
 //   paillier::PublicKey::ConstMultBatch / AddBatch / SubPairs  <- operations.go:11-64
+//   paillier::PublicKey::EncryptWithRAtLevelBatch / AltEncryptWithRAtLevelBatch     <- paillier.go:206-238
+//   paillier::PublicKey::RandomizeWithRBatch / NestedRandomizeWithBatch / NestedAddBatch / NestedSubBatch  <- operations.go:67-140
+//   paillier::SecretKey::NestedDecryptBatch / ExtractRandonnessBatch / ProveDDLEQBatch, PublicKey::VerifyDDLEQProofBatch
+//                                                   <- paillier.go:344-372, operations.go:75-91, ddleq.go:27-153
+//   paillier::SafePrimeScan / MillerRabinBatch      <- safe_prime.go:170-278
 //   paillier::ThresholdSecretKey::PartialDecryptBatch / PartialDecryptionWithZKPBatch  <- thresholdkey.go:192-255
 //   paillier::ThresholdPublicKey::VerifyProofBatch / CombinePartialDecryptionsBatch    <- thresholdkey.go:149-172,278-311
 //
@@ -62,6 +67,8 @@ struct Ciphertext {                                                             
     Int C; int Level = EncLevelOne; int EncMethod = RegularEncryption;
     std::vector<uint8_t> Bytes() const;                  // Ciphertext.Bytes, paillier.go:392-401 (encoding/gob stream)
 };
+struct DDLEQProofInstance { Int X, Y, Alpha, E, F; };                                               // ddleq.go:13-19
+struct DDLEQProof { std::vector<DDLEQProofInstance> Instances; };                                   // ddleq.go:21-24
 struct PartialDecryption { int ID = 0; Int Decryption; };                                           // thresholdkey.go:45-48
 struct PartialDecryptionZKP { int ID = 0; Int Decryption, E, Z, C; };                               // thresholdkey.go:52-58
 
@@ -85,6 +92,15 @@ inline std::vector<Int> from_records(const std::vector<uint8_t>& buf, size_t wid
         for (size_t j = 0; j < n; ++j) out[i][j] = buf[i * width + n - 1 - j];
     }
     return out;
+}
+// x mod 2^bits on a big-endian magnitude
+inline void reduce_pow2(Int& x, unsigned bits) {
+    const size_t keep = (bits + 7) / 8;
+    if (x.size() > keep) x.erase(x.begin(), x.end() - keep);
+    if (x.size() == keep && bits % 8) x[0] &= (uint8_t)((1u << (bits % 8)) - 1);
+    size_t z = 0;
+    while (z < x.size() && x[z] == 0) ++z;
+    x.erase(x.begin(), x.begin() + z);
 }
 }  // namespace detail
 
@@ -286,10 +302,124 @@ public:
         return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
     }
 
+    // N x PublicKey.Add(a_i, b_i) (operations.go:11-29)
+    std::vector<Ciphertext> AddPairs(const std::vector<Ciphertext>& a, const std::vector<Ciphertext>& b) {
+        if (a.size() != b.size()) throw Error(PGPU_ERR_ARG, "pairs");
+        auto ra = detail::to_records(values(a), w_n2), rb = detail::to_records(values(b), w_n2);
+        std::vector<uint8_t> o(a.size() * w_n2);
+        check(pgpu_add_pairs(ctx_, a.size(), ra.data(), rb.data(), o.data()));
+        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
+    }
+    // Add(ConstMult(c_i, k_i)...) in one call: the encrypted dot product with 64-bit scalars
+    Ciphertext DotProduct(const std::vector<Ciphertext>& cts, const std::vector<uint64_t>& ks) {
+        if (cts.size() != ks.size()) throw Error(PGPU_ERR_ARG, "one scalar per ciphertext");
+        auto c = detail::to_records(values(cts), w_n2);
+        std::vector<uint8_t> o(w_n2);
+        check(pgpu_dot_u64(ctx_, cts.size(), cts.empty() ? nullptr : c.data(), ks.data(), o.data()));
+        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption)[0];
+    }
+    // r^n mod n^2 ahead of time, then N x EncryptWithR in two multiplications each (pgpu_encrypt_with_rn)
+    virtual std::vector<Int> PrecomputeRnBatch(const std::vector<Int>& rs) {
+        std::vector<Int> zeros(rs.size());
+        std::vector<Int> out;
+        for (auto& c : EncryptWithRBatch(zeros, rs)) out.push_back(std::move(c.C));
+        return out;
+    }
+    std::vector<Ciphertext> EncryptWithRnBatch(const std::vector<Int>& ms, const std::vector<Int>& rns) {
+        if (ms.size() != rns.size()) throw Error(PGPU_ERR_ARG, "one r^n per plaintext");
+        auto m = detail::to_records(ms, w_n), r = detail::to_records(rns, w_n2);
+        std::vector<uint8_t> c(ms.size() * w_n2);
+        check(pgpu_encrypt_with_rn(ctx_, ms.size(), m.data(), r.data(), c.data()));
+        return wrap(detail::from_records(c, w_n2), EncLevelOne, RegularEncryption);
+    }
+    // N x PublicKey.EncryptWithRAtLevel (paillier.go:206-218)
+    virtual std::vector<Ciphertext> EncryptWithRAtLevelBatch(const std::vector<Int>& ms, const std::vector<Int>& rs, int level) {
+        if (ms.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per plaintext");
+        auto m = detail::to_records(ms, plain_width(level)), r = detail::to_records(rs, w_n);
+        std::vector<uint8_t> c(ms.size() * cipher_width(level));
+        check(pgpu_encrypt_with_r_at_level(ctx_, level + 1, ms.size(), m.data(), r.data(), c.data()));
+        return wrap(detail::from_records(c, cipher_width(level)), level, RegularEncryption);
+    }
+    // PublicKey.H, K = 2^k_bits (paillier.go:46-56): enables AltEncryptWithRAtLevelBatch
+    void SetAltGenerator(const Int& H, unsigned k_bits) {
+        check(pgpu_ctx_set_alt_generator(ctx_, H.data(), H.size(), k_bits));
+        k_bits_ = k_bits;
+    }
+    // N x PublicKey.AltEncryptWithRAtLevel (paillier.go:221-238); like the reference (:228) the caller's r is reduced mod K
+    std::vector<Ciphertext> AltEncryptWithRAtLevelBatch(const std::vector<Int>& ms, std::vector<Int>& rs, int level) {
+        if (ms.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per plaintext");
+        if (k_bits_ == 0) throw Error(PGPU_ERR_STATE, "AltEncrypt needs PublicKey.H and K");
+        for (Int& r : rs) detail::reduce_pow2(r, k_bits_);
+        auto m = detail::to_records(ms, plain_width(level)), r = detail::to_records(rs, w_n);
+        std::vector<uint8_t> c(ms.size() * cipher_width(level));
+        check(pgpu_alt_encrypt_with_r_at_level(ctx_, level + 1, ms.size(), m.data(), r.data(), c.data()));
+        return wrap(detail::from_records(c, cipher_width(level)), level, AlternativeEncryption);
+    }
+    // N x PublicKey.Randomize (operations.go:67-69) with the r of the fresh Encrypt(0) supplied
+    std::vector<Ciphertext> RandomizeWithRBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& rs) {
+        if (cts.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per ciphertext");
+        auto c = detail::to_records(values(cts), w_n2), r = detail::to_records(rs, w_n);
+        std::vector<uint8_t> o(cts.size() * w_n2);
+        check(pgpu_randomize_with_r(ctx_, cts.size(), c.data(), r.data(), o.data()));
+        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
+    }
+    // N x PublicKey.NestedRandomize (operations.go:96-118) with (a, b) supplied
+    std::vector<Ciphertext> NestedRandomizeWithBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& as, const std::vector<Int>& bs) {
+        if (cts.size() != as.size() || cts.size() != bs.size()) throw Error(PGPU_ERR_ARG, "one (a, b) per ciphertext");
+        for (const auto& c : cts)
+            if (c.Level != EncLevelTwo) throw Error(PGPU_ERR_ARG, "can only homomorphically randomize doubly encrypted values");
+        auto c = detail::to_records(values(cts), w_n3), a = detail::to_records(as, w_n), b = detail::to_records(bs, w_n);
+        std::vector<uint8_t> o(cts.size() * w_n3);
+        check(pgpu_nested_randomize_with(ctx_, cts.size(), c.data(), a.data(), b.data(), o.data()));
+        return wrap(detail::from_records(o, w_n3), EncLevelTwo, RegularEncryption);
+    }
+    // N x PublicKey.NestedAdd / NestedSub (operations.go:121-140)
+    std::vector<Ciphertext> NestedAddBatch(const std::vector<Ciphertext>& ct1, const std::vector<Ciphertext>& ct2) { return nested(pgpu_nested_add, ct1, ct2); }
+    std::vector<Ciphertext> NestedSubBatch(const std::vector<Ciphertext>& ct1, const std::vector<Ciphertext>& ct2) { return nested(pgpu_nested_sub, ct1, ct2); }
+    // N x PublicKey.VerifyDDLEQProof (ddleq.go:44-53); one instance count per batch
+    std::vector<bool> VerifyDDLEQProofBatch(const std::vector<Ciphertext>& ct1, const std::vector<Ciphertext>& ct2, const std::vector<DDLEQProof>& proofs) {
+        if (proofs.empty()) return {};
+        if (ct1.size() != proofs.size() || ct2.size() != proofs.size()) throw Error(PGPU_ERR_ARG, "one statement per proof");
+        const size_t secpar = proofs[0].Instances.size();
+        if (secpar == 0) return std::vector<bool>(proofs.size(), true);
+        std::vector<Int> x, y, al, e, f;
+        for (const auto& p : proofs) {
+            if (p.Instances.size() != secpar) throw Error(PGPU_ERR_ARG, "VerifyDDLEQProofBatch: one secpar per batch");
+            for (const auto& i : p.Instances) { x.push_back(i.X); y.push_back(i.Y); al.push_back(i.Alpha); e.push_back(i.E); f.push_back(i.F); }
+        }
+        auto c1 = detail::to_records(values(ct1), w_n3), c2 = detail::to_records(values(ct2), w_n3);
+        auto rx = detail::to_records(x, w_n), ry = detail::to_records(y, w_n);
+        auto ra = detail::to_records(al, w_n3), re = detail::to_records(e, w_n2), rf = detail::to_records(f, w_n3);
+        std::vector<uint8_t> ok(x.size());
+        check(pgpu_ddleq_verify(ctx_, proofs.size(), (unsigned)secpar, c1.data(), c2.data(), rx.data(), ry.data(), ra.data(), re.data(), rf.data(), ok.data()));
+        std::vector<bool> out(proofs.size(), true);
+        for (size_t i = 0; i < ok.size(); ++i) if (!ok[i]) out[i / secpar] = false;
+        return out;
+    }
+
     size_t w_n = 0, w_n2 = 0, w_n3 = 0;
 
 protected:
     pgpu_ctx* ctx_ = nullptr;
+    unsigned k_bits_ = 0;
+    size_t plain_width(int level) const {
+        if (level != EncLevelOne && level != EncLevelTwo) throw Error(PGPU_ERR_ARG, "unsupported encryption level");
+        return level == EncLevelOne ? w_n : w_n2;
+    }
+    size_t cipher_width(int level) const { return plain_width(level) == w_n ? w_n2 : w_n3; }
+    template <class Fn>
+    std::vector<Ciphertext> nested(Fn fn, const std::vector<Ciphertext>& ct1, const std::vector<Ciphertext>& ct2) {
+        if (ct1.size() != ct2.size()) throw Error(PGPU_ERR_ARG, "pairs");
+        for (size_t i = 0; i < ct1.size(); ++i)
+            if (ct1[i].Level != EncLevelTwo || ct2[i].Level != EncLevelOne)
+                throw Error(PGPU_ERR_ARG, "can only homomorphically add an encrypted value to a doubly encrypted value");
+        auto a = detail::to_records(values(ct1), w_n3), b = detail::to_records(values(ct2), w_n2);
+        std::vector<uint8_t> o(ct1.size() * w_n3);
+        check(fn(ctx_, ct1.size(), a.data(), b.data(), o.data()));
+        auto out = wrap(detail::from_records(o, w_n3), EncLevelTwo, RegularEncryption);
+        for (size_t i = 0; i < out.size(); ++i) out[i].EncMethod = ct1[i].EncMethod;
+        return out;
+    }
     void check(int rc) const {
         if (rc != PGPU_OK) throw Error(rc, pgpu_last_error(ctx_));
     }
@@ -323,16 +453,108 @@ public:
         check(pgpu_encrypt_with_r_sk(ctx_, ms.size(), m.data(), r.data(), c.data()));
         return wrap(detail::from_records(c, w_n2), EncLevelOne, RegularEncryption);
     }
-    // N x SecretKey.Decrypt (paillier.go:292-303), level 1
+    std::vector<Ciphertext> EncryptWithRAtLevelBatch(const std::vector<Int>& ms, const std::vector<Int>& rs, int level) override {
+        if (ms.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per plaintext");
+        auto m = detail::to_records(ms, plain_width(level)), r = detail::to_records(rs, w_n);
+        std::vector<uint8_t> c(ms.size() * cipher_width(level));
+        check(pgpu_encrypt_with_r_at_level_sk(ctx_, level + 1, ms.size(), m.data(), r.data(), c.data()));
+        return wrap(detail::from_records(c, cipher_width(level)), level, RegularEncryption);
+    }
+    std::vector<Int> PrecomputeRnBatch(const std::vector<Int>& rs) override {
+        std::vector<Int> zeros(rs.size()), out;
+        for (auto& c : EncryptWithRBatch(zeros, rs)) out.push_back(std::move(c.C));
+        return out;
+    }
+    // N x SecretKey.Decrypt (paillier.go:292-340); one encryption level per batch
     std::vector<Int> DecryptBatch(const std::vector<Ciphertext>& cts) {
+        if (cts.empty()) return {};
+        const int level = cts[0].Level;
         for (const auto& c : cts)
-            if (c.Level != EncLevelOne) throw Error(PGPU_ERR_ARG, "DecryptBatch handles level-1 ciphertexts");
-        auto c = detail::to_records(values(cts), w_n2);
-        std::vector<uint8_t> m(cts.size() * w_n);
-        check(pgpu_decrypt(ctx_, cts.size(), c.data(), m.data()));
-        return detail::from_records(m, w_n);
+            if (c.Level != level) throw Error(PGPU_ERR_ARG, "DecryptBatch: one encryption level per batch");
+        auto c = detail::to_records(values(cts), cipher_width(level));
+        std::vector<uint8_t> m(cts.size() * plain_width(level));
+        if (level == EncLevelOne) check(pgpu_decrypt(ctx_, cts.size(), c.data(), m.data()));
+        else check(pgpu_decrypt_at_level(ctx_, level + 1, cts.size(), c.data(), m.data()));
+        return detail::from_records(m, plain_width(level));
+    }
+    // N x SecretKey.DecryptNestedCiphertextLayer (paillier.go:360-372)
+    std::vector<Ciphertext> DecryptNestedCiphertextLayerBatch(const std::vector<Ciphertext>& cts) {
+        for (const auto& c : cts)
+            if (c.Level == EncLevelOne) throw Error(PGPU_ERR_ARG, "no nested ciphertexts to recover");
+        return wrap(DecryptBatch(cts), EncLevelOne, MixedEncryption);
+    }
+    // N x SecretKey.NestedDecrypt (paillier.go:344-356): an inner value 0 decrypts to 0 (:350-354)
+    std::vector<Int> NestedDecryptBatch(const std::vector<Ciphertext>& cts) {
+        auto inner = DecryptNestedCiphertextLayerBatch(cts);
+        std::vector<Ciphertext> nz;
+        std::vector<size_t> at;
+        for (size_t i = 0; i < inner.size(); ++i)
+            if (!inner[i].C.empty()) { nz.push_back(inner[i]); at.push_back(i); }
+        auto vals = DecryptBatch(nz);
+        std::vector<Int> out(cts.size());
+        for (size_t k = 0; k < at.size(); ++k) out[at[k]] = std::move(vals[k]);
+        return out;
+    }
+    // N x SecretKey.ExtractRandonness (operations.go:75-91); one level per batch
+    std::vector<Int> ExtractRandonnessBatch(const std::vector<Ciphertext>& cts) {
+        if (cts.empty()) return {};
+        const int level = cts[0].Level;
+        auto c = detail::to_records(values(cts), cipher_width(level));
+        std::vector<uint8_t> o(cts.size() * w_n);
+        check(pgpu_extract_randomness(ctx_, level + 1, cts.size(), c.data(), o.data()));
+        return detail::from_records(o, w_n);
+    }
+    // N x SecretKey.ProveDDLEQ (ddleq.go:27-40): xs[i][j], ys[i][j] in Z*_n = the randomness of instance j of statement i
+    // (:71-79).  Throws PGPU_ERR_ARG where the reference panics on wrong inputs (:67-69).
+    std::vector<DDLEQProof> ProveDDLEQBatch(unsigned secpar, const std::vector<Ciphertext>& ct1, const std::vector<Ciphertext>& ct2,
+                                            const std::vector<Int>& as, const std::vector<Int>& bs,
+                                            const std::vector<std::vector<Int>>& xs, const std::vector<std::vector<Int>>& ys) {
+        const size_t count = ct1.size();
+        std::vector<DDLEQProof> out(count);
+        if (secpar == 0 || count == 0) return out;
+        if (ct2.size() != count || as.size() != count || bs.size() != count || xs.size() != count || ys.size() != count)
+            throw Error(PGPU_ERR_ARG, "ProveDDLEQBatch: one (ct2, a, b, xs, ys) per statement");
+        std::vector<Int> fx, fy;
+        for (size_t i = 0; i < count; ++i) {
+            if (xs[i].size() != secpar || ys[i].size() != secpar) throw Error(PGPU_ERR_ARG, "ProveDDLEQBatch: secpar values of x and y per statement");
+            fx.insert(fx.end(), xs[i].begin(), xs[i].end()); fy.insert(fy.end(), ys[i].begin(), ys[i].end());
+        }
+        auto c1 = detail::to_records(values(ct1), w_n3), c2 = detail::to_records(values(ct2), w_n3);
+        auto a = detail::to_records(as, w_n), b = detail::to_records(bs, w_n), x = detail::to_records(fx, w_n), y = detail::to_records(fy, w_n);
+        const size_t total = count * secpar;
+        std::vector<uint8_t> al(total * w_n3), e(total * w_n2), f(total * w_n3);
+        check(pgpu_ddleq_prove(ctx_, count, secpar, c1.data(), c2.data(), a.data(), b.data(), x.data(), y.data(), al.data(), e.data(), f.data()));
+        auto A = detail::from_records(al, w_n3), E = detail::from_records(e, w_n2), F = detail::from_records(f, w_n3);
+        for (size_t k = 0; k < total; ++k)
+            out[k / secpar].Instances.push_back(DDLEQProofInstance{fx[k], fy[k], std::move(A[k]), std::move(E[k]), std::move(F[k])});
+        return out;
     }
 };
+
+// One iteration of the safe-prime search (safe_prime.go:170-278) for each `raw` byte string (ceil((p_bits-1)/8) bytes each,
+// as read from the reference's io.Reader): candidate q (after the sieve's delta search), p = 2q+1 and whether the pair is accepted.
+struct SafePrimeCandidate { Int p, q; bool ok = false; };
+inline std::vector<SafePrimeCandidate> SafePrimeScan(unsigned p_bits, const std::vector<uint8_t>& raw, int device = 0) {
+    const size_t rec = (p_bits - 1 + 7) / 8;
+    if (rec == 0 || raw.size() % rec) throw Error(PGPU_ERR_ARG, "raw: whole records of ceil((p_bits-1)/8) bytes");
+    const size_t count = raw.size() / rec, w = 4 * (p_bits <= 1024 ? 32 : p_bits <= 1536 ? 48 : 64);
+    std::vector<uint8_t> p(count * w), q(count * w), ok(count);
+    int rc = pgpu_safe_prime_scan(device, p_bits, count, raw.data(), p.data(), q.data(), ok.data(), nullptr);
+    if (rc != PGPU_OK) throw Error(rc, pgpu_primes_last_error());
+    auto P = detail::from_records(p, w), Q = detail::from_records(q, w);
+    std::vector<SafePrimeCandidate> out(count);
+    for (size_t i = 0; i < count; ++i) out[i] = SafePrimeCandidate{std::move(P[i]), std::move(Q[i]), ok[i] != 0};
+    return out;
+}
+// big.Int.ProbablyPrime stand-in: `rounds` Miller-Rabin tests (bases 2, 3, 5, ...) on odd candidates of exactly `bits` bits
+inline std::vector<bool> MillerRabinBatch(unsigned bits, const std::vector<Int>& cand, unsigned rounds = 20, int device = 0) {
+    const size_t w = 4 * (bits <= 1024 ? 32 : bits <= 1536 ? 48 : 64);
+    auto c = detail::to_records(cand, w);
+    std::vector<uint8_t> ok(cand.size());
+    int rc = pgpu_miller_rabin(device, bits, cand.size(), c.data(), rounds, ok.data(), nullptr);
+    if (rc != PGPU_OK) throw Error(rc, pgpu_primes_last_error());
+    return std::vector<bool>(ok.begin(), ok.end());
+}
 
 // ThresholdPublicKey (thresholdkey.go:26-32)
 class ThresholdPublicKey : public PublicKey {

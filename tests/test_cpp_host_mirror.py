@@ -45,6 +45,24 @@ def _input():
         for i in range(c["w"]):
             lines += [str(i + 1), c["shares"][i]]
         lines += [str(len(c["c"]))] + c["c"] + c["m"] + c["zkp_r"]
+    for name in ("paillier_64", "paillier_2048"):
+        c = V["cases"][name]
+        p, q = I(c["p"]), I(c["q"])
+        e1, e2, a, d = c["encrypt"], c["encrypt_level2"], c["alt_encrypt"], c["ddleq"]
+        count = min(len(e2["m"]), len(e1["m"]))
+        lines += ["level2", hex(p * q), hex((p - 1) * (q - 1)), c["H"], str(I(c["K"]).bit_length() - 1), str(count)]
+        for i in range(count):
+            lines += [e1["m"][i], e2["m"][i], e2["r"][i], e2["c"][i]]
+        lines.append(str(len(a["r"])))
+        for i in range(len(a["r"])):
+            lines += [a["r"][i], a["c_level1"][i], a["c_level2"][i]]
+        lines += [d["ct1"], d["ct2"], d["a"], d["b"], str(len(d["x"]))]
+        for i in range(len(d["x"])):
+            lines += [d["x"][i], d["y"][i], d["alpha"][i], d["e"][i], d["f"][i]]
+    for bits, d in V["safe_prime"].items():
+        lines += ["safeprime", bits, str(len(d["raw"]))]
+        for raw, qv, ok in zip(d["raw"], d["q"], d["ok"]):
+            lines += [raw, qv, str(int(ok))]
     return "\n".join(lines) + "\n"
 
 
