@@ -242,7 +242,7 @@ int pgpu_dot_u64_dev(pgpu_ctx* ctx, size_t count, const void* c, const uint64_t*
     if (count >= 16 * resident && !getenv("PGPU_DOT_SIMPLE"))
         return dot_pippenger_dev(ctx, count, (const uint32_t*)c, (const uint32_t*)k, 2, (uint32_t*)out);
     void* tmp;
-    if ((rc = stage(ctx, 2, std::max<size_t>(count, 1) * ctx->m_n2.sh.S * 4, &tmp))) return rc;
+    if ((rc = stage(ctx, 15, std::max<size_t>(count, 1) * ctx->m_n2.sh.S * 4, &tmp))) return rc;
     if ((rc = modexp_items_dev(ctx, ctx->m_n2, count, (const uint32_t*)c, (const uint32_t*)k, 2, (uint32_t*)tmp))) return rc;
     return prod_dev(ctx, ctx->m_n2, count, (const uint32_t*)tmp, (uint32_t*)out);
     GUARD_END(ctx)

@@ -372,8 +372,8 @@ int decrypt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, uint32_t* m) {
     // c (S2 limbs) = lo (Sp limbs) + hi * 2^(32*Sp); S2 <= 2*Sp
     const uint32_t hi_limbs = S2 > Sp ? S2 - Sp : 0;
     void *xp, *xq; int rc;
-    if ((rc = stage(ctx, 4, count * Sp * 4, &xp))) return rc;
-    if ((rc = stage(ctx, 5, count * Sp * 4, &xq))) return rc;
+    if ((rc = stage(ctx, 12, count * Sp * 4, &xp))) return rc;
+    if ((rc = stage(ctx, 13, count * Sp * 4, &xq))) return rc;
     IoDesc ins[2] = {{c, S2, std::min(S2, Sp)}, {c + Sp, S2, hi_limbs}};
     if ((rc = run_vm(ctx, P2, ctx->prog_dec_p, count, ins, 2, (uint32_t*)xp, Sp, Sp))) return rc;
     if ((rc = run_vm(ctx, Q2, ctx->prog_dec_q, count, ins, 2, (uint32_t*)xq, Sp, Sp))) return rc;
@@ -414,8 +414,8 @@ int encrypt_crt_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32
     const ModCtx &P2 = ctx->m_p2, &Q2 = ctx->m_q2, &N2 = ctx->m_n2;
     const uint32_t Sp = P2.sh.S, wn = (uint32_t)ctx->wn;
     void *xq, *t; int rc;
-    if ((rc = stage(ctx, 4, count * Sp * 4, &xq))) return rc;
-    if ((rc = stage(ctx, 5, count * Sp * 4, &t))) return rc;
+    if ((rc = stage(ctx, 12, count * Sp * 4, &xq))) return rc;
+    if ((rc = stage(ctx, 13, count * Sp * 4, &t))) return rc;
     IoDesc iq[1] = {{r, wn, wn}};
     if ((rc = run_vm(ctx, Q2, ctx->prog_encq, count, iq, 1, (uint32_t*)xq, Sp, Sp))) return rc;
     IoDesc ip[2] = {{r, wn, wn}, {(const uint32_t*)xq, Sp, Sp}};
@@ -517,7 +517,7 @@ int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_
     size_t b1 = std::min(max_blocks, (count + gpb - 1) / gpb);
     if (b1 == 0) b1 = 1;
     void* part; int rc;
-    if ((rc = stage(ctx, 3, (b1 + 1) * M.sh.S * 4, &part))) return rc;
+    if ((rc = stage(ctx, 14, (b1 + 1) * M.sh.S * 4, &part))) return rc;
     uint32_t* partial = (uint32_t*)part;
     auto rounds = [&](size_t n, size_t blocks) { size_t G = blocks * gpb; return n == 0 ? (size_t)1 : (n + G - 1) / G; };
     // stage 1: b1 blocks -> b1 partials, each carrying R^-(gpb*rounds1 - 1)

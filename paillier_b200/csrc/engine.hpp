@@ -108,8 +108,8 @@ struct pgpu_ctx {
 
     // scratch
     uint32_t* d_table = nullptr; size_t table_limbs = 0;
-    void* d_stage[12] = {};
-    size_t stage_bytes[12] = {};
+    void* d_stage[16] = {};                 // 0-9: host-buffer staging (HostIo); 12-15: scratch of the device-side ops
+    size_t stage_bytes[16] = {};
 
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

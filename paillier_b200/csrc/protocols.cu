@@ -482,16 +482,108 @@ int extract_randomness_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_
     return PGPU_OK;
 }
 
+// base[i]^exp[i] mod n^3 for the holder of p, q: the same exponentiation over q^3 and p^3 (half-width moduli, the
+// exponent unreduced so that no assumption on the base is needed), Garner's step in the tail of the p^3 program and
+// x = x_q + q^3*t over n^3.  Bit-identical to modexp_items_io(M3, ...) -- both return the canonical residue.
+static int modexp3_items_crt(pgpu_ctx* ctx, size_t count, const IoDesc& base, const ExpDesc& exp, uint32_t* out) {
+    const ModCtx &P3 = ctx->m_p3, &Q3 = ctx->m_q3, &N3 = ctx->m_n3;
+    const uint32_t Sp = P3.sh.S, S3 = N3.sh.S;
+    int rc;
+    auto prefix = [](Program& np) {             // (lo + hi*R) mod P^3 in Montgomery form, R = 2^(32*Sp)
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_STT, 0); np.use_slot(0);
+        np.emit(OP_LDI, 1);
+        np.emit(OP_MULC, K_R3); np.n_mul++;
+        np.emit(OP_ADDT, 0);
+    };
+    const std::string kq = "crt3q:" + std::to_string(exp.bits), kp = "crt3p:" + std::to_string(exp.bits), kf = "crt3f";
+    Program* Pq = cached_program(ctx, kq);
+    if (!Pq) {
+        Program np;
+        prefix(np);
+        emit_pow_items(np, exp.bits, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        Pq = &(ctx->prog_cache[kq] = np);
+    }
+    Program* Pp = cached_program(ctx, kp);
+    if (!Pp) {
+        Program np;
+        prefix(np);
+        emit_pow_items(np, exp.bits, 0);
+        const uint32_t XP = np.tbl_entries, XQ = XP + 1;
+        np.emit(OP_STT, XP); np.use_slot(XP);
+        np.emit(OP_LDI, 2);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_STT, XQ); np.use_slot(XQ);
+        np.emit(OP_LDT, XP);
+        np.emit(OP_SUBT, XQ);
+        np.emit(OP_MULC, K_CRT); np.n_mul++;
+        np.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        Pp = &(ctx->prog_cache[kp] = np);
+    }
+    Program* Pf = cached_program(ctx, kf);
+    if (!Pf) {
+        Program np;
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_CRT); np.n_mul++;    // q^3 * t, Montgomery form
+        np.emit(OP_STT, 0); np.use_slot(0);
+        np.emit(OP_LDI, 1);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_ADDT, 0);
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        if ((rc = program_upload(ctx, np))) return rc;
+        Pf = &(ctx->prog_cache[kf] = np);
+    }
+    DEVBUF(xq, ctx, count * Sp); DEVBUF(t, ctx, count * Sp);
+    const uint32_t lo = std::min(base.limbs, Sp), hi = base.limbs > Sp ? base.limbs - Sp : 0;
+    IoDesc iq[2] = {{base.ptr, base.stride, lo, base.div}, {base.ptr + Sp, base.stride, hi, base.div}};
+    if ((rc = run_vm(ctx, Q3, *Pq, count, iq, 2, xq.p, Sp, Sp, exp))) return rc;
+    IoDesc ip[3] = {iq[0], iq[1], {xq.p, Sp, Sp}};
+    if ((rc = run_vm(ctx, P3, *Pp, count, ip, 3, t.p, Sp, Sp, exp))) return rc;
+    IoDesc fin[2] = {{t.p, Sp, Sp}, {xq.p, Sp, Sp}};
+    return run_vm(ctx, N3, *Pf, count, fin, 2, out, S3, S3);
+}
+
+// Exponentiations of the protocols that the holder of p, q may run over the prime powers (same results, about half the work)
+struct KeyHolderPow {
+    pgpu_ctx* ctx; bool crt; DevBuf zero; uint32_t wn, S2, e2bits;
+    KeyHolderPow(pgpu_ctx* c, size_t max_items)
+        : ctx(c), crt(c->has_secret && c->enc2_crt_ready && c->has_enc_crt && !getenv("PGPU_NO_CRT_PROTOCOLS")),
+          zero(c, crt ? max_items * 2 * c->wn : 1), wn((uint32_t)c->wn), S2(c->m_n2.sh.S), e2bits((uint32_t)c->n2.bitlen()) {
+        if (crt && zero.p) cudaMemsetAsync(zero.p, 0, max_items * 2 * c->wn * 4, c->stream);
+    }
+    // base^e mod n^3 with per-item exponents e (n^2-wide records)
+    int pow3_items(size_t k, const IoDesc& base, const uint32_t* e_ptr, uint32_t* out) {
+        const ExpDesc ed{e_ptr, S2, e2bits, nullptr};
+        return crt ? modexp3_items_crt(ctx, k, base, ed, out) : modexp_items_io(ctx, ctx->m_n3, k, base, ed, out);
+    }
+    // r^(n^2) mod n^3 = EncryptWithRAtLevel(0, r); r: n-wide records
+    int pow3_n2(size_t k, const uint32_t* r, uint32_t* out) {
+        return crt ? encrypt2_crt_dev(ctx, k, zero.p, r, out) : modexp_shared_io(ctx, ctx->m_n3, k, IoDesc{r, wn, wn}, ctx->n2, out);
+    }
+    // r^n mod n^2 = EncryptWithR(0, r)
+    int pow2_n(size_t k, const uint32_t* r, uint32_t* out) {
+        return crt ? encrypt_crt_dev(ctx, k, zero.p, r, out) : modexp_shared_io(ctx, ctx->m_n2, k, IoDesc{r, wn, wn}, ctx->n, out);
+    }
+};
+
 // NestedRandomize (operations.go:96-118) with a, b supplied: ct^(a^n mod n^2) * b^(n^2) mod n^3
 int nested_randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* ct, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     if (!ctx->level2_ready) return fail(ctx, PGPU_ERR_UNSUPPORTED, "level 2: n^3 is wider than the built kernel shapes");
     const ModCtx &M2 = ctx->m_n2, &M3 = ctx->m_n3;
-    const uint32_t S2 = M2.sh.S, S3 = M3.sh.S, wn = (uint32_t)ctx->wn, e2bits = (uint32_t)ctx->n2.bitlen();
+    const uint32_t S2 = M2.sh.S, S3 = M3.sh.S;
     DEVBUF(an, ctx, count * S2); DEVBUF(bn2, ctx, count * S3); DEVBUF(t, ctx, count * S3);
     int rc;
-    if ((rc = modexp_shared_io(ctx, M2, count, IoDesc{a, wn, wn}, ctx->n, an.p))) return rc;          // :108
-    if ((rc = modexp_shared_io(ctx, M3, count, IoDesc{b, wn, wn}, ctx->n2, bn2.p))) return rc;        // :109
-    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{ct, S3, S3}, ExpDesc{an.p, S2, e2bits, nullptr}, t.p))) return rc;   // :112
+    KeyHolderPow kh(ctx, count);                 // over p^3, q^3 when the context holds the secret key
+    if (kh.zero.err != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, "device allocation failed");
+    if ((rc = kh.pow2_n(count, a, an.p))) return rc;                                                  // a^n mod n^2      :108
+    if ((rc = kh.pow3_n2(count, b, bn2.p))) return rc;                                                // b^(n^2) mod n^3  :109
+    if ((rc = kh.pow3_items(count, IoDesc{ct, S3, S3}, an.p, t.p))) return rc;                        // ct^(a^n)         :112
     return modmul_dev(ctx, M3, count, t.p, bn2.p, out);                                               // :113-114
 }
 
@@ -519,20 +611,25 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     const uint32_t S2 = M2.sh.S, S3 = M3.sh.S, wn = (uint32_t)ctx->wn, e2bits = (uint32_t)ctx->n2.bitlen();
     const size_t total = count * secpar;
     int rc;
+    KeyHolderPow kh(ctx, std::max(total, count));   // the prover holds p, q: exponentiations run over the prime powers
+    if (kh.zero.err != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, "device allocation failed");
+    auto pow3_items = [&](size_t k, const IoDesc& base, const uint32_t* e_ptr, uint32_t* out) { return kh.pow3_items(k, base, e_ptr, out); };
+    auto pow3_n2 = [&](size_t k, const uint32_t* r, uint32_t* out) { return kh.pow3_n2(k, r, out); };
+    auto pow2_n = [&](size_t k, const uint32_t* r, uint32_t* out) { return kh.pow2_n(k, r, out); };
     // ---- per statement
     DEVBUF(an, ctx, count * S2); DEVBUF(bn2, ctx, count * S3); DEVBUF(t3, ctx, count * S3); DEVBUF(san, ctx, count * S3);
     DEVBUF(s, ctx, count * wn); DEVBUF(c0, ctx, count * S3); DEVBUF(ainv, ctx, count * S2); DEVBUF(a2, ctx, count * S2);
     DEVBUF(flags, ctx, (count + 3) / 4 + 1);
-    if ((rc = modexp_shared_io(ctx, M2, count, IoDesc{a, wn, wn}, ctx->n, an.p))) return rc;                                 // a^n        :63,104
-    if ((rc = modexp_shared_io(ctx, M3, count, IoDesc{b, wn, wn}, ctx->n2, bn2.p))) return rc;                               // b^(n^2)    :64
-    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{ct1, S3, S3}, ExpDesc{an.p, S2, e2bits, nullptr}, t3.p))) return rc;  // ct1^(a^n)  :63
+    if ((rc = pow2_n(count, a, an.p))) return rc;                                                                            // a^n        :63,104
+    if ((rc = pow3_n2(count, b, bn2.p))) return rc;                                                                          // b^(n^2)    :64
+    if ((rc = pow3_items(count, IoDesc{ct1, S3, S3}, an.p, t3.p))) return rc;                                                // ct1^(a^n)  :63
     if ((rc = modmul_dev(ctx, M3, count, t3.p, bn2.p, san.p))) return rc;                                                    // :64-65
     CU(ctx, equal_launch(san.p, ct2, S3, (uint32_t)count, (uint8_t*)flags.p, ctx->stream));                                  // :67
     ctx->launches++;
     CU(ctx, first_zero_launch((const uint8_t*)flags.p, (uint32_t)count, d_bad, ctx->stream));
     ctx->launches++;
     if ((rc = extract_randomness_dev(ctx, 2, count, ct1, s.p))) return rc;                                                   // s          :103
-    if ((rc = modexp_items_io(ctx, M3, count, IoDesc{s.p, wn, wn}, ExpDesc{an.p, S2, e2bits, nullptr}, t3.p))) return rc;  // s^(a^n)    :107
+    if ((rc = pow3_items(count, IoDesc{s.p, wn, wn}, an.p, t3.p))) return rc;                                                // s^(a^n)    :107
     if ((rc = modmul_io(ctx, M3, count, IoDesc{t3.p, S3, S3}, IoDesc{b, wn, wn}, c0.p))) return rc;                          // * b        :108
     CU(ctx, resize_launch(a, wn, wn, a2.p, S2, (uint32_t)count, ctx->stream));
     ctx->launches++;
@@ -540,9 +637,9 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     if ((rc = modinv_batch_dev(ctx, M2, count, a2.p, ainv.p, badinv.p))) return rc;                                                // a^-1 mod n^2 :96
     // ---- per instance
     DEVBUF(xn, ctx, total * S2); DEVBUF(yn2, ctx, total * S3); DEVBUF(u3, ctx, total * S3); DEVBUF(dig, ctx, total * 8);
-    if ((rc = modexp_shared_io(ctx, M2, total, IoDesc{x, wn, wn}, ctx->n, xn.p))) return rc;                                 // x^n        :81
-    if ((rc = modexp_shared_io(ctx, M3, total, IoDesc{y, wn, wn}, ctx->n2, yn2.p))) return rc;                               // y^(n^2)    :82
-    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{ct1, S3, S3, secpar}, ExpDesc{xn.p, S2, e2bits, nullptr}, u3.p))) return rc;   // ct1^xn :85
+    if ((rc = pow2_n(total, x, xn.p))) return rc;                                                                            // x^n        :81
+    if ((rc = pow3_n2(total, y, yn2.p))) return rc;                                                                          // y^(n^2)    :82
+    if ((rc = pow3_items(total, IoDesc{ct1, S3, S3, secpar}, xn.p, u3.p))) return rc;                                        // ct1^xn     :85
     if ((rc = modmul_dev(ctx, M3, total, u3.p, yn2.p, alpha))) return rc;                                                    // alpha      :86-87
     if ((rc = ddleq_hash(ctx, total, secpar, ct2, x, y, alpha, dig.p))) return rc;                                           // challenge  :91
     // (e, f) = (x, y) where the challenge bit is 0 ...
@@ -570,9 +667,9 @@ int ddleq_prove_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_t
     ctx->launches += 6;
     if ((rc = modmul_io(ctx, M2, n1, IoDesc{xg.p, wn, wn}, IoDesc{ainvg.p, S2, S2}, e1.p))) return rc;                       // e = x*a^-1 mod n^2 :94-99
     if ((rc = modexp_shared_dev(ctx, M2, n1, e1.p, ctx->n, en.p))) return rc;                                                // e^n        :105
-    if ((rc = modexp_items_io(ctx, M3, n1, IoDesc{c0g.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, u3.p))) return rc;     // (s^an*b)^en :109
+    if ((rc = pow3_items(n1, IoDesc{c0g.p, S3, S3}, en.p, u3.p))) return rc;                                                 // (s^an*b)^en :109
     if ((rc = modinv_batch_dev(ctx, M3, n1, u3.p, v3.p, badinv.p))) return rc;                                               // ^-1        :110
-    if ((rc = modexp_items_io(ctx, M3, n1, IoDesc{sg.p, wn, wn}, ExpDesc{xng.p, S2, e2bits, nullptr}, u3.p))) return rc;     // s^xn       :112
+    if ((rc = pow3_items(n1, IoDesc{sg.p, wn, wn}, xng.p, u3.p))) return rc;                                                 // s^xn       :112
     if ((rc = modmul_dev(ctx, M3, n1, v3.p, u3.p, v3.p))) return rc;                                                         // c          :112
     if ((rc = modmul_io(ctx, M3, n1, IoDesc{yg.p, wn, wn}, IoDesc{v3.p, S3, S3}, f1.p))) return rc;                          // f = y*c    :113-114
     CU(ctx, scatter_launch(e1.p, S2, didx.p, e, N1, ctx->stream));

@@ -171,6 +171,14 @@ def test_ddleq_prove_verify(keys):
     if not big:
         assert chal == {True, False}          # both challenge values exercised
     assert sk.VerifyDDLEQProofBatch(ct1, ct2, proofs) == [True] * count
+    # the prover works over p^3, q^3 (CRT); the direct route over n^3 must give the same transcripts
+    import os
+    os.environ["PGPU_NO_CRT_PROTOCOLS"] = "1"
+    try:
+        direct = sk.ProveDDLEQBatch(secpar, ct1, ct2, As, Bs, xs, ys)
+    finally:
+        del os.environ["PGPU_NO_CRT_PROTOCOLS"]
+    assert direct == proofs
     # soundness (ddleq_test.go:38-72): a proof for other ciphertexts / a tampered instance must be rejected
     bad = [DDLEQProof(list(p.Instances)) for p in proofs]
     i0 = bad[0].Instances[1]
