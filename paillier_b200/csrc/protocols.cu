@@ -482,6 +482,47 @@ int extract_randomness_dev(pgpu_ctx* ctx, int level, size_t count, const uint32_
     return PGPU_OK;
 }
 
+// out[i] = b1[i]^e1[i] * b2[i]^e2 mod M: per-item exponents e1 (exp.bits bits, fixed window) and one shared exponent e2,
+// interleaved so that the squarings are shared (Straus / Shamir): per window w squarings, one multiplication by
+// T1[bits of e1] (OP_WIN) and, where e2's window is non-zero, one by T2[bits of e2] (the host knows e2: a plain OP_MULT).
+static int modexp_dual_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& b1, const ExpDesc& exp, const IoDesc& b2,
+                          const BigU& e2, const std::string& e2_name, uint32_t* out) {
+    const size_t bits = std::max<size_t>(exp.bits, e2.bitlen());
+    const std::string key = "dual:" + std::to_string(M.sh.S) + ":" + std::to_string(exp.bits) + ":" + e2_name;
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        int w = 1;
+        { double best = 1e300; for (int c = 1; c <= 6; ++c) { double cost = 2.0 * (1u << c) + 2.0 * (double)bits / c; if (cost < best) { best = cost; w = c; } } }
+        const uint32_t n = 1u << w, B = n;                    // T1 = slots [0, n), T2 = slots [n, 2n)
+        np.emit(OP_LDI, 1);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_STT, B + 1);
+        for (uint32_t i = 2; i < n; ++i) { np.emit(OP_MULT, B + 1); np.n_mul++; np.emit(OP_STT, B + i); }
+        np.use_slot(B + n - 1);
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        np.emit(OP_STT, 1);
+        for (uint32_t i = 2; i < n; ++i) { np.emit(OP_MULT, 1); np.n_mul++; np.emit(OP_STT, i); }
+        np.emit(OP_LDC, K_R1); np.emit(OP_STT, 0);
+        const size_t nwin = (bits + w - 1) / w;
+        for (size_t k = nwin; k-- > 0;) {
+            np.emit(OP_WIN, (uint32_t)(k * w) | ((uint32_t)w << 20));
+            np.n_sqr += w; np.n_mul++;
+            uint32_t val = 0;
+            for (int j = w - 1; j >= 0; --j) val = (val << 1) | (e2.bit(k * w + j) ? 1u : 0u);
+            if (val) { np.emit(OP_MULT, B + val); np.n_mul++; }
+        }
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STO, 0);
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[2] = {b1, b2};
+    return run_vm(ctx, M, *P, count, ins, 2, out, M.sh.S, M.sh.S, exp);
+}
+
 // base[i]^exp[i] mod n^3 for the holder of p, q: the same exponentiation over q^3 and p^3 (half-width moduli, the
 // exponent unreduced so that no assumption on the base is needed), Garner's step in the tail of the p^3 program and
 // x = x_q + q^3*t over n^3.  Bit-identical to modexp_items_io(M3, ...) -- both return the canonical residue.
@@ -582,6 +623,8 @@ int nested_randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* ct, const 
     KeyHolderPow kh(ctx, count);                 // over p^3, q^3 when the context holds the secret key
     if (kh.zero.err != cudaSuccess) return fail(ctx, PGPU_ERR_CUDA, "device allocation failed");
     if ((rc = kh.pow2_n(count, a, an.p))) return rc;                                                  // a^n mod n^2      :108
+    if (!kh.crt && !getenv("PGPU_NO_DUAL_EXP"))                                                       // ct^(a^n) * b^(n^2), squarings shared :109-114
+        return modexp_dual_io(ctx, M3, count, IoDesc{ct, S3, S3}, ExpDesc{an.p, S2, kh.e2bits, nullptr}, IoDesc{b, kh.wn, kh.wn}, ctx->n2, "n2", out);
     if ((rc = kh.pow3_n2(count, b, bn2.p))) return rc;                                                // b^(n^2) mod n^3  :109
     if ((rc = kh.pow3_items(count, IoDesc{ct, S3, S3}, an.p, t.p))) return rc;                        // ct^(a^n)         :112
     return modmul_dev(ctx, M3, count, t.p, bn2.p, out);                                               // :113-114
@@ -692,9 +735,13 @@ int ddleq_verify_dev(pgpu_ctx* ctx, size_t count, uint32_t secpar, const uint32_
     CU(ctx, select_launch(dig.p, ct2, secpar, ct1, secpar, S3, (uint32_t)total, chk.p, ctx->stream));                        // :140-143
     ctx->launches++;
     if ((rc = modexp_shared_dev(ctx, M2, total, e, ctx->n, en.p))) return rc;                                                // E^n        :145
-    if ((rc = modexp_shared_dev(ctx, M3, total, f, ctx->n2, fn2.p))) return rc;                                              // F^(n^2)    :146
-    if ((rc = modexp_items_io(ctx, M3, total, IoDesc{chk.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, t.p))) return rc;  // check^en   :148
-    if ((rc = modmul_dev(ctx, M3, total, t.p, fn2.p, t.p))) return rc;                                                       // :149-150
+    if (getenv("PGPU_NO_DUAL_EXP")) {
+        if ((rc = modexp_shared_dev(ctx, M3, total, f, ctx->n2, fn2.p))) return rc;                                              // F^(n^2)    :146
+        if ((rc = modexp_items_io(ctx, M3, total, IoDesc{chk.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, t.p))) return rc;  // check^en   :148
+        if ((rc = modmul_dev(ctx, M3, total, t.p, fn2.p, t.p))) return rc;                                                       // :149-150
+    } else {                                                                            // check^en * F^(n^2) with shared squarings :146-150
+        if ((rc = modexp_dual_io(ctx, M3, total, IoDesc{chk.p, S3, S3}, ExpDesc{en.p, S2, e2bits, nullptr}, IoDesc{f, S3, S3}, ctx->n2, "n2", t.p))) return rc;
+    }
     CU(ctx, equal_launch(alpha, t.p, S3, (uint32_t)total, ok, ctx->stream));                                                 // :152
     ctx->launches++;
     return PGPU_OK;

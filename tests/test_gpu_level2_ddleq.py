@@ -190,3 +190,44 @@ def test_ddleq_prove_verify(keys):
     with pytest.raises(PgpuError) as ei:
         sk.ProveDDLEQBatch(secpar, ct1, ct2, As[::-1], Bs, xs, ys)
     assert ei.value.code == PGPU_ERR_ARG and "inputs are wrong" in str(ei.value)
+
+
+def test_nested_randomize_three_routes(keys):
+    """NestedRandomize (operations.go:96-118) = ct^(a^n mod n^2) * b^(n^2) mod n^3: the key holder's route over p^3, q^3,
+    the public-key route with interleaved (shared-squaring) exponentiation and the plain route give the same bits;
+    DDLEQ verification accepts/rejects identically with and without the interleaved exponentiation."""
+    import os
+    sk, osk, opk, rnd = keys
+    n = sk.N
+    n2, n3 = n * n, n ** 3
+    count = 9
+    cts = [Ciphertext(rnd.randrange(1, n3), ENC_LEVEL_TWO) for _ in range(count)]
+    As, Bs = _units(rnd, n, count), _units(rnd, n, count)
+    want = [pow(c.C, pow(a, n, n2), n3) * pow(b, n2, n3) % n3 for c, a, b in zip(cts, As, Bs)]
+    pk = PublicKey(n)
+    try:
+        assert [c.C for c in sk.NestedRandomizeWithBatch(cts, As, Bs)] == want          # CRT
+        assert [c.C for c in pk.NestedRandomizeWithBatch(cts, As, Bs)] == want          # interleaved
+        os.environ["PGPU_NO_DUAL_EXP"] = "1"
+        os.environ["PGPU_NO_CRT_PROTOCOLS"] = "1"
+        assert [c.C for c in pk.NestedRandomizeWithBatch(cts, As, Bs)] == want          # plain
+        assert [c.C for c in sk.NestedRandomizeWithBatch(cts, As, Bs)] == want
+        del os.environ["PGPU_NO_DUAL_EXP"], os.environ["PGPU_NO_CRT_PROTOCOLS"]
+        # a small DDLEQ statement verified through both routes, honest and tampered
+        inner = sk.EncryptWithRBatch([5], _units(rnd, n, 1))
+        ct1 = sk.EncryptWithRAtLevelBatch([inner[0].C], _units(rnd, n, 1), ENC_LEVEL_TWO)
+        a, b = _units(rnd, n, 1), _units(rnd, n, 1)
+        ct2 = sk.NestedRandomizeWithBatch(ct1, a, b)
+        proofs = sk.ProveDDLEQBatch(6, ct1, ct2, a, b, [_units(rnd, n, 6)], [_units(rnd, n, 6)])
+        bad = [DDLEQProof(list(proofs[0].Instances))]
+        i0 = bad[0].Instances[2]
+        bad[0].Instances[2] = DDLEQProofInstance(i0.X, i0.Y, i0.Alpha, (i0.E + 1) % n2, i0.F)
+        for env in (None, "1"):
+            if env:
+                os.environ["PGPU_NO_DUAL_EXP"] = env
+            assert pk.VerifyDDLEQProofBatch(ct1, ct2, proofs) == [True]
+            assert pk.VerifyDDLEQProofBatch(ct1, ct2, bad) == [False]
+    finally:
+        os.environ.pop("PGPU_NO_DUAL_EXP", None)
+        os.environ.pop("PGPU_NO_CRT_PROTOCOLS", None)
+        pk.close()
