@@ -9,6 +9,10 @@
   the partial decryptions of ALL ciphertexts, one all-gather moves them ([share][ciphertext] layout), then
   rank r combines ciphertext slice r (thresholdkey.go:149-161) straight out of the gathered buffer.
 
+* Safe-prime search (threshold key generation, SURVEY 8e "replicas only, one winner"): rank 0 reads a batch of
+  candidate byte strings from the random source and broadcasts it, rank r tests slice r, one MIN all-reduce picks the
+  earliest accepted candidate in stream order -- the same (p, q) a single device returns for that stream.
+
 The compute steps are injected as callables so that the plumbing can be exercised with the gloo backend on
 CPU tensors in tests (tests/test_multi_gloo.py); `gpu_threshold_round` binds them to the CUDA engine.
 """
@@ -69,6 +73,57 @@ def sharded_add(dist, rank: int, world: int, record_width: int, local_product: "
     else:
         parts.copy_(local_product)
     return multiply_all(parts)
+
+
+def sharded_safe_prime(dist, rank: int, world: int, bit_len: int, random_reader: Optional[Callable[[int], bytes]],
+                       scan: Callable[[int, bytes], Tuple[Sequence[int], Sequence[int], Sequence[bool]]],
+                       batch: int = 1 << 14, max_batches: int = 64):
+    """GenerateSafePrime (safe_prime.go:61-105) with the candidate stream split across ranks.
+
+    random_reader(nbytes) -> bytes is consulted on rank 0 only (other ranks may pass None); every batch is broadcast so
+    that all ranks see the same stream.  scan(bit_len, raw) -> (ps, qs, accepted) is the per-candidate procedure
+    (keygen.safe_prime_scan on a GPU; a CPU stand-in in the gloo tests).  Returns (p, q) of the first accepted
+    candidate in stream order on every rank -- identical to the single-device search over the same stream."""
+    import torch
+    if bit_len < 6:
+        raise ValueError("safe prime size must be at least 6 bits")               # safe_prime.go:67-69
+    nb = (bit_len - 1 + 7) // 8
+    pw = (bit_len + 7) // 8
+    NONE = 1 << 62
+    for _ in range(max_batches):
+        raw = torch.empty(batch * nb, dtype=torch.uint8)
+        if rank == 0:
+            data = random_reader(batch * nb)
+            if len(data) != batch * nb:
+                raise ValueError("random source returned a short read")
+            raw.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(raw, src=0)
+        lo, hi = shard_range(batch, world, rank)
+        ps, qs, ok = scan(bit_len, raw[lo * nb:hi * nb].numpy().tobytes()) if hi > lo else ([], [], [])
+        first = next((i for i, good in enumerate(ok) if good), None)
+        best = torch.tensor([NONE if first is None else lo + first], dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
+        win = int(best.item())
+        if win == NONE:
+            continue
+        owner = next(r for r in range(world) if shard_range(batch, world, r)[0] <= win < shard_range(batch, world, r)[1])
+        pq = torch.zeros(2 * pw, dtype=torch.uint8)
+        if rank == owner:
+            pq.copy_(torch.frombuffer(bytearray(ps[win - lo].to_bytes(pw, "big") + qs[win - lo].to_bytes(pw, "big")), dtype=torch.uint8))
+        if world > 1:
+            dist.broadcast(pq, src=owner)
+        b = pq.numpy().tobytes()
+        return int.from_bytes(b[:pw], "big"), int.from_bytes(b[pw:], "big")
+    raise TimeoutError(f"generator gave up after {max_batches} batches of {batch} candidates")   # safe_prime.go:101-103
+
+
+def gpu_safe_prime_search(dist, rank: int, world: int, bit_len: int, random_reader, device: int, batch: int = 1 << 14, max_batches: int = 64):
+    """sharded_safe_prime bound to the CUDA candidate procedure (keygen.safe_prime_scan) on `device`"""
+    from .keygen import safe_prime_scan
+    return sharded_safe_prime(dist, rank, world, bit_len, random_reader, lambda bits, raw: safe_prime_scan(bits, raw, device),
+                              batch=batch, max_batches=max_batches)
 
 
 def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, with_zkp_r=None):

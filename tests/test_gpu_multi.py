@@ -70,3 +70,15 @@ def test_device_resident_chain():
     assert from_records(out.cpu().numpy(), sk.w_n) == [expect]
     check(lib.pgpu_ctx_set_stream(sk._ctx, None), sk._ctx)
     sk.close()
+
+
+def test_sharded_safe_prime_world1_matches_single_device_search():
+    # SURVEY 8(e), threshold keygen: the split search returns the first accepted candidate in stream order,
+    # i.e. what GenerateSafePrime returns for the same stream
+    from paillier_b200.keygen import GenerateSafePrime, safe_prime_scan
+    from paillier_b200.multi import sharded_safe_prime
+    for bits, batch in ((64, 512), (128, 2048)):
+        r1, r2 = random.Random(77), random.Random(77)
+        want = GenerateSafePrime(bits, lambda nb: r1.randbytes(nb), batch=batch)
+        got = sharded_safe_prime(None, 0, 1, bits, lambda nb: r2.randbytes(nb), safe_prime_scan, batch=batch)
+        assert got == want and got[0] == 2 * got[1] + 1 and got[0].bit_length() == bits

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import paillier_ref as R
-from paillier_b200.multi import shard_range, sharded_add, threshold_round
+from paillier_b200.multi import shard_range, sharded_add, sharded_safe_prime, threshold_round
 
 
 def test_shard_range_partitions_everything():
@@ -114,3 +114,50 @@ def test_threshold_round_and_sharded_add_gloo(world, count, drop):
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
     assert res[0][2] == 0 and res[-1][3] == count
+
+
+# ---- safe-prime search split across ranks (one winner, earliest in stream order) -------------------------
+
+def _oracle_scan(bit_len, raw):
+    nb = (bit_len - 1 + 7) // 8
+    ps, qs, ok = [], [], []
+    for i in range(0, len(raw), nb):
+        p, q, good = R.safe_prime_candidate(raw[i:i + nb], bit_len)
+        ps.append(p); qs.append(q); ok.append(good)
+    return ps, qs, ok
+
+
+def _stream_reader(seed):
+    rnd = random.Random(seed)
+    return lambda nbytes: rnd.randbytes(nbytes)
+
+
+def _sp_worker(rank, world, port, bits, batch, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        reader = _stream_reader(seed) if rank == 0 else None
+        q.put((rank, sharded_safe_prime(dist, rank, world, bits, reader, _oracle_scan, batch=batch, max_batches=40)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,bits,batch", [(2, 16, 64), (3, 24, 50)])
+def test_sharded_safe_prime_gloo(world, bits, batch):
+    seed = 1234
+    # single-process answer over the same stream: first accepted candidate in stream order
+    want = sharded_safe_prime(None, 0, 1, bits, _stream_reader(seed), _oracle_scan, batch=batch, max_batches=40)
+    p, qv = want
+    assert p == 2 * qv + 1 and p.bit_length() == bits
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sp_worker, args=(r, world, port, bits, batch, seed, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert [r[1] for r in res] == [want] * world
