@@ -8,7 +8,7 @@ std::string& thread_error() { return g_err; }
 
 // smallest built shape holding `limbs` limbs; override with PGPU_SHAPE_<S>="tpi,L"
 bool pick_shape(size_t limbs, Shape& out) {
-    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 8, 12}, {128, 4, 32}, {192, 8, 24}};
+    static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 4, 24}, {128, 4, 32}, {192, 8, 24}};
     for (const Shape& s : defaults) {
         if ((size_t)s.S >= limbs) {
             out = s;
@@ -60,6 +60,11 @@ int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
     if ((rc = set_kconst(ctx, m, K_R3, m.R3))) return rc;
     m.blocks_per_sm = vm_occupancy(m.sh.tpi, m.sh.L);
     if (m.blocks_per_sm <= 0) return fail(ctx, PGPU_ERR_CUDA, "powm_vm occupancy query failed for shape");
+    m.sh_items = m.sh; m.blocks_per_sm_items = m.blocks_per_sm;
+    if (m.sh.S == 96 && m.sh.tpi == 4 && !getenv("PGPU_SHAPE_96")) {      // measured: tools/ddleq_rate.py, tools/shape96.py
+        const int b = vm_occupancy(8, 12);
+        if (b > 0) { m.sh_items = Shape{96, 8, 12}; m.blocks_per_sm_items = b; }
+    }
     m.ready = true;
     return PGPU_OK;
 }
@@ -166,8 +171,10 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const ExpDesc& ex, uint32_t* out2, uint32_t out2_stride, int force_blocks) {
     if (count == 0) return PGPU_OK;
     if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
-    const int gpb = VM_BLOCK_THREADS / m.sh.tpi;
-    const size_t max_blocks = (size_t)ctx->sms * m.blocks_per_sm;
+    const bool items_shape = prog.per_item && force_blocks <= 0;
+    const Shape& sh = items_shape ? m.sh_items : m.sh;
+    const int gpb = VM_BLOCK_THREADS / sh.tpi;
+    const size_t max_blocks = (size_t)ctx->sms * (items_shape ? m.blocks_per_sm_items : m.blocks_per_sm);
     const size_t want = (count + gpb - 1) / gpb;
     const int blocks = force_blocks > 0 ? force_blocks : (int)std::min(max_blocks, want);
     VmParams P{};
@@ -186,7 +193,7 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     if (rc) return rc;
     P.table = ctx->d_table;
     P.dump = ctx->d_table + tbl_limbs;
-    CU(ctx, vm_launch(m.sh.tpi, m.sh.L, P, blocks, ctx->stream));
+    CU(ctx, vm_launch(sh.tpi, sh.L, P, blocks, ctx->stream));
     ctx->launches++;
     return PGPU_OK;
 }

@@ -38,7 +38,8 @@ struct Program {
     std::vector<uint32_t> ops;
     uint32_t* d_ops = nullptr;
     uint32_t n_sqr = 0, n_mul = 0, tbl_entries = 0;
-    void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); }
+    bool per_item = false;          // uses OP_WIN: table entries picked by per-item exponent bits
+    void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); if (code == OP_WIN) per_item = true; }
     void use_slot(uint32_t s) { tbl_entries = std::max(tbl_entries, s + 1); }
 };
 
@@ -50,6 +51,8 @@ struct ModCtx {
     uint32_t* d_mod = nullptr;
     uint32_t* d_kconst = nullptr;   // K_SLOTS records of S limbs
     int blocks_per_sm = 0;
+    Shape sh_items{};               // shape for programs with per-item exponents (more warps in flight hide the table loads)
+    int blocks_per_sm_items = 0;
 };
 
 // fixed-base comb table for OP_FIXW: row k holds base^(d * 2^(w*k)), d = 0 .. 2^w-1, Montgomery form
