@@ -27,6 +27,44 @@ def test_header_symbols_are_exported_and_bound():
     assert L.lib.pgpu_version() == 1
 
 
+def test_go_binding_and_cpp_mirror_use_declared_symbols_only():
+    """go/*.go (uncompiled here) and include/paillier_b200.hpp may only call what pgpu.h declares, with the right arity."""
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "pgpu.h")).read(), flags=re.S)
+    arity = {}
+    for name, args in re.findall(r"\b(pgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        arity[name] = 0 if args.strip() in ("", "void") else args.count(",") + 1
+
+    def calls(text, prefix):
+        out = []
+        for m in re.finditer(prefix + r"(pgpu_[a-z0-9_]+)\s*\(", text):
+            depth, i, n_args, any_arg = 1, m.end(), 0, False
+            while depth:
+                ch = text[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    n_args += 1
+                if depth and not ch.isspace():
+                    any_arg = True
+                i += 1
+            out.append((m.group(1), n_args + 1 if any_arg else 0))
+        return out
+
+    go_dir = os.path.join(ROOT, "go")
+    used = []
+    for f in sorted(os.listdir(go_dir)):
+        if f.endswith(".go"):
+            used += calls(open(os.path.join(go_dir, f)).read(), r"C\.")
+    assert len({n for n, _ in used}) >= 25
+    hpp = open(os.path.join(ROOT, "include", "paillier_b200.hpp")).read()
+    used += calls(hpp, r"(?<![A-Za-z_])")
+    for name, n in used:
+        assert name in arity, f"{name} is not declared in pgpu.h"
+        assert n == arity[name], f"{name}: called with {n} arguments, declared with {arity[name]}"
+
+
 def test_no_torch_types_in_abi():
     header = open(os.path.join(ROOT, "include", "pgpu.h")).read()
     assert "torch" not in header.lower() and "at::" not in header
