@@ -161,3 +161,13 @@ def test_sharded_safe_prime_gloo(world, bits, batch):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert [r[1] for r in res] == [want] * world
+
+
+def test_sharded_safe_prime_gives_up_and_validates_arguments():
+    reject_all = lambda bits, raw: ([0] * (len(raw) // 2), [0] * (len(raw) // 2), [False] * (len(raw) // 2))
+    with pytest.raises(TimeoutError):                       # safe_prime.go:101-103: the generator gives up
+        sharded_safe_prime(None, 0, 1, 16, _stream_reader(1), reject_all, batch=8, max_batches=3)
+    with pytest.raises(ValueError):                         # safe_prime.go:67-69
+        sharded_safe_prime(None, 0, 1, 5, _stream_reader(1), reject_all)
+    with pytest.raises(ValueError):                         # short read from the random source
+        sharded_safe_prime(None, 0, 1, 16, lambda nb: b"\x00", reject_all, batch=8, max_batches=1)
