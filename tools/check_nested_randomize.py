@@ -1,4 +1,4 @@
-"""debug: key-holder (CRT) exponentiations through NestedRandomize / DDLEQ against Python ints"""
+"""NestedRandomize on a SecretKey context (exponentiations over the prime powers) against Python ints at several batch sizes"""
 import os, random, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from paillier_b200 import synth
