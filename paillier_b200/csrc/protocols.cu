@@ -166,6 +166,14 @@ int encrypt2_dev(pgpu_ctx* ctx, size_t count, const uint32_t* m, const uint32_t*
 int randomize_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* out) {
     const ModCtx& M = ctx->m_n2;
     const uint32_t wn = (uint32_t)ctx->wn, S = M.sh.S;
+    if (ctx->has_secret && ctx->has_enc_crt && !getenv("PGPU_NO_CRT_PROTOCOLS")) {
+        // key holder: r^n = EncryptWithR(0, r) over p^2 and q^2 (encrypt_crt_dev), then one multiplication
+        DEVBUF(zero, ctx, count * wn); DEVBUF(rn, ctx, count * S);
+        CU(ctx, cudaMemsetAsync(zero.p, 0, count * wn * 4, ctx->stream));
+        int rc = encrypt_crt_dev(ctx, count, zero.p, r, rn.p);
+        if (rc) return rc;
+        return modmul_dev(ctx, M, count, c, rn.p, out);
+    }
     IoDesc ins[2] = {{r, wn, wn}, {c, S, S}};
     return run_vm(ctx, M, ctx->prog_rand, count, ins, 2, out, S, S);
 }

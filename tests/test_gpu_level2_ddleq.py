@@ -117,6 +117,9 @@ def test_randomize_and_extract_randomness(keys):
     assert [c.C for c in rz] == [R.add(opk, R.Ciphertext(c.C), R.encrypt_with_r(opk, 0, r)).C for c, r in zip(cts, r2)]
     assert sk.DecryptBatch(rz) == ms
     assert sk.ExtractRandonnessBatch(rz) == [a * b % n for a, b in zip(rs, r2)]
+    pk = PublicKey(n)                      # public-key route (r^n mod n^2 directly) against the key holder's (over p^2, q^2)
+    assert [c.C for c in pk.RandomizeWithRBatch(cts, r2)] == [c.C for c in rz]
+    pk.close()
 
 
 def test_nested_operations(keys):
