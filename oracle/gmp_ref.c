@@ -252,6 +252,31 @@ int ref_modmul(const uint8_t* mod_be, size_t mod_len, size_t count, const uint8_
     return 0;
 }
 
+/* ---- gmp.Int.ModInverse (mpz_invert) per item: Sub (operations.go:46-50), verifyPart1/2 (thresholdkey.go:293-311),
+ *      proveDDLEQInstance (ddleq.go:96,110).  ok[i] = 0 where no inverse exists (the record is left zero). ---- */
+static void modinv_items(const job_t* j, size_t lo, size_t hi) {
+    mpz_t a;
+    mpz_init(a);
+    for (size_t i = lo; i < hi; ++i) {
+        imp_le(a, j->a + i * j->wa, j->wa);
+        const int ok = mpz_invert(a, a, j->k1);
+        ((uint8_t*)j->b)[i] = (uint8_t)(ok != 0);
+        if (ok) exp_le(j->out + i * j->wout, j->wout, a);
+    }
+    mpz_clear(a);
+}
+
+int ref_modinv(const uint8_t* mod_be, size_t mod_len, size_t count, const uint8_t* a, size_t width, uint8_t* out,
+               uint8_t* ok, int threads) {
+    job_t j; memset(&j, 0, sizeof j);
+    mpz_init(j.k1);
+    imp_be(j.k1, mod_be, mod_len);
+    j.fn = modinv_items; j.a = a; j.b = ok; j.out = out; j.wa = width; j.wout = width;
+    run_parallel(&j, count, threads);
+    mpz_clear(j.k1);
+    return 0;
+}
+
 /* ---- Add over a batch (operations.go:11-29): accumulator := Mod(Mul(accumulator, c), ns1).
  *      Each thread folds its slice; partial products are folded at the end (same value). ---- */
 static void fold_items(const job_t* j, size_t lo, size_t hi) {

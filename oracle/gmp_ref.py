@@ -96,6 +96,17 @@ def modmul(mod: int, a, b, width: int, threads: int = 0) -> np.ndarray:
     return out
 
 
+def modinv(mod: int, a, width: int, threads: int = 0):
+    """-> (inverses, ok): mpz_invert per record; ok[i] = 0 where a[i] is not a unit (record left zero)"""
+    a = _u8(a)
+    count = a.size // width
+    out = np.zeros(count * width, dtype=np.uint8)
+    ok = np.zeros(count, dtype=np.uint8)
+    mb = _be(mod)
+    lib().ref_modinv(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(a), C.c_size_t(width), _p(out), _p(ok), threads or cores())
+    return out, ok
+
+
 def add_reduce(mod: int, c, width: int, threads: int = 0) -> np.ndarray:
     c = _u8(c)
     count = c.size // width

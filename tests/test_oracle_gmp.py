@@ -45,3 +45,21 @@ def test_partial_decrypt_kat_and_modexp():
     out = G.add_reduce(n2, to_records(bases, 256), 256, threads=3)
     pk = R.PublicKey(N=n)
     assert from_records(out, 256) == [R.add(pk, *[R.Ciphertext(b) for b in bases]).C]
+
+
+def test_modinv_and_sub_call_sequence_match_python_oracle():
+    # Sub (operations.go:32-55): ct1 * ModInverse(ct2, n^2) through mpz_invert / mpz_mul / mpz_mod at 2048 bits
+    p, q, n = _key("paillier_2048")
+    n2 = n * n
+    pk = R.PublicKey(N=n)
+    a = [pow(5, i + 3, n2) for i in range(6)]
+    b = [pow(7, 2 * i + 1, n2) for i in range(6)]
+    inv, ok = G.modinv(n2, to_records(b, 512), 512, threads=2)
+    assert ok.tolist() == [1] * 6
+    assert from_records(inv, 512) == [pow(x, -1, n2) for x in b]
+    out = G.modmul(n2, to_records(a, 512), inv, 512)
+    assert from_records(out, 512) == [R.sub(pk, R.Ciphertext(x), R.Ciphertext(y)).C for x, y in zip(a, b)]
+    # non-units are reported, not inverted (mpz_invert returns 0)
+    inv, ok = G.modinv(n2, to_records([p, 2, q * q, 1], 512), 512, threads=1)
+    assert ok.tolist() == [0, 1, 0, 1]
+    assert from_records(inv, 512) == [0, pow(2, -1, n2), 0, 1]
