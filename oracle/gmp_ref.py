@@ -114,3 +114,59 @@ def add_reduce(mod: int, c, width: int, threads: int = 0) -> np.ndarray:
     mb = _be(mod)
     lib().ref_add_reduce(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(c), C.c_size_t(width), _p(out), threads or cores())
     return out
+
+
+def pdec_zkp(n: int, share: int, l: int, v: int, c, r, w_n2: int, w_z: int, threads: int = 0):
+    """PartialDecryptionWithZKP (thresholdkey.go:225-255) with r supplied -> (dec, e, z) records (e: 32 bytes little-endian)"""
+    c, r = _u8(c), _u8(r)
+    count = c.size // w_n2
+    dec = np.zeros(count * w_n2, dtype=np.uint8)
+    e = np.zeros(count * 32, dtype=np.uint8)
+    z = np.zeros(count * w_z, dtype=np.uint8)
+    nb, sb, vb = _be(n), _be(share), _be(v)
+    lib().ref_pdec_zkp(nb, C.c_size_t(len(nb)), sb, C.c_size_t(len(sb)), l, vb, C.c_size_t(len(vb)), C.c_size_t(count), _p(c), _p(r),
+                       C.c_size_t(w_n2), _p(dec), _p(e), _p(z), C.c_size_t(w_z), threads or cores())
+    return dec, e, z
+
+
+def zkp_verify(n: int, v: int, vi: int, c, dec, e, z, w_n2: int, w_z: int, threads: int = 0) -> np.ndarray:
+    """PartialDecryptionZKP.VerifyProof (thresholdkey.go:278-311) for proofs of the server whose verification key is vi"""
+    c, dec, e, z = _u8(c), _u8(dec), _u8(e), _u8(z)
+    count = c.size // w_n2
+    ok = np.zeros(count, dtype=np.uint8)
+    nb, vb, vib = _be(n), _be(v), _be(vi)
+    lib().ref_zkp_verify(nb, C.c_size_t(len(nb)), vb, C.c_size_t(len(vb)), vib, C.c_size_t(len(vib)), C.c_size_t(count), _p(c), _p(dec),
+                         _p(e), _p(z), C.c_size_t(w_n2), C.c_size_t(w_z), _p(ok), threads or cores())
+    return ok
+
+
+def ddleq_verify(n: int, secpar: int, ct1, ct2, x, y, alpha, e, f, w_n: int, w_n2: int, w_n3: int, threads: int = 0) -> np.ndarray:
+    """verifyDDLEQProofInstance (ddleq.go:129-153) for count statements x secpar instances -> ok per instance"""
+    ct1, ct2, x, y, alpha, e, f = (_u8(a) for a in (ct1, ct2, x, y, alpha, e, f))
+    count = ct1.size // w_n3
+    ok = np.zeros(count * secpar, dtype=np.uint8)
+    nb = _be(n)
+    lib().ref_ddleq_verify(nb, C.c_size_t(len(nb)), C.c_size_t(count), C.c_uint(secpar), _p(ct1), _p(ct2), _p(x), _p(y), _p(alpha), _p(e),
+                           _p(f), C.c_size_t(w_n), C.c_size_t(w_n2), C.c_size_t(w_n3), _p(ok), threads or cores())
+    return ok
+
+
+def dot_u64(mod: int, c, width: int, k, threads: int = 0) -> np.ndarray:
+    """prod c[i]^k[i] mod `mod`: ConstMult (operations.go:58-64) per term folded by Add (operations.go:11-29)"""
+    c = _u8(c)
+    k = np.ascontiguousarray(k, dtype=np.uint64)
+    count = c.size // width
+    out = np.zeros(width, dtype=np.uint8)
+    mb = _be(mod)
+    lib().ref_dot_u64(mb, C.c_size_t(len(mb)), C.c_size_t(count), _p(c), C.c_size_t(width), _p(k), _p(out), threads or cores())
+    return out
+
+
+def safe_prime_scan(p_bits: int, raw: bytes, threads: int = 0) -> np.ndarray:
+    """one iteration of runGenPrimeRoutine's loop (safe_prime.go:170-263) per byte string -> accept flags"""
+    nb = (p_bits - 1 + 7) // 8
+    a = np.frombuffer(raw, dtype=np.uint8)
+    count = a.size // nb
+    ok = np.zeros(count, dtype=np.uint8)
+    lib().ref_safe_prime_scan(C.c_uint(p_bits), C.c_size_t(count), _p(a), _p(ok), threads or cores())
+    return ok

@@ -30,8 +30,9 @@ def units(rnd, n, k):
     return out
 
 
-def main():
-    out = {"generator": "tools/gen_golden.py", "oracle": "oracle/paillier_ref.py", "cases": {}}
+def build_cases():
+    """every vector of the "cases" section, recomputed by oracle/paillier_ref.py (whatever bignum primitives it is bound to)"""
+    out = {"cases": {}}
     for name in ("paillier_64", "paillier_1024", "paillier_2048"):
         rnd = random.Random("golden:" + name)
         p, q = int(KEYS[name]["p"], 16), int(KEYS[name]["q"], 16)
@@ -91,6 +92,11 @@ def main():
             "partial_decrypt_id2": [H(z.Decryption) for z in zk], "zkp_r": [H(x) for x in zr],
             "zkp_e": [H(z.E) for z in zk], "zkp_z": [H(z.Z) for z in zk],
         }
+    return out["cases"]
+
+
+def main():
+    out = {"generator": "tools/gen_golden.py", "oracle": "oracle/paillier_ref.py", "cases": build_cases()}
     # safe-prime candidate procedure (safe_prime.go:170-263): byte strings -> (p, q, accepted)
     sp = {}
     for p_bits, count in ((16, 40), (64, 400), (1024, 24)):
