@@ -685,14 +685,14 @@ int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t*
 }
 
 // PartialDecryptionWithZKP (thresholdkey.go:225-255), r supplied
-int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z) {
+int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z, bool dec_given) {
     if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecryptionWithZKP: no threshold share loaded");
     ModCtx& M = ctx->m_n2;
     const uint32_t S = M.sh.S;
     const BigU k = ctx->tk_delta * ctx->tk_share;
     if (k.v.size() + 8 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "share too large for the Z record");
     int rc;
-    if ((rc = pdec_dev(ctx, count, c, dec))) return rc;
+    if (!dec_given && (rc = pdec_dev(ctx, count, c, dec))) return rc;
     DEVBUF(c4r, ctx, count * S); DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(v, ctx, S);
     DEVBUF(kd, ctx, k.v.size() + 1);
     if ((rc = upload(ctx, v.p, ctx->tk_v.limbs(S)))) return rc;

@@ -208,7 +208,8 @@ int bigmul_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, uint32_t na, cons
 int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, const uint32_t* stride, const int* limbs, uint32_t* out,
             const uint32_t* div = nullptr);
 uint32_t z_limbs(const pgpu_ctx* ctx);
-int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z);
+// dec_given: dec already holds PartialDecrypt(c) (the caller ran pdec_dev), only a, b, E, Z are computed
+int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z, bool dec_given = false);
 int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok);
 // share j's batch starts at record j*share_stride (0 = count: tightly packed)
 int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
