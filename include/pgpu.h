@@ -219,6 +219,10 @@ int pgpu_sub_pairs_dev(pgpu_ctx* ctx, size_t count, const void* a, const void* b
 int pgpu_randomize_with_r_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* out);
 
 int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, void* dec, void* e, void* z);
+/* the proof half of PartialDecryptionWithZKP (thresholdkey.go:233-254) for partial decryptions the caller already holds
+ * (dec = output of pgpu_partial_decrypt_dev for the same c): computes E and Z only, so that a share-holder can time or
+ * pipeline PartialDecrypt and the proof separately.  Same E, Z as pgpu_pdec_zkp_prove_dev. */
+int pgpu_pdec_zkp_prove_given_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, const void* dec, void* e, void* z);
 int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
 /* as pgpu_combine_dev, but share j's batch starts at record j*share_stride of decs: combines a slice of the
  * all-gathered [share][ciphertext] buffer in place (one share-holder per GPU) */

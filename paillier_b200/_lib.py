@@ -70,6 +70,7 @@ SIGNATURES = {
     "pgpu_pdec_zkp_verify": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
     "pgpu_combine": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
     "pgpu_pdec_zkp_prove_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
+    "pgpu_pdec_zkp_prove_given_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
     "pgpu_combine_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
     "pgpu_ctx_set_alt_generator": (C.c_int, [_p, _u8p, _sz, C.c_uint]),
     "pgpu_encrypt_with_r_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),

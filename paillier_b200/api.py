@@ -412,10 +412,16 @@ class PublicKey:
         x, y = to_records([i.X for i in inst], self.w_n), to_records([i.Y for i in inst], self.w_n)
         al, e, f = (to_records([i.Alpha for i in inst], self.w_n3), to_records([i.E for i in inst], self.w_n2),
                     to_records([i.F for i in inst], self.w_n3))
-        ok = np.zeros(len(inst), dtype=np.uint8)
-        check(lib.pgpu_ddleq_verify(self._ctx, len(proofs), secpar, _ptr(c1), _ptr(c2), _ptr(x), _ptr(y), _ptr(al), _ptr(e), _ptr(f),
-                                    _ptr(ok)), self._ctx)
+        ok = self.verify_ddleq_records(len(proofs), secpar, c1, c2, x, y, al, e, f)
         return [bool(ok[i * secpar:(i + 1) * secpar].all()) for i in range(len(proofs))]
+
+    def verify_ddleq_records(self, count: int, secpar: int, c1, c2, x, y, al, e, f) -> np.ndarray:
+        """record-level VerifyDDLEQProofBatch: count statements (n3-width ct1, ct2) x secpar instances (n-width x, y,
+        n3-width alpha, n2-width e, n3-width f) -> one verdict byte per instance"""
+        ok = np.zeros(count * secpar, dtype=np.uint8)
+        check(lib.pgpu_ddleq_verify(self._ctx, count, secpar, _ptr(c1), _ptr(c2), _ptr(x), _ptr(y), _ptr(al), _ptr(e), _ptr(f),
+                                    _ptr(ok)), self._ctx)
+        return ok
 
     # -- introspection -------------------------------------------------------
     def launch_count(self) -> int:
@@ -529,14 +535,20 @@ class SecretKey(PublicKey):
         c1, c2 = to_records([c.C for c in ct1s], self.w_n3), to_records([c.C for c in ct2s], self.w_n3)
         a, b = to_records(As, self.w_n), to_records(Bs, self.w_n)
         x, y = to_records(fx, self.w_n), to_records(fy, self.w_n)
+        al, e, f = self.prove_ddleq_records(count, secpar, c1, c2, a, b, x, y)
+        A, E, F = from_records(al, self.w_n3), from_records(e, self.w_n2), from_records(f, self.w_n3)
+        return [DDLEQProof([DDLEQProofInstance(fx[k], fy[k], A[k], E[k], F[k]) for k in range(i * secpar, (i + 1) * secpar)])
+                for i in range(count)]
+
+
+    def prove_ddleq_records(self, count: int, secpar: int, c1, c2, a, b, x, y):
+        """record-level ProveDDLEQBatch -> (alpha, e, f) records of count * secpar instances"""
         total = count * secpar
         al, e, f = (np.empty(total * self.w_n3, dtype=np.uint8), np.empty(total * self.w_n2, dtype=np.uint8),
                     np.empty(total * self.w_n3, dtype=np.uint8))
         check(lib.pgpu_ddleq_prove(self._ctx, count, secpar, _ptr(c1), _ptr(c2), _ptr(a), _ptr(b), _ptr(x), _ptr(y),
                                    _ptr(al), _ptr(e), _ptr(f)), self._ctx)
-        A, E, F = from_records(al, self.w_n3), from_records(e, self.w_n2), from_records(f, self.w_n3)
-        return [DDLEQProof([DDLEQProofInstance(fx[k], fy[k], A[k], E[k], F[k]) for k in range(i * secpar, (i + 1) * secpar)])
-                for i in range(count)]
+        return al, e, f
 
 
 class ThresholdPublicKey(PublicKey):

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128) prod_reduce_kernel(ProdParams P) {
     }
 }
 
-#define PGPU_PROD_SHAPES(X) X(4, 8) X(4, 16) X(8, 12) X(8, 16) X(4, 32) X(8, 24) X(16, 12)
+#define PGPU_PROD_SHAPES(X) X(4, 8) X(4, 16) X(8, 12) X(4, 24) X(8, 16) X(4, 32) X(8, 24) X(16, 12)
 
 cudaError_t prod_reduce_launch(int tpi, int limbs, const ProdParams& P, int blocks, cudaStream_t stream) {
 #define X(T, LL) if (tpi == T && limbs == LL) { prod_reduce_kernel<T, LL><<<blocks, 128, 0, stream>>>(P); return cudaGetLastError(); }

@@ -566,6 +566,15 @@ int pgpu_pdec_zkp_prove_dev(pgpu_ctx* ctx, size_t count, const void* c, const vo
     GUARD_END(ctx)
 }
 
+int pgpu_pdec_zkp_prove_given_dev(pgpu_ctx* ctx, size_t count, const void* c, const void* r, const void* dec, void* e, void* z) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && (count == 0 || (c && r && dec && e && z)), "pgpu_pdec_zkp_prove_given_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return zkp_prove_dev(ctx, count, (const uint32_t*)c, (const uint32_t*)r, (uint32_t*)dec, (uint32_t*)e, (uint32_t*)z, true);
+    GUARD_END(ctx)
+}
+
 int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m) {
     GUARD_BEGIN
     REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids), "pgpu_combine_dev: null argument");

@@ -6,22 +6,33 @@ namespace pgpu {
 namespace { thread_local std::string g_err; }
 std::string& thread_error() { return g_err; }
 
-// smallest built shape holding `limbs` limbs; override with PGPU_SHAPE_<S>="tpi,L"
-bool pick_shape(size_t limbs, Shape& out) {
+// integer-pipe shape for records of S limbs (also what the 32-bit-limb helper kernels run on)
+static bool int_shape(size_t limbs, Shape& out) {
     static const Shape defaults[] = {{32, 4, 8}, {64, 4, 16}, {96, 4, 24}, {128, 4, 32}, {192, 8, 24}};
-    for (const Shape& s : defaults) {
-        if ((size_t)s.S >= limbs) {
-            out = s;
-            char name[32];
-            snprintf(name, sizeof name, "PGPU_SHAPE_%d", s.S);
-            if (const char* e = getenv(name)) {
-                int t = 0, l = 0;
-                if (sscanf(e, "%d,%d", &t, &l) == 2 && t * l == s.S && vm_occupancy(t, l) > 0) { out.tpi = t; out.L = l; }
-            }
-            return true;
-        }
-    }
+    for (const Shape& s : defaults)
+        if ((size_t)s.S >= limbs) { out = s; return true; }
     return false;
+}
+
+// Smallest built shape holding `limbs` limbs.  Moduli of 2048 bits and more run on the FP64 pipe (52-bit limbs,
+// mont52.cuh: measured 1.09-1.17x the integer-pipe multiplier, tools/mont52_test.cu); PGPU_NO_FP64=1 keeps everything on
+// the integer pipe.  Override per width with PGPU_SHAPE_<S>="tpi,L" (integer pipe) or "tpi,L,fp64".
+bool pick_shape(size_t limbs, Shape& out) {
+    static const Shape fp64_defaults[] = {{64, 4, 10, true}, {96, 4, 15, true}, {128, 8, 10, true}, {192, 8, 15, true}};
+    static const bool no_fp64 = getenv("PGPU_NO_FP64") != nullptr;
+    if (!int_shape(limbs, out)) return false;
+    if (!no_fp64)
+        for (const Shape& s : fp64_defaults)
+            if (s.S == out.S && vm_occupancy(s) > 0) { out = s; break; }
+    char name[32];
+    snprintf(name, sizeof name, "PGPU_SHAPE_%d", out.S);
+    if (const char* e = getenv(name)) {
+        int t = 0, l = 0; char tag[8] = "";
+        const int got = sscanf(e, "%d,%d,%7s", &t, &l, tag);
+        Shape c{out.S, t, l, got == 3 && std::string(tag) == "fp64"};
+        if (got >= 2 && (c.fp64 || t * l == out.S) && vm_occupancy(c) > 0) out = c;
+    }
+    return true;
 }
 
 int fail(pgpu_ctx* ctx, int code, const std::string& msg) {
@@ -44,10 +55,12 @@ int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
     if (!N.is_odd()) return fail(ctx, PGPU_ERR_ARG, "modulus must be odd");
     if (!pick_shape(N.v.size(), m.sh)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus wider than the built kernel shapes");
     m.N = N;
-    const BigU R = BigU::pow2(32 * (size_t)m.sh.S);
+    int_shape(N.v.size(), m.sh32);
+    const BigU R = BigU::pow2((size_t)m.sh.rbits());
     m.R1 = R % N;
     m.R2 = (m.R1 * m.R1) % N;
-    m.R3 = (m.R2 * m.R1) % N;
+    m.W1 = BigU::pow2(32 * (size_t)m.sh.S) % N;
+    m.R3 = (m.R2 * m.W1) % N;              // takes the high chunk of a record split at 2^(32*S) into Montgomery form
     m.np0 = mont_np0(N.v[0]);
     CU(ctx, cudaMalloc(&m.d_mod, (size_t)m.sh.S * 4));
     CU(ctx, cudaMalloc(&m.d_kconst, (size_t)K_SLOTS * m.sh.S * 4));
@@ -58,11 +71,11 @@ int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
     if ((rc = set_kconst(ctx, m, K_R1, m.R1))) return rc;
     if ((rc = set_kconst(ctx, m, K_ONE, BigU(1)))) return rc;
     if ((rc = set_kconst(ctx, m, K_R3, m.R3))) return rc;
-    m.blocks_per_sm = vm_occupancy(m.sh.tpi, m.sh.L);
+    m.blocks_per_sm = vm_occupancy(m.sh);
     if (m.blocks_per_sm <= 0) return fail(ctx, PGPU_ERR_CUDA, "powm_vm occupancy query failed for shape");
     m.sh_items = m.sh; m.blocks_per_sm_items = m.blocks_per_sm;
-    if (m.sh.S == 96 && m.sh.tpi == 4 && !getenv("PGPU_SHAPE_96")) {      // measured: tools/ddleq_rate.py, tools/shape96.py
-        const int b = vm_occupancy(8, 12);
+    if (!m.sh.fp64 && m.sh.S == 96 && m.sh.tpi == 4 && !getenv("PGPU_SHAPE_96")) {      // measured: tools/ddleq_rate.py, tools/shape96.py
+        const int b = vm_occupancy(Shape{96, 8, 12});
         if (b > 0) { m.sh_items = Shape{96, 8, 12}; m.blocks_per_sm_items = b; }
     }
     m.ready = true;
@@ -188,12 +201,12 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed;
     P.n_groups = (uint32_t)blocks * gpb;
     { static const bool no_sqr = getenv("PGPU_NO_SQR") != nullptr; P.flags = no_sqr ? 1u : 0u; }
-    const size_t tbl_limbs = (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * m.sh.S;
+    const size_t tbl_limbs = (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * sh.tbl_limbs();
     int rc = ensure_table(ctx, tbl_limbs + (size_t)P.n_groups * m.sh.S);
     if (rc) return rc;
     P.table = ctx->d_table;
     P.dump = ctx->d_table + tbl_limbs;
-    CU(ctx, vm_launch(sh.tpi, sh.L, P, blocks, ctx->stream));
+    CU(ctx, vm_launch(sh, P, blocks, ctx->stream));
     ctx->launches++;
     return PGPU_OK;
 }
@@ -519,7 +532,7 @@ int modmul_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* a, 
 
 // out = prod in[i] mod M (Add over a batch)
 int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_t* out) {
-    const int gpb = 128 / M.sh.tpi;
+    const int gpb = 128 / M.sh32.tpi;
     const size_t max_blocks = (size_t)ctx->sms * 4;
     size_t b1 = std::min(max_blocks, (count + gpb - 1) / gpb);
     if (b1 == 0) b1 = 1;
@@ -529,20 +542,21 @@ int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_
     auto rounds = [&](size_t n, size_t blocks) { size_t G = blocks * gpb; return n == 0 ? (size_t)1 : (n + G - 1) / G; };
     // stage 1: b1 blocks -> b1 partials, each carrying R^-(gpb*rounds1 - 1)
     ProdParams P1{in, (uint32_t)count, M.d_mod, M.np0, partial};
-    CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P1, (int)b1, ctx->stream));
+    CU(ctx, prod_reduce_launch(M.sh32.tpi, M.sh32.L, P1, (int)b1, ctx->stream));
     ctx->launches++;
     uint64_t T = (uint64_t)b1 * (gpb * rounds(count, b1) - 1);
     uint32_t* last = partial;
     if (b1 > 1) {
         uint32_t* fin = partial + b1 * M.sh.S;
         ProdParams P2{partial, (uint32_t)b1, M.d_mod, M.np0, fin};
-        CU(ctx, prod_reduce_launch(M.sh.tpi, M.sh.L, P2, 1, ctx->stream));
+        CU(ctx, prod_reduce_launch(M.sh32.tpi, M.sh32.L, P2, 1, ctx->stream));
         ctx->launches++;
         T += gpb * rounds(b1, 1) - 1;
         last = fin;
     }
-    // final correction: times R^(T+1), one more Montgomery multiply
-    const BigU fix = BigU::modexp(M.R1, BigU(T + 1), M.N);
+    // final correction: the partial product carries W^-T (W = 2^(32*S), the radix of prod_reduce_kernel); one more
+    // Montgomery multiply of the exponentiation kernel (radix R) by W^T * R restores it
+    const BigU fix = (BigU::modexp(M.W1, BigU(T), M.N) * M.R1) % M.N;
     if ((rc = set_kconst(ctx, M, K_FIX, fix))) return rc;
     const std::string key = "fix:" + std::to_string(M.sh.S);
     Program* P = cached_program(ctx, key);

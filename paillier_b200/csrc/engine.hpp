@@ -20,16 +20,17 @@
 
 namespace pgpu {
 
-struct Shape { int S, tpi, L; };
+using Shape = VmShape;
 
 // kconst slots shared by every modulus
 enum : uint32_t {
-    K_R2 = 0, K_R1 = 1, K_ONE = 2, K_R3 = 3, K_NR2 = 4, K_FIX = 5,
+    K_R2 = 0, K_R1 = 1, K_ONE = 2, K_NR2 = 4, K_FIX = 5,
+    K_R3 = 3,     // W * R^2 mod N, W = 2^(32*S): second chunk of a record split at the record width -> Montgomery form
     K_NEG1 = 6,   // -1                         (Montgomery form; level-2 g^m shortcut)
     K_C1 = 7,     // n^2 / 2 mod n^3            (Montgomery form)
     K_NM = 8,     // n                          (Montgomery form)
     K_NSM = 9,    // n^s for the modulus n^(s+1) (Montgomery form; g^(-v) = g^(n^s - v))
-    K_R4 = 10,    // R^4 mod N
+    K_R4 = 10,    // W^2 * R^2 mod N: third chunk
     K_CRT = 11,   // secret-key EncryptWithR: q^-2 mod p^2 (plain) in the p^2 context, q^2 * R^2 mod n^2 in the n^2 context
     K_SLOTS = 16
 };
@@ -46,7 +47,9 @@ struct Program {
 struct ModCtx {
     bool ready = false;
     Shape sh{};
-    BigU N, R1, R2, R3;
+    BigU N, R1, R2, R3;             // R mod N, R^2 mod N, W*R^2 mod N with R the kernel's Montgomery radix, W = 2^(32*S)
+    BigU W1;                        // W mod N: the radix of the 32-bit-limb helper kernels and of records split into chunks
+    Shape sh32{};                   // integer-pipe shape of the same record width (prod_reduce_kernel)
     uint32_t np0 = 0;
     uint32_t* d_mod = nullptr;
     uint32_t* d_kconst = nullptr;   // K_SLOTS records of S limbs

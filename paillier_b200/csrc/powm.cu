@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include "mont.cuh"
+#include "mont52.cuh"
 #include "vm.h"
 #include "launch.h"
 
@@ -46,6 +47,53 @@ __device__ __forceinline__ void store_vec(uint32_t* __restrict__ p, const uint32
     }
 }
 
+
+// ---- the two multipliers behind one interpreter -----------------------------------------------------------------
+// Vm32: 32-bit limbs on the integer pipe (mont.cuh); registers, table entries and records share one format.
+// Mont52 (mont52.cuh): 52-bit limbs as doubles on the FP64 pipe; records are converted when they are loaded or stored.
+// Pointers handed to load_rec / store_rec / load_full are record starts, to load_tbl / store_tbl the group's slot.
+template <int TPI, int L>
+struct Vm32 : Mont<TPI, L, SqrShape<TPI, L>::value> {
+    using Base = Mont<TPI, L, SqrShape<TPI, L>::value>;
+    using elem = uint32_t;
+    static constexpr int TPI_ = TPI, L_ = L;
+    static constexpr int S32 = TPI * L;
+    static constexpr int TBL = L;
+
+    __device__ __forceinline__ void load_full(uint32_t (&x)[L], const uint32_t* __restrict__ p) const { load_vec<L>(x, p + this->t * L); }
+    __device__ __forceinline__ void store_full(uint32_t* __restrict__ p, const uint32_t (&x)[L]) const { store_vec<L>(p + this->t * L, x); }
+    // records narrower than the modulus read as zero-extended; full records stream in 128-bit vectors
+    __device__ __forceinline__ void load_rec(uint32_t (&x)[L], const uint32_t* __restrict__ p, uint32_t lim) const {
+        if (lim == (uint32_t)S32 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) { load_full(x, p); return; }
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            const uint32_t idx = this->t * L + k;
+            x[k] = idx < lim ? __ldg(p + idx) : 0u;
+        }
+    }
+    __device__ __forceinline__ void store_rec(uint32_t* __restrict__ p, const uint32_t (&x)[L], uint32_t lim) const {
+        if (lim == (uint32_t)S32 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) { store_full(p, x); return; }
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            const uint32_t idx = this->t * L + k;
+            if (idx < lim) p[idx] = x[k];
+        }
+    }
+    __device__ __forceinline__ void load_tbl(uint32_t (&x)[L], const uint32_t* __restrict__ p) const { load_vec<L>(x, p + this->t * L); }
+    __device__ __forceinline__ void store_tbl(uint32_t* __restrict__ p, const uint32_t (&x)[L]) const { store_vec<L>(p + this->t * L, x); }
+};
+
+template <int TPI, int L, int S32_>
+struct Vm52 : Mont52<TPI, L, S32_> {
+    using Base = Mont52<TPI, L, S32_>;
+    static constexpr bool HAS_SQR = false;
+    static constexpr int TPI_ = TPI, L_ = L;
+    __device__ __forceinline__ void load_full(double (&x)[L], const uint32_t* __restrict__ p) const { this->load_rec(x, p, S32_); }
+    __device__ __forceinline__ void store_full(uint32_t* __restrict__ p, const double (&x)[L]) const { this->store_rec(p, x, S32_); }
+    __device__ __forceinline__ void load_tbl(double (&x)[L], const uint32_t* __restrict__ p) const { Base::load_tbl(x, p + this->t * Base::TBL); }
+    __device__ __forceinline__ void store_tbl(uint32_t* __restrict__ p, const double (&x)[L]) const { Base::store_tbl(p + this->t * Base::TBL, x); }
+};
+
 // bits [pos, pos+w) of a little-endian limb array
 __device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uint32_t nbits, uint32_t pos, uint32_t w) {
     if (pos >= nbits) return 0;
@@ -57,24 +105,26 @@ __device__ __forceinline__ uint32_t exp_bits(const uint32_t* __restrict__ e, uin
     return r;
 }
 
-template <int TPI, int L>
-__global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 : 1)) powm_vm(const VmParams P) {
-    constexpr int S = TPI * L;
-    using MontT = Mont<TPI, L, SqrShape<TPI, L>::value>;
-    MontT M;
+template <class B>
+__device__ __forceinline__ void vm_run(const VmParams& P) {
+    constexpr int L = B::L_;
+    constexpr int TPI = B::TPI_;
+    constexpr int S = B::S32;                  // 32-bit limbs of a record
+    constexpr int TS = TPI * B::TBL;           // 32-bit words of one table entry of a group
+    using elem = typename B::elem;
+    B M;
     const uint32_t n_groups = P.n_groups;
     const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / TPI;
     const uint32_t n_inst = P.n_items;
     const uint32_t rounds = (n_inst + n_groups - 1) / n_groups;
-    const int lane_t = (threadIdx.x & 31) & (TPI - 1);
-    uint32_t* const tbl = P.table + (size_t)group * S + lane_t * L;
-    const size_t tbl_entry_stride = (size_t)n_groups * S;
+    uint32_t* const tbl = P.table + (size_t)group * TS;
+    const size_t tbl_entry_stride = (size_t)n_groups * TS;
     M.init(P.mod, P.np0);
-    if constexpr (MontT::HAS_SQR) {
+    if constexpr (B::HAS_SQR) {
         extern __shared__ uint4 vm_smem[];
-        M.init_sqr(vm_smem + (threadIdx.x >> 5) * (MontT::SQR_ROWS * 32));
+        M.init_sqr(vm_smem + (threadIdx.x >> 5) * (B::SQR_ROWS * 32));
     }
-    const uint32_t* const kc = P.kconst + lane_t * L;
+    const uint32_t* const kc = P.kconst;
     uint32_t* const dump = P.dump + (size_t)group * S;
 
     for (uint32_t rd = 0; rd < rounds; ++rd) {
@@ -82,7 +132,7 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
         const bool active = item < n_inst;      // whole warps stay in lock-step; idle groups redo item 0
         if (!active) item = 0;
 
-        uint32_t x[L], y[L], y2[L];
+        elem x[L], y[L];
 #pragma unroll
         for (int k = 0; k < L; ++k) x[k] = 0;
 
@@ -92,86 +142,66 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
             if (code == OP_END) break;
             uint32_t nsq = 0, nmul = 0, bkt = 0xffffffffu;
             switch (code) {
-                case OP_LDI: {
-                    const uint32_t* p = P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg];
-                    const uint32_t lim = P.in_limbs[arg];
-#pragma unroll
-                    for (int k = 0; k < L; ++k) {
-                        const uint32_t idx = lane_t * L + k;
-                        x[k] = idx < lim ? __ldg(p + idx) : 0u;
-                    }
-                } break;
-                case OP_LDC: load_vec<L>(x, kc + (size_t)arg * S); break;
-                case OP_LDT: load_vec<L>(x, tbl + arg * tbl_entry_stride); break;
-                case OP_STT: store_vec<L>(tbl + arg * tbl_entry_stride, x); break;
-                case OP_STO: {
+                case OP_LDI: M.load_rec(x, P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg], P.in_limbs[arg]); break;
+                case OP_LDC: M.load_full(x, kc + (size_t)arg * S); break;
+                case OP_LDT: M.load_tbl(x, tbl + arg * tbl_entry_stride); break;
+                case OP_STT: M.store_tbl(tbl + arg * tbl_entry_stride, x); break;
+                case OP_STO:
                     // idle groups (they redo item 0 in lock step) store into their dump record: no branch on `active`,
                     // which would make the compiler clone the whole interpreter loop
-                    uint32_t* p = active ? P.out[arg] + (size_t)item * P.out_stride[arg] : dump;
-                    const uint32_t lim = P.out_limbs[arg];
-#pragma unroll
-                    for (int k = 0; k < L; ++k) {
-                        const uint32_t idx = lane_t * L + k;
-                        if (idx < lim) p[idx] = x[k];
-                    }
-                } break;
+                    M.store_rec(active ? P.out[arg] + (size_t)item * P.out_stride[arg] : dump, x, P.out_limbs[arg]);
+                    break;
                 case OP_SQR: nsq = arg; break;
-                case OP_MULT: load_vec<L>(y, tbl + arg * tbl_entry_stride); nmul = 1; break;
-                case OP_MULC: load_vec<L>(y, kc + (size_t)arg * S); nmul = 1; break;
-                case OP_MULI: {
-                    const uint32_t* p = P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg];
-                    const uint32_t lim = P.in_limbs[arg];
-#pragma unroll
-                    for (int k = 0; k < L; ++k) {
-                        const uint32_t idx = lane_t * L + k;
-                        y[k] = idx < lim ? __ldg(p + idx) : 0u;
-                    }
+                case OP_MULT: M.load_tbl(y, tbl + arg * tbl_entry_stride); nmul = 1; break;
+                case OP_MULC: M.load_full(y, kc + (size_t)arg * S); nmul = 1; break;
+                case OP_MULI:
+                    M.load_rec(y, P.in[arg] + (size_t)(item / P.in_div[arg]) * P.in_stride[arg], P.in_limbs[arg]);
                     nmul = 1;
-                } break;
-                case OP_ADDT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.add(x, x, y); break;
-                case OP_ADDC: load_vec<L>(y, kc + (size_t)arg * S); M.add(x, x, y); break;
+                    break;
+                case OP_ADDT: M.load_tbl(y, tbl + arg * tbl_entry_stride); M.add(x, x, y); break;
+                case OP_ADDC: M.load_full(y, kc + (size_t)arg * S); M.add(x, x, y); break;
                 case OP_WIN: {
                     const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, tbase = arg >> 24;
                     const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w);
-                    load_vec<L>(y, tbl + (tbase + idx) * tbl_entry_stride);
+                    M.load_tbl(y, tbl + (tbase + idx) * tbl_entry_stride);
                     nsq = w; nmul = 1;
                 } break;
                 case OP_FIXW: {
                     const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu;
                     const uint32_t idx = exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w);
-                    load_vec<L>(y, P.fixed + ((size_t)(pos / w) * (1u << w) + idx) * S + lane_t * L);
+                    M.load_full(y, P.fixed + ((size_t)(pos / w) * (1u << w) + idx) * S);
                     nmul = 1;
                 } break;
                 case OP_LDIO:
-                    load_vec<L>(x, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S + lane_t * L);
+                    M.load_full(x, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S);
                     break;
                 case OP_MULIO:
-                    load_vec<L>(y, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S + lane_t * L);
+                    M.load_full(y, P.in[arg & 3u] + (size_t)item * P.in_stride[arg & 3u] + (size_t)(arg >> 2) * S);
                     nmul = 1;
                     break;
                 case OP_STOO: {
                     const uint32_t a = arg & 1u, off = arg >> 2;
-                    uint32_t* p = active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump;
-                    store_vec<L>(p + lane_t * L, x);
+                    M.store_full(active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump, x);
                 } break;
                 case OP_BKT: {
                     const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu;
                     // idle groups must not touch the buckets: they multiply into the spare entry 2^w
                     bkt = active ? exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w) : (1u << w);
-                    load_vec<L>(y, tbl + bkt * tbl_entry_stride);
+                    M.load_tbl(y, tbl + bkt * tbl_entry_stride);
                     nmul = 1;
                 } break;
-                case OP_SUBT: load_vec<L>(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
+                case OP_SUBT: M.load_tbl(y, tbl + arg * tbl_entry_stride); M.sub(x, x, y); break;
                 case OP_SQMT: {
                     const uint32_t idx = arg >> 12;
-                    load_vec<L>(y, tbl + idx * tbl_entry_stride);
+                    M.load_tbl(y, tbl + idx * tbl_entry_stride);
                     nsq = arg & 0xfffu; nmul = 1;
                 } break;
                 default: break;
             }
             // the single Montgomery multiplier of the instruction stream
-            if constexpr (MontT::HAS_SQR) {
+            if constexpr (B::HAS_SQR) {
                 if (P.flags & 1u) {
+                    elem y2[L];
 #pragma unroll 1
                     for (uint32_t i = nsq; i > 0; --i) {
 #pragma unroll
@@ -186,15 +216,28 @@ __global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 :
             } else {
                 for (uint32_t i = nsq + nmul; i > 0; --i) {
                     const bool sq = i > nmul;
-                    uint32_t b[L];
+                    elem b[L];
 #pragma unroll
                     for (int k = 0; k < L; ++k) b[k] = sq ? x[k] : y[k];
                     M.mul(x, x, b);
                 }
             }
-            if (bkt != 0xffffffffu) store_vec<L>(tbl + bkt * tbl_entry_stride, x);
+            if (bkt != 0xffffffffu) M.store_tbl(tbl + bkt * tbl_entry_stride, x);
         }
     }
+}
+
+template <int TPI, int L>
+__global__ void __launch_bounds__(VM_BLOCK_THREADS, (L <= 16 ? 4 : L <= 32 ? 2 : 1)) powm_vm(const VmParams P) {
+    vm_run<Vm32<TPI, L>>(P);
+}
+
+// resident blocks per SM the FP64 shapes are compiled for (register budget 65536 / (128 * blocks))
+constexpr int vm52_min_blocks(int L) { return L <= 5 ? 6 : L <= 8 ? 4 : L <= 10 ? 3 : 2; }
+
+template <int TPI, int L, int S32>
+__global__ void __launch_bounds__(VM_BLOCK_THREADS, vm52_min_blocks(L)) powm_vm52(const VmParams P) {
+    vm_run<Vm52<TPI, L, S32>>(P);
 }
 
 template <int TPI, int L>
@@ -234,6 +277,19 @@ static int occupancy_t() {
     return nb;
 }
 
+template <int TPI, int L, int S32>
+static cudaError_t launch52_t(const VmParams& P, int blocks, cudaStream_t stream) {
+    powm_vm52<TPI, L, S32><<<blocks, VM_BLOCK_THREADS, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <int TPI, int L, int S32>
+static int occupancy52_t() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, powm_vm52<TPI, L, S32>, VM_BLOCK_THREADS, 0);
+    return nb;
+}
+
 #define PGPU_FOR_EACH_SHAPE(X) \
     X(2, 16) X(4, 8)           \
     X(4, 16) X(8, 8)           \
@@ -241,15 +297,35 @@ static int occupancy_t() {
     X(8, 16) X(16, 8) X(4, 32) X(32, 4) \
     X(8, 24) X(16, 12) X(32, 6)
 
-cudaError_t vm_launch(int tpi, int limbs, const VmParams& P, int blocks, cudaStream_t stream) {
-#define X(T, LL) if (tpi == T && limbs == LL) return launch_t<T, LL>(P, blocks, stream);
+// FP64-pipe shapes (TPI, L, 32-bit record limbs): 52*TPI*L >= 32*S32 + 2
+#define PGPU_FOR_EACH_SHAPE52(X) \
+    X(4, 5, 32)                  \
+    X(4, 10, 64) X(8, 5, 64)     \
+    X(4, 15, 96) X(8, 8, 96)     \
+    X(8, 10, 128)                \
+    X(8, 15, 192) X(16, 8, 192)
+
+cudaError_t vm_launch(const VmShape& sh, const VmParams& P, int blocks, cudaStream_t stream) {
+    if (sh.fp64) {
+#define X(T, LL, SS) if (sh.tpi == T && sh.L == LL && sh.S == SS) return launch52_t<T, LL, SS>(P, blocks, stream);
+        PGPU_FOR_EACH_SHAPE52(X)
+#undef X
+        return cudaErrorInvalidValue;
+    }
+#define X(T, LL) if (sh.tpi == T && sh.L == LL && sh.S == T * LL) return launch_t<T, LL>(P, blocks, stream);
     PGPU_FOR_EACH_SHAPE(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int vm_occupancy(int tpi, int limbs) {
-#define X(T, LL) if (tpi == T && limbs == LL) return occupancy_t<T, LL>();
+int vm_occupancy(const VmShape& sh) {
+    if (sh.fp64) {
+#define X(T, LL, SS) if (sh.tpi == T && sh.L == LL && sh.S == SS) return occupancy52_t<T, LL, SS>();
+        PGPU_FOR_EACH_SHAPE52(X)
+#undef X
+        return 0;
+    }
+#define X(T, LL) if (sh.tpi == T && sh.L == LL && sh.S == T * LL) return occupancy_t<T, LL>();
     PGPU_FOR_EACH_SHAPE(X)
 #undef X
     return 0;

@@ -208,3 +208,95 @@ def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, wit
     stream.synchronize()
     check(lib.pgpu_ctx_set_stream(tsk._ctx, None), tsk._ctx)
     return res
+
+
+def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: int, zkp_r=None, keep=None):
+    """BASELINE config 4 with a fixed number of share-holders spread over `world` GPUs: `tsks` = this rank's
+    ThresholdSecretKeys (share ids rank*k+1 .. rank*k+k, k = len(tsks), the same k on every rank; 8 shares on 8 GPUs = one
+    share-holder per GPU).  Every share-holder computes PartialDecrypt (thresholdkey.go:192-201) and, with `zkp_r` (one
+    device tensor of count n2-width r records per local share), the proof (thresholdkey.go:225-255) for ALL `count`
+    ciphertexts; one all-gather per field lands [share][ciphertext]; this rank then verifies every share's proofs of
+    its ciphertext slice (VerifyProof, thresholdkey.go:278-311) and combines the slice from the shares that verified
+    (CombinePartialDecryptionsZKP, thresholdkey.go:164-172).
+
+    Returns (plaintext slice tensor, (lo, hi), phases) with phases = device milliseconds of this rank per phase
+    {"pdec", "prove", "all_gather", "verify", "combine"} (CUDA events on the stream the work is enqueued on).
+    keep: optional dict that receives the gathered buffers ("dec", "e", "z") for parity checks."""
+    import torch
+    from ._lib import check, lib
+    k = len(tsks)
+    t0 = tsks[0]
+    w2, wn, wz = t0.w_n2, t0.w_n, t0.w_z
+    dev = c_dev.device
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    stream = torch.cuda.Stream(dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    for t in tsks:
+        check(lib.pgpu_ctx_set_stream(t._ctx, C.c_void_p(stream.cuda_stream)), t._ctx)
+    ev = {name: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for name in ("pdec", "prove", "all_gather", "verify", "combine")}
+    shares = world * k
+    lo, hi = shard_range(count, world, rank)
+    n = hi - lo
+    try:
+        with torch.cuda.stream(stream):
+            dec = torch.empty(k * count * w2, dtype=torch.uint8, device=dev)
+            ev["pdec"][0].record(stream)
+            for j, t in enumerate(tsks):
+                check(lib.pgpu_partial_decrypt_dev(t._ctx, count, vp(c_dev), vp(dec[j * count * w2:])), t._ctx)
+            ev["pdec"][1].record(stream)
+            e = z = None
+            ev["prove"][0].record(stream)
+            if zkp_r is not None:
+                e = torch.empty(k * count * 32, dtype=torch.uint8, device=dev)
+                z = torch.empty(k * count * wz, dtype=torch.uint8, device=dev)
+                for j, t in enumerate(tsks):
+                    check(lib.pgpu_pdec_zkp_prove_given_dev(t._ctx, count, vp(c_dev), vp(zkp_r[j]), vp(dec[j * count * w2:]),
+                                                            vp(e[j * count * 32:]), vp(z[j * count * wz:])), t._ctx)
+            ev["prove"][1].record(stream)
+            # ---- the one exchange of the path: [share][ciphertext] on every rank
+            ev["all_gather"][0].record(stream)
+            if world > 1:
+                g_dec = torch.empty(shares * count * w2, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(g_dec, dec)
+                if zkp_r is not None:
+                    g_e = torch.empty(shares * count * 32, dtype=torch.uint8, device=dev)
+                    g_z = torch.empty(shares * count * wz, dtype=torch.uint8, device=dev)
+                    dist.all_gather_into_tensor(g_e, e)
+                    dist.all_gather_into_tensor(g_z, z)
+            else:
+                g_dec, g_e, g_z = dec, e, z
+            ev["all_gather"][1].record(stream)
+            # ---- VerifyProof of every share for this rank's ciphertext slice
+            ids = list(range(1, shares + 1))
+            ev["verify"][0].record(stream)
+            if zkp_r is not None and n > 0:
+                rows = lambda buf, w: torch.cat([buf[(s * count + lo) * w:(s * count + hi) * w] for s in range(shares)])
+                ok = torch.zeros(shares * n, dtype=torch.uint8, device=dev)
+                idarr = (C.c_int * shares)(*ids)
+                check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(c_dev[lo * w2:hi * w2].repeat(shares)),
+                                                         vp(rows(g_dec, w2)), vp(rows(g_e, 32)), vp(rows(g_z, wz)), vp(ok)), t0._ctx)
+                verdict = ok.view(shares, n).all(dim=1)
+            ev["verify"][1].record(stream)
+            if zkp_r is not None and n > 0:
+                ids = [s + 1 for s in range(shares) if bool(verdict[s].item())]
+            # ---- Combine the slice in place out of the gathered buffer
+            out = torch.empty(max(n, 1) * wn, dtype=torch.uint8, device=dev)
+            ev["combine"][0].record(stream)
+            if n > 0:
+                if ids == list(range(1, shares + 1)):
+                    base, stride = g_dec[lo * w2:], count
+                else:
+                    picked = [g_dec[((i - 1) * count + lo) * w2:((i - 1) * count + hi) * w2] for i in ids]
+                    base, stride = (torch.cat(picked) if picked else g_dec[:0]), n
+                idarr = (C.c_int * max(len(ids), 1))(*ids)
+                check(lib.pgpu_combine_strided_dev(t0._ctx, n, len(ids), idarr, vp(base), max(stride, n), vp(out)), t0._ctx)
+            ev["combine"][1].record(stream)
+        stream.synchronize()
+        if keep is not None:
+            keep["dec"], keep["e"], keep["z"], keep["ids"] = g_dec, g_e if zkp_r is not None else None, g_z if zkp_r is not None else None, ids
+    finally:
+        for t in tsks:
+            check(lib.pgpu_ctx_set_stream(t._ctx, None), t._ctx)
+    phases = {name: a.elapsed_time(b) for name, (a, b) in ev.items()}
+    return out[:n * wn], (lo, hi), phases
