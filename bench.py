@@ -9,8 +9,12 @@ One "step" = one pass of the hot path over one batch: EncryptWithR over C items,
 ciphertexts.  `value` = items through the whole step per second, summed over ranks, inputs resident in HBM.
 `e2e` = the same step through the host-buffer C-ABI calls (pgpu_encrypt_with_r / pgpu_decrypt) with pinned
 host buffers, H2D and D2H copies inside the timed region.  `breakdown` carries the headline enc/s, dec/s and
-partial-dec/s separately.  `--impl reference` times the libgmp restatement of the reference's call sequence
-(oracle/gmp_ref.c: a stand-in for the Go package, which cannot be built in this image) on all host cores.
+partial-dec/s separately; `strong` is one 2^20 batch split over the N ranks (configs[1]'s "then sharded across 2/4/8");
+`config4` is BASELINE configs[3] (3072-bit threshold key, 8 shares / threshold 5, PartialDecrypt + proofs for every
+ciphertext, NCCL all-gather, proof verification and Combine of each rank's slice) with device time per phase;
+`cpu_baselines` times the libgmp call sequences of the other rows on the host cores.  `--impl reference` times the libgmp
+restatement of the reference's call sequence (oracle/gmp_ref.c: a stand-in for the Go package, which cannot be built in
+this image) on all host cores.
 """
 from __future__ import annotations
 
@@ -29,6 +33,18 @@ sys.path.insert(0, ROOT)
 METRIC = "2048-bit Paillier EncryptWithR + CRT Decrypt items/s"
 UNIT = "items/s"
 WORKLOAD = "config[1]: 2048-bit n, EncryptWithR (seeded r) + CRT Decrypt over a batch, sharded across GPUs"
+
+
+def fp64_peak() -> dict | None:
+    """Measured DFMA issue rate of this GPU (tools/dfma_peak.cu)"""
+    exe = os.path.join(ROOT, "tools", "dfma_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120, check=True).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception:
+        return None
 
 
 def mont_macs(S: int, n_sqr: int, n_mul: int) -> float:
@@ -115,7 +131,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (libgmp u64)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "key": "tests/golden/keys.json:paillier_2048", "items_per_step": sample},
+        "config": {"workload": WORKLOAD, "key": "tests/golden/keys.json:paillier_2048", "items_per_step": sample,
+                   "note": "a bounded sample per step (the B200 arm runs 2^20 items per GPU per step): items/s is size-independent on the CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} items/step: libgmp mpz_powm call sequence of paillier.go:213-216 and :296-300 "
                                    "(no g=n+1 shortcut, no CRT); stand-in for the Go package (no Go toolchain in the image)"},
@@ -138,6 +155,141 @@ def imad_peak() -> dict | None:
         return None
 
 
+def config4_leg(args, dist, rank, world, local, dev, barrier, max_over_ranks):
+    """BASELINE configs[3]: 3072-bit n threshold key, 8 shares / threshold 5.  The 8 share-holders are spread over the N
+    GPUs (8/N per GPU; one per GPU at N = 8).  Every share-holder computes PartialDecrypt (thresholdkey.go:192-201) and the
+    proof (thresholdkey.go:225-255) for ALL ciphertexts, one NCCL all-gather per field lands [share][ciphertext], every rank
+    verifies the 8 proofs of its ciphertext slice (:278-311) and combines it (:149-172).  Timed on the device, max over ranks."""
+    import random
+    import numpy as np
+    import torch
+    from paillier_b200 import synth
+    from paillier_b200.keygen import ThresholdKeyGenerator
+    from paillier_b200.multi import gpu_threshold_round_shares, shard_range
+
+    l, w = 8, 5
+    k = l // world
+    tp3, tq3 = synth.load_key("threshold_3072")
+    n3 = tp3 * tq3
+    keys = ThresholdKeyGenerator(3072, l, w, rng=random.Random(synth.SEED)).with_safe_primes(tp3, tq3).GenerateKeys(device=local)
+    mine = keys[rank * k:(rank + 1) * k]
+    for t in keys:
+        if t not in mine:
+            t.close()
+    t0 = mine[0]
+    count = args.c4_count or min(1 << 18, (1 << 15) * world)
+    w_n, w2 = t0.w_n, t0.w_n2
+    # the same seeded ciphertext batch on every rank (valid ciphertexts: EncryptWithR of seeded plaintexts)
+    m = synth.plaintexts(count, n3, w_n, synth.SEED + 4)
+    c_dev = torch.from_numpy(t0.encrypt_with_r_records(m, synth.randomness(count, n3, w_n, synth.SEED + 4))).to(dev)
+    zr = [torch.from_numpy(synth.random_records(count, w2, 2 * n3.bit_length() - 2, synth.SEED + 4, stream=70 + t.ID)).to(dev) for t in mine]
+    d = dist if world > 1 else None
+    small = min(count, 256)
+    gpu_threshold_round_shares(d, mine, c_dev[:small * w2], small, world, rank, [z[:small * w2] for z in zr])        # warm-up: programs, tables
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    keep = {}
+    plain, (lo, hi), phases = gpu_threshold_round_shares(d, mine, c_dev, count, world, rank, zr, keep=keep)
+    e1.record(torch.cuda.current_stream(dev))
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ok = bool(np.array_equal(plain.cpu().numpy(), m[lo * w_n:hi * w_n]))
+    bad = max_over_ranks(0.0 if ok else 1.0)
+    ph = {name: max_over_ranks(v) for name, v in phases.items()}
+    out = None
+    if rank == 0:
+        # parity of a slice of share-holder 1's output against the libgmp call sequence (thresholdkey.go:192-255)
+        from oracle import gmp_ref as G
+        ns = min(count, 32)
+        cs = c_dev[:ns * w2].cpu().numpy()
+        rs = zr[0][:ns * w2].cpu().numpy()
+        rd, re_, rz = G.pdec_zkp(n3, t0.Share, l, t0.VerificationKey, cs, rs, w2, t0.w_z)
+        par = (np.array_equal(rd, keep["dec"][:ns * w2].cpu().numpy()) and np.array_equal(re_, keep["e"][:ns * 32].cpu().numpy())
+               and np.array_equal(rz, keep["z"][:ns * t0.w_z].cpu().numpy()))
+        S3, q3, m3 = t0.program_cost(2)
+        out = {
+            "workload": "config[3]: 3072-bit n threshold key, 8 shares (threshold 5) on %d GPU(s), %d per GPU; PartialDecrypt + proof for "
+                        "every ciphertext, all-gather, VerifyProof x 8 and Combine of each rank's slice" % (world, k),
+            "ciphertexts": count, "ciphertexts_note": "2^18 per share-holder at 8 GPUs; min(2^18, 2^15 * N) otherwise so that the leg fits the bench budget",
+            "ms": total_ms, "ciphertexts_per_s": count / (total_ms * 1e-3), "partial_decryptions_per_s": l * count / (total_ms * 1e-3),
+            "phases_ms": ph, "all_gather_share_of_step": ph["all_gather"] / total_ms if total_ms else None,
+            "all_gather_bytes_per_gpu": {"sent": k * count * (w2 + 32 + t0.w_z), "received": l * count * (w2 + 32 + t0.w_z)},
+            "shares_verified": len(keep.get("ids", [])), "all_plaintexts_recovered": bad == 0.0,
+            "oracle_parity": {"items": ns, "fields": "c_i, E, Z of share-holder 1 against oracle/gmp_ref.c", "equal": bool(par)},
+            "pdec_program": {"limbs": S3, "sqr": q3, "mul": m3, "mac32_per_item": mont_macs(S3, q3, m3)},
+            "kernel": t0.kernel_shape(1),
+        }
+        assert par, "config 4: partial decryption / proof differs from the libgmp oracle"
+    assert bad == 0.0, "config 4: recovered plaintexts differ from the inputs"
+    for t in mine:
+        t.close()
+    return out
+
+
+def cpu_baselines_leg(sk, n, p, q, w_n, w_n2, c_host_np, extras_keep, breakdown):
+    """libgmp call sequences of the other rows (oracle/gmp_ref.c), all host cores, bounded samples; each entry doubles as a
+    bit-exact check of the GPU result where the GPU result is at hand."""
+    import random
+    import numpy as np
+    from oracle import gmp_ref as G
+    from paillier_b200 import synth
+    cores = G.cores()
+    out = {"cores": cores, "kind": "port", "note": "libgmp call sequence of the reference per row, one thread per core; samples sized for 1-4 s each"}
+    # PartialDecrypt 2048 / 3072 (thresholdkey.go:192-201)
+    for bits, ns in ((2048, 8 * cores), (3072, 4 * cores)):
+        tp, tq = synth.load_key(f"threshold_{bits}")
+        nn = tp * tq
+        wn2 = {2048: 512, 3072: 768}[bits]
+        share = random.Random(bits).randrange(nn * ((tp - 1) // 2) * ((tq - 1) // 2))
+        cs = synth.random_records(ns, wn2, 2 * nn.bit_length() - 2, stream=81)
+        t0 = time.perf_counter()
+        G.partial_decrypt(nn, share, 8, cs, wn2, threads=cores)
+        out[f"pdec{bits}_per_s"] = ns / (time.perf_counter() - t0)
+        # ZKP prove + verify at the same size (thresholdkey.go:225-311)
+        v = pow(random.Random(bits + 1).randrange(2, nn * nn), 2, nn * nn)
+        vi = pow(v, 40320 * share, nn * nn)
+        nz = max(cores, ns // 4)
+        rs = synth.random_records(nz, wn2, 2 * nn.bit_length() - 2, stream=82)
+        wz = wn2 + 64
+        t0 = time.perf_counter()
+        dec, e, z = G.pdec_zkp(nn, share, 8, v, cs[:nz * wn2], rs, wn2, wz, threads=cores)
+        t1 = time.perf_counter()
+        okv = G.zkp_verify(nn, v, vi, cs[:nz * wn2], dec, e, z, wn2, wz, threads=cores)
+        t2 = time.perf_counter()
+        assert bool(okv.all()), "libgmp oracle: ZKP verification rejected its own proof"
+        out[f"pdec_zkp_prove{bits}_per_s"] = nz / (t1 - t0)
+        out[f"pdec_zkp_verify{bits}_per_s"] = nz / (t2 - t1)
+    # encrypted dot product with 64-bit scalars (operations.go:11-64): ConstMult per term + Add fold
+    nd = 256 * cores
+    ks = synth.scalars_u64(nd)
+    t0 = time.perf_counter()
+    ref_dot = G.dot_u64(n * n, c_host_np[:nd * w_n2], w_n2, ks, threads=cores)
+    out["dot_u64_terms_per_s"] = nd / (time.perf_counter() - t0)
+    out["dot_u64_sample"] = nd
+    # DDLEQ verification (ddleq.go:129-153) of the GPU's own proofs: baseline and parity in one
+    if "ddleq" in extras_keep:
+        dn, dsecpar, c1r, c2r, xr, yr, al_r, e_r, f_r = extras_keep["ddleq"]
+        ns = max(1, min(dn, 2 * cores // dsecpar or 1))
+        w3 = sk.w_n3
+        t0 = time.perf_counter()
+        okr = G.ddleq_verify(n, dsecpar, c1r[:ns * w3], c2r[:ns * w3], xr[:ns * dsecpar * w_n], yr[:ns * dsecpar * w_n], al_r[:ns * dsecpar * w3],
+                             e_r[:ns * dsecpar * w_n2], f_r[:ns * dsecpar * w3], w_n, w_n2, w3, threads=cores)
+        out["ddleq_verify_instances_per_s"] = ns * dsecpar / (time.perf_counter() - t0)
+        assert bool(okr.all()), "libgmp oracle rejected a DDLEQ proof made on the GPU"
+    # safe-prime candidates (safe_prime.go:170-263): same byte strings as the GPU leg, decisions compared
+    if "safe_prime" in extras_keep:
+        rawb, gpu_ok = extras_keep["safe_prime"]
+        nbc = (1024 - 1 + 7) // 8
+        ns = 2048 * cores
+        t0 = time.perf_counter()
+        okc = G.safe_prime_scan(1024, rawb[:ns * nbc].tobytes(), threads=cores)
+        out["safe_prime_candidates_per_s"] = ns / (time.perf_counter() - t0)
+        assert np.array_equal(okc, gpu_ok[:ns]), "safe-prime decisions differ between the GPU and the libgmp oracle"
+    return out, ref_dot
+
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,6 +300,9 @@ def main() -> None:
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="items of the cpu_baseline sample (default 48 per core)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / partial-decrypt extras")
+    ap.add_argument("--c4-count", type=int, default=0, help="config 4: ciphertexts per share-holder (default min(2^18, 2^15 * N))")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--strong-count", type=int, default=1 << 20, help="items of the strong-scaling batch (split over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -284,6 +439,8 @@ def main() -> None:
                  "enc_program": {"limbs": S, "sqr": n_sqr, "mul": n_mul, "mac32_per_item": enc_macs},
                  "dec_program": {"limbs": Sd, "sqr": d_sqr, "mul": d_mul, "mac32_per_item": dec_macs}}
 
+    extras_keep = {}
+    sk_resident = sk.kernel_shape(1)["resident_groups"]
     if not args.no_extras:
         # EncryptWithR by the key holder (r^n over p^2 and q^2, pgpu_encrypt_with_r_sk): same ciphertexts, outside the timed steps
         c2_dev = torch.empty_like(c_dev)
@@ -444,44 +601,102 @@ def main() -> None:
         assert torch.equal(l2c_sk, l2c), "level 2: secret-key EncryptWithRAtLevel differs from the public-key path"
         breakdown["level2_enc_sk_e2e_per_s"] = world * lcount / max_over_ranks(t1 - t0)
         del l2c_sk
-        # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI
+        # DDLEQ (ddleq.go): prove + verify, `dsecpar` instances per statement, through the host-buffer ABI on records
+        # (marshalling of Python integers stays outside the timed region); device time of the kernels beside it
         if rank == 0:
-            from paillier_b200.api import ENC_LEVEL_TWO
+            from paillier_b200.api import ENC_LEVEL_TWO, to_records
             dn, dsecpar = 2048, 8
             ints = lambda a, w: [int.from_bytes(a[i * w:(i + 1) * w].tobytes(), "little") for i in range(len(a) // w)]
-            rr = ints(synth.randomness(dn * (4 + 2 * dsecpar), n, w_n, seed + 7), w_n)
+            rr_rec = synth.randomness(dn * (4 + 2 * dsecpar), n, w_n, seed + 7)
+            rr = ints(rr_rec, w_n)
             inner = sk.EncryptWithRBatch(ints(synth.plaintexts(dn, n, w_n, seed + 7), w_n), rr[:dn])
             ct1 = sk.EncryptWithRAtLevelBatch([c.C for c in inner], rr[dn:2 * dn], ENC_LEVEL_TWO)
             As, Bs = rr[2 * dn:3 * dn], rr[3 * dn:4 * dn]
             ct2 = sk.NestedRandomizeWithBatch(ct1, As, Bs)
-            xs = [rr[4 * dn + i * dsecpar:4 * dn + (i + 1) * dsecpar] for i in range(dn)]
-            ys = [rr[(4 + dsecpar) * dn + i * dsecpar:(4 + dsecpar) * dn + (i + 1) * dsecpar] for i in range(dn)]
-            sk.ProveDDLEQBatch(dsecpar, ct1[:2], ct2[:2], As[:2], Bs[:2], xs[:2], ys[:2])
+            c1r, c2r = to_records([c.C for c in ct1], sk.w_n3), to_records([c.C for c in ct2], sk.w_n3)
+            ar, br = rr_rec[2 * dn * w_n:3 * dn * w_n], rr_rec[3 * dn * w_n:4 * dn * w_n]
+            xr = rr_rec[4 * dn * w_n:(4 + dsecpar) * dn * w_n]
+            yr = rr_rec[(4 + dsecpar) * dn * w_n:(4 + 2 * dsecpar) * dn * w_n]
+            sk.prove_ddleq_records(2, dsecpar, c1r[:2 * sk.w_n3], c2r[:2 * sk.w_n3], ar[:2 * w_n], br[:2 * w_n], xr[:2 * dsecpar * w_n], yr[:2 * dsecpar * w_n])
+            check(lib.pgpu_ctx_enable_timing(sk._ctx, 1), sk._ctx)
+            kms = C.c_float()
             t0 = time.perf_counter()
-            proofs = sk.ProveDDLEQBatch(dsecpar, ct1, ct2, As, Bs, xs, ys)
+            al_r, e_r, f_r = sk.prove_ddleq_records(dn, dsecpar, c1r, c2r, ar, br, xr, yr)
             t1 = time.perf_counter()
-            okd = sk.VerifyDDLEQProofBatch(ct1, ct2, proofs)
+            check(lib.pgpu_ctx_last_kernel_ms(sk._ctx, C.byref(kms)), sk._ctx); prove_kms = kms.value
+            okd = sk.verify_ddleq_records(dn, dsecpar, c1r, c2r, xr, yr, al_r, e_r, f_r)
             t2 = time.perf_counter()
-            assert all(okd), "DDLEQ verification rejected an honest proof"
+            check(lib.pgpu_ctx_last_kernel_ms(sk._ctx, C.byref(kms)), sk._ctx); verify_kms = kms.value
+            check(lib.pgpu_ctx_enable_timing(sk._ctx, 0), sk._ctx)
+            assert bool(okd.all()), "DDLEQ verification rejected an honest proof"
             breakdown["ddleq_prove_instances_per_s"] = dn * dsecpar / (t1 - t0)
             breakdown["ddleq_verify_instances_per_s"] = dn * dsecpar / (t2 - t1)
+            if prove_kms > 0 and verify_kms > 0:
+                breakdown["ddleq_prove_instances_per_s_device"] = dn * dsecpar / (prove_kms * 1e-3)
+                breakdown["ddleq_verify_instances_per_s_device"] = dn * dsecpar / (verify_kms * 1e-3)
             breakdown["ddleq_instances"] = dn * dsecpar
-        # BASELINE configs[4]: safe-prime candidate procedure (sieve + Miller-Rabin + Fermat) at 1024-bit p
+            extras_keep["ddleq"] = (dn, dsecpar, c1r, c2r, xr, yr, al_r, e_r, f_r)
+        # BASELINE configs[4]: safe-prime candidate procedure (sieve + Miller-Rabin + Fermat) at 1024-bit p, 2^16 candidates
+        # per call, timed around the C-ABI call on byte strings (no conversion to Python integers inside)
         if rank == 0:
-            from paillier_b200.keygen import safe_prime_scan
-            ncand = 1 << 15
-            rawb = synth.random_records(ncand, 128, 1024, stream=41).tobytes()
-            safe_prime_scan(1024, rawb[:128 * 256], device=local)
-            t0 = time.perf_counter()
-            _, _, okf = safe_prime_scan(1024, rawb, device=local)
-            breakdown["safe_prime_candidates_per_s"] = ncand / (time.perf_counter() - t0)
+            ncand = 1 << 16
+            nbc = (1024 - 1 + 7) // 8
+            rawb = np.ascontiguousarray(synth.random_records(ncand, nbc, 8 * nbc, stream=41))
+            sp_p = np.zeros(ncand * 128, dtype=np.uint8); sp_q = np.zeros(ncand * 128, dtype=np.uint8); sp_ok = np.zeros(ncand, dtype=np.uint8)
+            nl = C.c_uint64()
+            npp = lambda a: a.ctypes.data_as(C.c_void_p)
+            for timed in (False, True):
+                cnt = ncand if timed else 1024
+                t0 = time.perf_counter()
+                rc = lib.pgpu_safe_prime_scan(local, 1024, cnt, npp(rawb), npp(sp_p), npp(sp_q), npp(sp_ok), C.byref(nl))
+                spdt = time.perf_counter() - t0
+                if rc != 0:
+                    raise SystemExit("pgpu_safe_prime_scan failed: " + (lib.pgpu_primes_last_error() or b"").decode())
+            breakdown["safe_prime_candidates_per_s"] = ncand / spdt
             breakdown["safe_prime_candidates"] = ncand
+            # one 1023-bit Miller-Rabin round = 1023 squarings + ~1023/2 doublings at s = 32 limbs (2.1e6 MAC32);
+            # every candidate that survives the sieves (all of them here: the scan tests one survivor per byte string) pays it
+            breakdown["safe_prime_mr_mac32_per_candidate"] = mont_macs(32, 1023, 0)
+            extras_keep["safe_prime"] = (rawb, sp_ok.copy())
+
+    # ---- strong scaling (configs[1]: "then sharded across 2/4/8"): ONE batch of --strong-count items split over the ranks
+    strong = None
+    if world > 1 and not args.no_extras:
+        from paillier_b200.multi import shard_range
+        slo, shi = shard_range(args.strong_count, world, rank)
+        scount = min(shi - slo, count)
+        def sstep():
+            check(lib.pgpu_encrypt_with_r_dev(sk._ctx, scount, vp(m_dev), vp(r_dev), vp(c_dev)), sk._ctx)
+            check(lib.pgpu_decrypt_dev(sk._ctx, scount, vp(c_dev), vp(d_dev)), sk._ctx)
+        sstep()
+        ssteps = 2
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        es[0].record(stream)
+        for _ in range(ssteps):
+            sstep()
+        es[1].record(stream)
+        barrier()
+        sms_ = max_over_ranks(es[0].elapsed_time(es[1])) / ssteps
+        assert torch.equal(d_dev[:scount * w_n], m_dev[:scount * w_n])
+        strong = {"value": world * scount / (sms_ * 1e-3), "unit": UNIT, "scaling": "strong", "items_total": world * scount,
+                  "items_per_gpu": scount, "ms_per_step": sms_, "steps": ssteps,
+                  "note": "one batch split into contiguous slices, no collective on the data path; resident groups per GPU = "
+                          "%d, so the last round of the persistent grid is partly idle at small slices" % sk_resident}
+
+    # ---- BASELINE configs[3]: threshold round, 3072-bit n, 8 shares / threshold 5
+    config4 = None
+    if not args.no_extras and not args.no_config4 and 8 % world == 0:
+        config4 = config4_leg(args, dist, rank, world, local, dev, barrier, max_over_ranks)
 
     if rank == 0:
         peak = imad_peak() if not args.no_extras else None
         peak_t = peak["imad_wide_tmacs"] if peak else None
+        fpeak = fp64_peak() if not args.no_extras else None
+        shape_n2, shape_p2 = sk.kernel_shape(1), sk.kernel_shape(3)
+        kname = lambda sh, S: ("powm_vm52<%d,%d,%d>" % (sh["tpi"], sh["limbs_per_lane"], S)) if sh["fp64"] else ("powm_vm<%d,%d>" % (sh["tpi"], sh["limbs_per_lane"]))
         achieved = enc_macs * count / (enc_ms * 1e-3) / 1e12      # per GPU: one launch processes `count` items
-        # what the multiplier pipe actually executes: powm_vm<4,32> squares with the general multiplier (2s^2+s)
+        # what the multiplier executes: no dedicated squaring in this kernel, every modular multiplication is a full product
         executed = (n_sqr + n_mul) * (2.0 * S * S + S) * count / (enc_ms * 1e-3) / 1e12
         mp = {}
         try:
@@ -489,46 +704,70 @@ def main() -> None:
         except Exception:
             pass
         alg_bytes = count * (2 * w_n + w_n2)
-        # DRAM bytes of the EncryptWithR launch: per-item traffic of the committed `ncu --set full` capture of the same
-        # kernel (profiles/r01_ncu_powm_vm_summary_v4.json, 18944 items) scaled to this launch's item count
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_powm_vm_summary_v4.json")))
-            k0 = prof["kernels"][0]
-            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-            def _b(sv):
-                v, u = sv.split()[:2]
-                return float(v) * unit[u]
-            traffic = (_b(k0["dram__bytes_read.sum"]) + _b(k0["dram__bytes_write.sum"])) / prof["items_per_launch"] * count
-        except Exception:
-            traffic = None
+        # DRAM bytes of the EncryptWithR launch: NOT measured in this run -- per-item traffic of the committed `ncu --set full`
+        # capture of the same program (window table spilling past the L2) scaled to this launch's item count
+        traffic, traffic_src = None, None
+        for name in ("r02_ncu_summary.json", "r01_ncu_powm_vm_summary_v4.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                k0 = prof["kernels"][0]
+                unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                def _b(sv):
+                    v, u = sv.split()[:2]
+                    return float(v) * unit[u]
+                traffic = (_b(k0["dram__bytes_read.sum"]) + _b(k0["dram__bytes_write.sum"])) / prof["items_per_launch"] * count
+                traffic_src = "extrapolated from profiles/%s (%d items per launch there), not measured in this run" % (name, prof["items_per_launch"])
+                break
+            except Exception:
+                continue
+        def frac_of(key_prog, key_rate):
+            if key_rate not in breakdown:
+                return None
+            a = breakdown[key_prog]["mac32_per_item"] * breakdown[key_rate] / world / 1e12
+            return {"achieved": a, "frac": (a / peak_t) if peak_t else None}
+        other = {"crt_decrypt (2 x %s + crt_combine)" % kname(shape_p2, Sd): {
+            "achieved": dec_macs * count / (dec_ms * 1e-3) / 1e12,
+            "frac": (dec_macs * count / (dec_ms * 1e-3) / 1e12 / peak_t) if peak_t else None}}
+        for label, kp, kr in (("partial_decrypt 2048-bit n", "pdec_program", "pdec_per_s"), ("partial_decrypt 3072-bit n", "pdec3072_program", "pdec3072_per_s")):
+            f = frac_of(kp, kr)
+            if f:
+                other[label] = f
+        if "safe_prime_candidates_per_s" in breakdown:
+            a = breakdown["safe_prime_mr_mac32_per_candidate"] * breakdown["safe_prime_candidates_per_s"] / 1e12
+            other["safe_prime_scan (strong_kernel: one Miller-Rabin round per candidate, e2e incl. sieve and copies)"] = {
+                "achieved": a, "frac": (a / peak_t) if peak_t else None}
+        if "pdec_zkp_prove_per_s" in breakdown and "pdec_program" in breakdown:
+            # proof = a = (c^4)^r (per-item exponent of 2*bits) + b = V^r (fixed base, no squarings) on top of the partial decryption
+            pm = breakdown["pdec_program"]["mac32_per_item"]
+            a = 2.1 * pm * breakdown["pdec_zkp_prove_per_s"] / world / 1e12
+            other["pdec_zkp_prove 2048-bit n (~2.1 x the partial-decrypt work per item)"] = {"achieved": a, "frac": (a / peak_t) if peak_t else None}
         roofline = {
-            "bound": "imad", "kernel": "powm_vm (EncryptWithR launch)", "achieved": achieved, "peak": peak_t, "unit": "TMAC32/s",
+            "bound": "imad", "kernel": "%s (EncryptWithR launch)" % kname(shape_n2, S), "achieved": achieved, "peak": peak_t, "unit": "TMAC32/s",
             "frac": (achieved / peak_t) if peak_t else None,
-            "peak_source": "tools/imad_peak.cu run live on this GPU: dependency-free IMAD.WIDE.U32 issue rate (SURVEY.md 8d); "
-                           "MEASURED_PEAKS.json holds HBM and bf16 peaks only, which do not bound this integer carry-chain kernel",
+            "peak_source": "tools/imad_peak.cu run live on this GPU: dependency-free IMAD.WIDE.U32 issue rate, the chip's integer-multiply peak "
+                           "(SURVEY.md 8d); MEASURED_PEAKS.json holds HBM and bf16 peaks only, which do not bound this carry-chain kernel",
             "mac32_per_item": enc_macs, "items_per_launch": count, "launch_ms": enc_ms,
             "executed_tmac32": executed, "executed_frac": (executed / peak_t) if peak_t else None,
-            "note": "achieved counts squarings at 1.5s^2+1.5s (SURVEY.md 8d); the 4096-bit kernel issues 2s^2+s for them, see executed_*",
+            "note": "achieved counts squarings at 1.5s^2+1.5s and multiplications at 2s^2+s MAC32 (SURVEY.md 8d) whichever pipe executes them; "
+                    "executed_* counts every modular multiplication as a full 2s^2+s product, which is what the kernel issues",
             "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (enc_ms * 1e-3) / 1e9,
                     "peak_gbs": mp.get("hbm_gbs"), "frac": (alg_bytes / (enc_ms * 1e-3) / 1e9 / mp["hbm_gbs"]) if mp.get("hbm_gbs") else None},
-            "traffic": traffic,
+            "traffic": traffic, "traffic_source": traffic_src,
             "imad_peak": peak,
-            "other_kernels": {
-                "crt_decrypt (2 x powm_vm<4,16> + crt_combine)": {
-                    "achieved": dec_macs * count / (dec_ms * 1e-3) / 1e12,
-                    "frac": (dec_macs * count / (dec_ms * 1e-3) / 1e12 / peak_t) if peak_t else None},
-                **({"partial_decrypt (powm_vm<4,32>)": {
-                    "achieved": breakdown["pdec_program"]["mac32_per_item"] * breakdown["pdec_per_s"] / world / 1e12,
-                    "frac": (breakdown["pdec_program"]["mac32_per_item"] * breakdown["pdec_per_s"] / world / 1e12 / peak_t) if peak_t else None}}
-                   if "pdec_per_s" in breakdown else {}),
-                **({"partial_decrypt 3072-bit n (powm_vm<8,24>)": {
-                    "achieved": breakdown["pdec3072_program"]["mac32_per_item"] * breakdown["pdec3072_per_s"] / world / 1e12,
-                    "frac": (breakdown["pdec3072_program"]["mac32_per_item"] * breakdown["pdec3072_per_s"] / world / 1e12 / peak_t) if peak_t else None}}
-                   if "pdec3072_per_s" in breakdown else {}),
-            },
+            "other_kernels": other,
         }
+        if shape_n2["fp64"]:
+            # the launch runs on the FP64 pipe: 52-bit limbs, 3 FP64 instructions (2 DFMA.RZ + 1 DADD) per limb product,
+            # 2*s52^2 limb products per modular multiplication
+            s52 = shape_n2["tpi"] * shape_n2["limbs_per_lane"]
+            fops = (n_sqr + n_mul) * 2.0 * s52 * s52 * 3.0 * count / (enc_ms * 1e-3) / 1e12
+            fp = fpeak["dfma_tops"] if fpeak else None
+            roofline["fp64_pipe"] = {"limbs52": s52, "executed_tfp64_inst": fops, "peak_tfp64_inst": fp, "frac": (fops / fp) if fp else None,
+                                     "peak_source": "tools/dfma_peak.cu run live: dependency-free DFMA issue rate",
+                                     "note": "the kernel alternates FP64 and integer-pipe instructions one to one; ncu shows both pipes "
+                                             "throttling each other (profiles/r02_fp64_experiments.md)"}
         cpu = None
+        cpu_rows = None
         if not args.no_extras:
             from oracle import gmp_ref as G
             cores = G.cores()
@@ -547,14 +786,26 @@ def main() -> None:
                    "sample": f"first {sample} items of rank 0's batch, EncryptWithR + Decrypt as the reference issues them to libgmp "
                              "(paillier.go:213-216, :296-300: two full mpz_powm per encrypt, no CRT); libgmp stand-in for the Go package",
                    "enc_per_s": sample / t_enc, "dec_per_s": sample / (t_all - t_enc)}
+            nd = 256 * cores
+            c_np = c_dev[:nd * w_n2].cpu().numpy()
+            cpu_rows, ref_dot = cpu_baselines_leg(sk, n, p, q, w_n, w_n2, c_np, extras_keep, breakdown)
+            # the dot-product sample, recomputed on the GPU over the same terms, must equal the libgmp fold
+            kd = torch.from_numpy(synth.scalars_u64(nd).view(np.int64).copy()).to(dev)
+            dd = torch.empty(w_n2, dtype=torch.uint8, device=dev)
+            check(lib.pgpu_dot_u64_dev(sk._ctx, nd, vp(c_dev), C.cast(C.c_void_p(kd.data_ptr()), C.POINTER(C.c_uint64)), vp(dd)), sk._ctx)
+            torch.cuda.synchronize(dev)
+            assert np.array_equal(ref_dot, dd.cpu().numpy()), "GPU dot product differs from the libgmp oracle"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (IMAD.WIDE 32x32+64)", "data": "synthetic",
+            "dtype": ("f64 (52-bit limbs, DFMA) + u64 accumulators" if shape_n2["fp64"] else "u32 limbs (IMAD.WIDE 32x32+64)"), "data": "synthetic",
             "config": {"workload": WORKLOAD, "key": "tests/golden/keys.json:paillier_2048", "items_per_gpu_per_step": count,
+                       "items_per_step": world * count,
                        "l2": "inputs per step (%.0f MB) exceed the 126 MB L2" % ((count * (2 * w_n + w_n2)) / 1e6),
-                       "sharding": f"{world} independent per-GPU batches, no collective on the data path"},
-            "breakdown": breakdown, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                       "sharding": f"{world} independent per-GPU batches, no collective on the data path",
+                       "kernels": {"n^2": kname(shape_n2, S), "p^2,q^2": kname(shape_p2, Sd)}},
+            "breakdown": breakdown, "roofline": roofline, "cpu_baseline": cpu, "cpu_baselines": cpu_rows, "e2e": e2e, "clocks": clocks,
+            "strong": strong, "config4": config4,
             "gpu_launches": launches,
         }
         print(json.dumps(line), flush=True)

@@ -240,6 +240,10 @@ int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches);
 /* Montgomery multiplications per item of the compiled programs
  * (what = 0 encrypt, 1 decrypt (both CRT halves), 2 partial decrypt, 3 secret-key encrypt (both halves)): squarings and multiplies */
 int pgpu_ctx_program_cost(const pgpu_ctx* ctx, int what, uint32_t* limbs, uint32_t* n_sqr, uint32_t* n_mul);
+/* which exponentiation kernel serves a modulus (modsel: 0 n, 1 n^2, 2 n^3, 3 p^2 / q^2, 4 p^3 / q^3): lanes per residue,
+ * limbs per lane, fp64 = 1 for the FP64-pipe kernel (52-bit limbs, powm_vm52) / 0 for the integer-pipe kernel (32-bit
+ * limbs, powm_vm), and how many residues a full persistent grid holds (any pointer may be NULL) */
+int pgpu_ctx_kernel_shape(const pgpu_ctx* ctx, int modsel, int* tpi, int* limbs_per_lane, int* fp64, int* resident_groups);
 /* device time of the last call's kernels in milliseconds (host-buffer and *_dev
  * calls record CUDA events around their launches when timing is enabled) */
 int pgpu_ctx_enable_timing(pgpu_ctx* ctx, int on);

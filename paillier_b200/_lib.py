@@ -92,6 +92,7 @@ SIGNATURES = {
     "pgpu_pdec_zkp_verify_multi_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p, _p]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "pgpu_ctx_kernel_shape": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),
     "pgpu_ctx_last_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "pgpu_selftest_bn": (C.c_int, [C.c_int, _u8p, _sz, _u8p, _sz, _u8p, _sz, C.c_char_p, C.POINTER(_sz)]),

@@ -429,6 +429,12 @@ class PublicKey:
         check(lib.pgpu_ctx_launch_count(self._ctx, C.byref(v)), self._ctx)
         return v.value
 
+    def kernel_shape(self, modsel: int) -> dict:
+        """exponentiation kernel serving a modulus (0 n, 1 n^2, 2 n^3, 3 p^2/q^2, 4 p^3/q^3)"""
+        t, l, f, g = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.pgpu_ctx_kernel_shape(self._ctx, modsel, C.byref(t), C.byref(l), C.byref(f), C.byref(g)), self._ctx)
+        return {"tpi": t.value, "limbs_per_lane": l.value, "fp64": bool(f.value), "resident_groups": g.value}
+
     def program_cost(self, what: int):
         s, q, m = C.c_uint32(), C.c_uint32(), C.c_uint32()
         check(lib.pgpu_ctx_program_cost(self._ctx, what, C.byref(s), C.byref(q), C.byref(m)), self._ctx)

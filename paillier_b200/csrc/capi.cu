@@ -885,6 +885,25 @@ int pgpu_ctx_program_cost(const pgpu_ctx* ctx, int what, uint32_t* limbs, uint32
     return PGPU_OK;
 }
 
+int pgpu_ctx_kernel_shape(const pgpu_ctx* ctx, int modsel, int* tpi, int* limbs_per_lane, int* fp64, int* resident_groups) {
+    if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
+    const ModCtx* m = nullptr;
+    switch (modsel) {
+        case 0: m = &ctx->m_n; break;
+        case 1: m = &ctx->m_n2; break;
+        case 2: m = &ctx->m_n3; break;
+        case 3: m = &ctx->m_p2; break;
+        case 4: m = &ctx->m_p3; break;
+        default: return fail(nullptr, PGPU_ERR_ARG, "bad modulus selector");
+    }
+    if (!m->ready) return fail(nullptr, PGPU_ERR_STATE, "modulus not loaded");
+    if (tpi) *tpi = m->sh.tpi;
+    if (limbs_per_lane) *limbs_per_lane = m->sh.L;
+    if (fp64) *fp64 = m->sh.fp64 ? 1 : 0;
+    if (resident_groups) *resident_groups = ctx->sms * m->blocks_per_sm * (VM_BLOCK_THREADS / m->sh.tpi);
+    return PGPU_OK;
+}
+
 int pgpu_ctx_enable_timing(pgpu_ctx* ctx, int on) {
     if (!ctx) return fail(nullptr, PGPU_ERR_ARG, "null context");
     ctx->timing = on != 0; ctx->ev_valid = false;

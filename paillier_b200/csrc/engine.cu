@@ -14,11 +14,13 @@ static bool int_shape(size_t limbs, Shape& out) {
     return false;
 }
 
-// Smallest built shape holding `limbs` limbs.  Moduli of 2048 bits and more run on the FP64 pipe (52-bit limbs,
-// mont52.cuh: measured 1.09-1.17x the integer-pipe multiplier, tools/mont52_test.cu); PGPU_NO_FP64=1 keeps everything on
-// the integer pipe.  Override per width with PGPU_SHAPE_<S>="tpi,L" (integer pipe) or "tpi,L,fp64".
+// Smallest built shape holding `limbs` limbs.  4096-bit moduli (n^2 of a 2048-bit key: EncryptWithR, PartialDecrypt) run on
+// the FP64 pipe (52-bit limbs, mont52.cuh): +3 % over the integer-pipe kernel end to end.  The other widths stay on the
+// integer pipe, where the FP64 kernel measured equal (2048-bit moduli, which have the dedicated squaring) or slower (3072-
+// and 6144-bit moduli: 15 limbs per lane need 254 registers) -- profiles/r02_fp64_experiments.md.  PGPU_NO_FP64=1 keeps
+// everything on the integer pipe; override per width with PGPU_SHAPE_<S>="tpi,L" (integer pipe) or "tpi,L,fp64".
 bool pick_shape(size_t limbs, Shape& out) {
-    static const Shape fp64_defaults[] = {{64, 4, 10, true}, {96, 4, 15, true}, {128, 8, 10, true}, {192, 8, 15, true}};
+    static const Shape fp64_defaults[] = {{128, 8, 10, true}};
     static const bool no_fp64 = getenv("PGPU_NO_FP64") != nullptr;
     if (!int_shape(limbs, out)) return false;
     if (!no_fp64)

@@ -246,6 +246,10 @@ struct Mont52 {
 
     // ---------------------------------------------------------------- r = a * b * R^-1 mod n, lazily in [0, 2n)
     __device__ __forceinline__ void mul(double (&r)[L], const double (&a)[L], const double (&b)[L]) {
+#if PGPU52_ADD == 2
+        mul_cf(r, a, b);
+        return;
+#endif
         uint64_t C[L + 1];
 #pragma unroll
         for (int k = 0; k < L; ++k) C[k] = (uint64_t)(0u - ((uint32_t)k * ROWB + 2u * BL)) << 32;
@@ -288,6 +292,73 @@ struct Mont52 {
         uint64_t X[L];
 #pragma unroll
         for (int k = 0; k < L; ++k) X[k] = C[k] + ((uint64_t)((uint32_t)(k + 1) * ROWB - 2u * BH) << 32);
+        normalize(X);
+        from_limbs(r, X);
+    }
+
+    // ---------------------------------------------------------------- the same product with carry-free accumulators
+    // Carry-propagating adds (IADD3 with carry-out predicates, IADD3.X) do not issue in the shadow of the FP64 pipe the way
+    // plain adds do (tools/pipe_probe.cu).  Here every 64-bit column is three 32-bit words updated by plain adds only:
+    //   lo = sum of the low words mod 2^32,  hi = sum of the high words mod 2^32,  ap = sum of (low word >> 16).
+    // The carries the low words lost are recovered when a column is read: the true low sum T is congruent to lo mod 2^32
+    // and lies in [ap*2^16, ap*2^16 + N*2^16) for N terms (N*2^16 < 2^32), so T = lo + 2^32*k with
+    // k = (ap*2^16 + (2^32 - 1 - lo)) >> 32.
+    struct Col3 { uint32_t lo, hi, ap; };
+    static __device__ __forceinline__ uint64_t col_value(const Col3& c) {
+        const uint64_t k = ((((uint64_t)c.ap) << 16) + (uint64_t)(~c.lo)) >> 32;
+        return (uint64_t)c.lo | ((uint64_t)(c.hi + (uint32_t)k) << 32);
+    }
+    static __device__ __forceinline__ void col_add1(Col3& c, uint64_t x) {
+        const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+        c.lo += xl; c.hi += xh; c.ap += xl >> 16;
+    }
+    static __device__ __forceinline__ void col_add2(Col3& c, uint64_t x, uint64_t y) {
+        const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32), yl = (uint32_t)y, yh = (uint32_t)(y >> 32);
+        c.lo = c.lo + xl + yl; c.hi = c.hi + xh + yh; c.ap = c.ap + (xl >> 16) + (yl >> 16);
+    }
+
+    __device__ __forceinline__ void mul_cf(double (&r)[L], const double (&a)[L], const double (&b)[L]) {
+        Col3 C[L + 1];
+#pragma unroll
+        for (int k = 0; k < L; ++k) { C[k].lo = 0; C[k].ap = 0; C[k].hi = 0u - ((uint32_t)k * ROWB + 2u * BL); }
+        constexpr uint32_t KSPH = 0u - (uint32_t)L * ROWB;
+        C[L].lo = C[L].hi = C[L].ap = 0;
+
+#pragma unroll 1
+        for (int u = 0; u < TPI; ++u) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                const double bj = __shfl_sync(FULL_MASK, b[k], u, TPI);
+                uint64_t h[L], l[L];
+#pragma unroll
+                for (int i = 0; i < L; ++i) split52(a[i], bj, h[i], l[i]);
+                col_add1(C[0], l[0]);
+#pragma unroll
+                for (int i = 1; i < L; ++i) col_add2(C[i], l[i], h[i - 1]);
+                C[L].lo = (uint32_t)h[L - 1]; C[L].hi = KSPH + (uint32_t)(h[L - 1] >> 32); C[L].ap = (uint32_t)h[L - 1] >> 16;
+                const uint64_t v0 = col_value(C[0]);
+                const uint64_t q = __shfl_sync(FULL_MASK, ((v0 & M52) * np) & M52, 0, TPI);
+                const double qd = u52_to_double(q);
+#pragma unroll
+                for (int i = 0; i < L; ++i) split52(n[i], qd, h[i], l[i]);
+                col_add1(C[0], l[0]);
+#pragma unroll
+                for (int i = 1; i < L; ++i) col_add2(C[i], l[i], h[i - 1]);
+                col_add1(C[L], h[L - 1]);
+                const uint64_t done = col_value(C[0]);
+                uint64_t recv = __shfl_down_sync(FULL_MASK, done, 1, TPI);
+                if (t == TPI - 1) recv = 0;
+                const uint32_t carry = (t == 0) ? (uint32_t)(done >> 52) : 0u;
+#pragma unroll
+                for (int i = 0; i < L - 1; ++i) C[i] = C[i + 1];
+                C[L - 1] = C[L];
+                col_add1(C[L - 1], recv);
+                C[0].lo += carry;            // < 2^12: nothing for ap
+            }
+        }
+        uint64_t X[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) X[k] = col_value(C[k]) + ((uint64_t)((uint32_t)(k + 1) * ROWB - 2u * BH) << 32);
         normalize(X);
         from_limbs(r, X);
     }

@@ -3,7 +3,9 @@
 The key-generation glue is a handful of big-integer operations per key, done once on the host
 (thresholdkey_generator.go:113-231 are O(l*w) multiplications); the l modular exponentiations of
 createVerificationKeys (thresholdkey_generator.go:246-254) go through the GPU engine's batched Exp.
-Randomness is injected (the reference takes an io.Reader, thresholdkey_generator.go:66).
+Randomness defaults to the operating system's CSPRNG (`random.SystemRandom`, i.e. os.urandom), as the reference draws
+every prime, coefficient and v from crypto/rand (thresholdkey_generator.go:66, paillier.go:122-139).  A seeded
+`random.Random` may be passed as `rng` for reproducible TESTS ONLY: keys made from it are predictable.
 """
 from __future__ import annotations
 
@@ -28,7 +30,7 @@ class ThresholdKeyGenerator:
     PublicKeyBitLength: int
     TotalNumberOfDecryptionServers: int
     Threshold: int
-    rng: random.Random = field(default_factory=lambda: random.Random(20260101))
+    rng: random.Random = field(default_factory=random.SystemRandom)      # CSPRNG; a seeded random.Random is for tests only
     p: int = 0
     q: int = 0
     batch: int = 1 << 15          # safe-prime candidates per GPU call
@@ -179,7 +181,7 @@ def KeyGen(secparam: int, rng: Optional[random.Random] = None, device: int = 0):
         raise ValueError("KeyGen: secparam must be divisible by 2")           # :108-110
     if secparam < 64:
         raise ValueError("KeyGen: secparam must be at least 64 bits")         # :112-114
-    rng = rng or random.Random()
+    rng = rng or random.SystemRandom()                                         # crypto/rand, :122-139
     while True:
         p = _random_prime_3mod4(secparam // 2, rng, device)
         q = _random_prime_3mod4(secparam // 2, rng, device)

@@ -251,6 +251,7 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
                 e = torch.empty(k * count * 32, dtype=torch.uint8, device=dev)
                 z = torch.empty(k * count * wz, dtype=torch.uint8, device=dev)
                 for j, t in enumerate(tsks):
+                    # (slices of live tensors: their storage stays allocated)
                     check(lib.pgpu_pdec_zkp_prove_given_dev(t._ctx, count, vp(c_dev), vp(zkp_r[j]), vp(dec[j * count * w2:]),
                                                             vp(e[j * count * 32:]), vp(z[j * count * wz:])), t._ctx)
             ev["prove"][1].record(stream)
@@ -274,8 +275,9 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
                 rows = lambda buf, w: torch.cat([buf[(s * count + lo) * w:(s * count + hi) * w] for s in range(shares)])
                 ok = torch.zeros(shares * n, dtype=torch.uint8, device=dev)
                 idarr = (C.c_int * shares)(*ids)
-                check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(c_dev[lo * w2:hi * w2].repeat(shares)),
-                                                         vp(rows(g_dec, w2)), vp(rows(g_e, 32)), vp(rows(g_z, wz)), vp(ok)), t0._ctx)
+                # (named tensors: a temporary would hand its memory back to torch's allocator before the kernels ran)
+                v_c, v_dec, v_e, v_z = c_dev[lo * w2:hi * w2].repeat(shares), rows(g_dec, w2), rows(g_e, 32), rows(g_z, wz)
+                check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(v_c), vp(v_dec), vp(v_e), vp(v_z), vp(ok)), t0._ctx)
                 verdict = ok.view(shares, n).all(dim=1)
             ev["verify"][1].record(stream)
             if zkp_r is not None and n > 0:

@@ -82,3 +82,36 @@ def test_sharded_safe_prime_world1_matches_single_device_search():
         want = GenerateSafePrime(bits, lambda nb: r1.randbytes(nb), batch=batch)
         got = sharded_safe_prime(None, 0, 1, bits, lambda nb: r2.randbytes(nb), safe_prime_scan, batch=batch)
         assert got == want and got[0] == 2 * got[1] + 1 and got[0].bit_length() == bits
+
+
+@pytest.mark.parametrize("bits,l,w", [(512, 4, 3), (2048, 8, 5)])
+def test_threshold_round_all_shares_on_one_device(bits, l, w):
+    # BASELINE config 4 with every share-holder on this device (bench.py's config4 leg at N = 1): PartialDecrypt, proof
+    # with the partial decryptions given, VerifyProof of all shares, Combine; per-share output equals the one-call path
+    import numpy as np
+    from paillier_b200.multi import gpu_threshold_round_shares
+    p, q = synth.load_key(f"threshold_{bits}")
+    n = p * q
+    keys = ThresholdKeyGenerator(bits, l, w, rng=random.Random(11)).with_safe_primes(p, q).GenerateKeys()
+    t0 = keys[0]
+    count = 21
+    m = synth.plaintexts(count, n, t0.w_n)
+    c = t0.encrypt_with_r_records(m, synth.randomness(count, n, t0.w_n))
+    dev = torch.device("cuda", 0)
+    c_dev = torch.from_numpy(c).to(dev)
+    rs = [synth.random_records(count, t0.w_n2, (n * n).bit_length() - 1, stream=5 + t.ID) for t in keys]
+    keep = {}
+    plain, (lo, hi), phases = gpu_threshold_round_shares(None, keys, c_dev, count, 1, 0, [torch.from_numpy(r).to(dev) for r in rs], keep=keep)
+    assert (lo, hi) == (0, count) and keep["ids"] == list(range(1, l + 1))
+    assert from_records(plain.cpu().numpy(), t0.w_n) == from_records(m, t0.w_n)
+    assert set(phases) == {"pdec", "prove", "all_gather", "verify", "combine"} and all(v >= 0 for v in phases.values())
+    for j, t in enumerate(keys):
+        dec, e, z = t.zkp_prove_records(c, rs[j])
+        assert np.array_equal(dec, keep["dec"][j * count * t.w_n2:(j + 1) * count * t.w_n2].cpu().numpy())
+        assert np.array_equal(e, keep["e"][j * count * 32:(j + 1) * count * 32].cpu().numpy())
+        assert np.array_equal(z, keep["z"][j * count * t.w_z:(j + 1) * count * t.w_z].cpu().numpy())
+    # without proofs
+    plain2, _, _ = gpu_threshold_round_shares(None, keys, c_dev, count, 1, 0, None)
+    assert torch.equal(plain2, plain)
+    for t in keys:
+        t.close()

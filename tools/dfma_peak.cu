@@ -56,7 +56,9 @@ __global__ void k_dfma_product(uint64_t* out, double a0, double b0, int trips) {
         for (int r = 0; r < INNER; ++r) {
             // a fresh multiplier per repetition, derived from the accumulators (as a quotient digit would be), so that
             // ptxas cannot reuse products across repetitions: an integer < 2^52 as a double
-            const uint64_t qb = lo[r % ACC];
+            // (only the even accumulators are updated below: an odd one would make bb loop-invariant and let ptxas hoist
+            // 3/8 of the products out of the loop -- the first version of this tool did, and overstated the rate by 1.6x)
+            const uint64_t qb = lo[(r % (ACC / 2)) * 2];
             const double bb = __hiloint2double((int)((uint32_t)(qb >> 32) & 0xfffffu) | 0x43200000, (int)(uint32_t)qb) - 0x1p51 + b[r & 3] * 0.0;
 #pragma unroll
             for (int i = 0; i < ACC; i += 2) {
