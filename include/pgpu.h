@@ -138,6 +138,8 @@ int pgpu_pdec_zkp_verify(pgpu_ctx* ctx, size_t count, int id, const void* c, con
  * decryptions (share j's batch starts at record j*count).  m: n-width plaintexts.
  * PGPU_ERR_THRESHOLD for "Threshold not meet" / duplicate ids (:77-89). */
 int pgpu_combine(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, void* m);
+/* host-buffer form of pgpu_combine_verified_dev (see there): decs = k batches of count records, ok = k * count verdict bytes */
+int pgpu_combine_verified(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, const uint8_t* ok, void* m, uint8_t* item_ok);
 
 
 /* ---- level 2 (mod n^3), alternative encryption, randomness, nested ops ---- */
@@ -202,6 +204,25 @@ int pgpu_modexp(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const
 int pgpu_modexp_shared(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const uint8_t* exp_be, size_t exp_len, void* out);
 int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const void* b, void* out);
 
+/* ---- device buffers and pinned host memory ------------------------------ */
+/* SURVEY.md 8(b) "Ownership" / 8(f) rank 1: ciphertexts stay on the device between calls (Encrypt -> ConstMult -> Add ->
+ * Decrypt without PCIe round trips, the callers of operations.go:11-64).  A pgpu_buf is device memory on the context's
+ * device; pgpu_buf_ptr() is what the *_dev entry points below take.  Upload / download block until the copy is done (no
+ * host pointer is retained); pgpu_buf_free waits for the work enqueued on the context before releasing the memory. */
+typedef struct pgpu_buf pgpu_buf;
+int pgpu_buf_alloc(pgpu_ctx* ctx, size_t bytes, pgpu_buf** out);
+int pgpu_buf_free(pgpu_buf* buf);
+void* pgpu_buf_ptr(const pgpu_buf* buf);
+size_t pgpu_buf_size(const pgpu_buf* buf);
+int pgpu_buf_upload(pgpu_buf* dst, size_t dst_off, const void* host, size_t bytes);
+int pgpu_buf_download(const pgpu_buf* src, size_t src_off, void* host, size_t bytes);
+/* wait for everything enqueued by *_dev calls on this context */
+int pgpu_ctx_sync(pgpu_ctx* ctx);
+/* page-locked host memory: with it the host-buffer entry points copy at full PCIe rate and overlap the copies of one chunk
+ * with the kernels of the next (Go: wrap the pointer with unsafe.Slice; pageable slices work too, at the pageable rate) */
+int pgpu_host_alloc(size_t bytes, void** out);
+int pgpu_host_free(void* p);
+
 /* ---- same operations on device-resident buffers ------------------------ */
 /* Pointers are device pointers on the context's device; work is enqueued on
  * the context's stream and NOT synchronised (the caller owns ordering). */
@@ -228,6 +249,13 @@ int pgpu_combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const v
  * all-gathered [share][ciphertext] buffer in place (one share-holder per GPU) */
 int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, void* m);
 int pgpu_pdec_zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const void* c, const void* dec, const void* e, const void* z, uint8_t* ok);
+/* CombinePartialDecryptionsZKP (thresholdkey.go:164-172) with the reference's PER-CIPHERTEXT filter: ok holds k * count
+ * verdict bytes grouped by server like decs (ok[j*count + i] != 0: server ids[j]'s proof for ciphertext i verified); a
+ * ciphertext is combined from the shares whose proof holds, one combine per distinct surviving set.  Ciphertexts left with
+ * fewer than `threshold` valid shares get a zero plaintext and item_ok[i] = 0 (item_ok may be NULL); if there are any the
+ * call returns PGPU_ERR_THRESHOLD ("Threshold not meet") AFTER filling every other plaintext. */
+int pgpu_combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, const uint8_t* ok,
+                              void* m, uint8_t* item_ok);
 /* VerifyProof for the proofs of k servers in one batch: n_per_id proofs per server, grouped by server in the order of
  * ids[0..k) (record i belongs to server ids[i / n_per_id]); c, dec, e, z, ok hold k * n_per_id records.  Used by the
  * combiner of a threshold round, which checks every share-holder's proofs of its ciphertext slice at once. */

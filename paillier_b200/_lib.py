@@ -50,6 +50,15 @@ SIGNATURES = {
     "pgpu_modexp": (C.c_int, [_p, C.c_int, _sz, _p, _p, _sz, _p]),
     "pgpu_modexp_shared": (C.c_int, [_p, C.c_int, _sz, _p, _u8p, _sz, _p]),
     "pgpu_modmul": (C.c_int, [_p, C.c_int, _sz, _p, _p, _p]),
+    "pgpu_buf_alloc": (C.c_int, [_p, _sz, C.POINTER(_p)]),
+    "pgpu_buf_free": (C.c_int, [_p]),
+    "pgpu_buf_ptr": (C.c_void_p, [_p]),
+    "pgpu_buf_size": (C.c_size_t, [_p]),
+    "pgpu_buf_upload": (C.c_int, [_p, _sz, _p, _sz]),
+    "pgpu_buf_download": (C.c_int, [_p, _sz, _p, _sz]),
+    "pgpu_ctx_sync": (C.c_int, [_p]),
+    "pgpu_host_alloc": (C.c_int, [_sz, C.POINTER(_p)]),
+    "pgpu_host_free": (C.c_int, [_p]),
     "pgpu_encrypt_with_r_dev": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_r_sk": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_encrypt_with_rn": (C.c_int, [_p, _sz, _p, _p, _p]),
@@ -69,6 +78,8 @@ SIGNATURES = {
     "pgpu_ctx_z_width": (C.c_int, [_p, C.POINTER(_sz)]),
     "pgpu_pdec_zkp_verify": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
     "pgpu_combine": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
+    "pgpu_combine_verified": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p]),
+    "pgpu_combine_verified_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _sz, _p, _p, _p]),
     "pgpu_pdec_zkp_prove_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
     "pgpu_pdec_zkp_prove_given_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),
     "pgpu_combine_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),

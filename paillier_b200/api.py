@@ -22,7 +22,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import MOD_N, MOD_N2, MOD_N3, PgpuError, check, lib  # noqa: F401
+from ._lib import MOD_N, MOD_N2, MOD_N3, PGPU_ERR_THRESHOLD, PGPU_OK, PgpuError, check, lib  # noqa: F401
 
 ENC_LEVEL_ONE, ENC_LEVEL_TWO = 0, 1          # paillier.go:17-23
 REGULAR, ALTERNATIVE, MIXED = 0, 1, 2        # paillier.go:29-39
@@ -614,10 +614,43 @@ class ThresholdPublicKey(PublicKey):
         flat = [pd.Decryption for s in shares for pd in s]
         return from_records(self.combine_records(ids, to_records(flat, self.w_n2)), self.w_n)
 
-    def CombinePartialDecryptionsZKPBatch(self, shares: Sequence[Sequence[PartialDecryptionZKP]]) -> List[int]:
-        """thresholdkey.go:164-172 for a batch: a server's batch takes part only if all its proofs verify."""
-        good = [s for s in shares if all(self.VerifyProofBatch(s))]
-        return self.CombinePartialDecryptionsBatch([[PartialDecryption(p.ID, p.Decryption) for p in s] for s in good])
+    def combine_verified_records(self, ids: Sequence[int], decs, ok):
+        """pgpu_combine_verified: decs = len(ids) batches of n2-width records, ok = len(ids) * count verdict bytes (server
+        major) -> (plaintext records, per-ciphertext flags: 0 where fewer than Threshold shares verified)"""
+        decs = np.ascontiguousarray(decs).view(np.uint8).reshape(-1)
+        ok = np.ascontiguousarray(ok, dtype=np.uint8).reshape(-1)
+        k = len(ids)
+        count = decs.size // (self.w_n2 * k) if k else 0
+        out = np.zeros(count * self.w_n, dtype=np.uint8)
+        item_ok = np.zeros(count, dtype=np.uint8)
+        idarr = (C.c_int * max(k, 1))(*ids)
+        rc = lib.pgpu_combine_verified(self._ctx, count, k, idarr, _ptr(decs) if decs.size else None, _ptr(ok) if ok.size else None,
+                                       _ptr(out) if count else None, _ptr(item_ok) if count else None)
+        if rc not in (PGPU_OK, PGPU_ERR_THRESHOLD):
+            check(rc, self._ctx)
+        return out, item_ok
+
+    def CombinePartialDecryptionsZKPBatch(self, shares: Sequence[Sequence[PartialDecryptionZKP]], strict: bool = True):
+        """N x CombinePartialDecryptionsZKP (thresholdkey.go:164-172): shares[j] is server j's batch, all batches in the same
+        ciphertext order.  As in the reference the proofs filter PER CIPHERTEXT: ciphertext i is combined from the servers
+        whose proof for i verifies.  Where fewer than Threshold remain the reference returns "Threshold not meet" for that
+        ciphertext: with strict (default) the call raises PgpuError(PGPU_ERR_THRESHOLD) if that happens to any of them, with
+        strict=False those positions hold None and the others their plaintext."""
+        if not shares:
+            raise PgpuError(PGPU_ERR_THRESHOLD, "Threshold not meet")
+        count = len(shares[0])
+        if any(len(s) != count for s in shares):
+            raise ValueError("CombinePartialDecryptionsZKPBatch: one proof per ciphertext and server")
+        ids = [s[0].ID if count else 0 for s in shares]
+        if len(set(ids)) != len(ids) and count:
+            raise PgpuError(PGPU_ERR_THRESHOLD, "two shares has been created by the same server")
+        ok = np.array([self.VerifyProofBatch(s) for s in shares], dtype=np.uint8).reshape(-1)
+        flat = [p.Decryption for s in shares for p in s]
+        out, item_ok = self.combine_verified_records(ids, to_records(flat, self.w_n2), ok)
+        vals = from_records(out, self.w_n)
+        if strict and not item_ok.all():
+            raise PgpuError(PGPU_ERR_THRESHOLD, f"Threshold not meet for {int(count - item_ok.sum())} of {count} ciphertexts")
+        return [v if f else None for v, f in zip(vals, item_ok)]
 
 
     def VerifyDecryptionBatch(self, encryptedMessages: Sequence[int], decryptedMessages: Sequence[int],

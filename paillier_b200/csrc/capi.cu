@@ -83,6 +83,12 @@ int pgpu_ctx_destroy(pgpu_ctx* ctx) {
     for (void* p : ctx->d_stage) if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); }
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
+        if (ctx->ev_cmp[b]) cudaEventDestroy(ctx->ev_cmp[b]);
+        if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return PGPU_OK;
@@ -278,20 +284,95 @@ int pgpu_randomize_with_r_dev(pgpu_ctx* ctx, size_t count, const void* c, const 
     GUARD_END(ctx)
 }
 
+// ---- device buffers, pinned host memory (SURVEY.md 8b "Ownership", 8f rank 1)
+int pgpu_buf_alloc(pgpu_ctx* ctx, size_t bytes, pgpu_buf** out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out, "pgpu_buf_alloc: null argument");
+    *out = nullptr;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    pgpu_buf* b = new pgpu_buf();
+    b->ctx = ctx; b->bytes = bytes;
+    cudaError_t e = cudaMalloc(&b->ptr, std::max<size_t>(bytes, 1));
+    if (e != cudaSuccess) { delete b; return fail(ctx, PGPU_ERR_CUDA, std::string("pgpu_buf_alloc: ") + cudaGetErrorString(e)); }
+    *out = b;
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_buf_free(pgpu_buf* b) {
+    if (!b) return PGPU_OK;
+    pgpu_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);            // work enqueued on the buffer has finished
+    cudaFree(b->ptr);
+    delete b;
+    return PGPU_OK;
+}
+
+void* pgpu_buf_ptr(const pgpu_buf* b) { return b ? b->ptr : nullptr; }
+size_t pgpu_buf_size(const pgpu_buf* b) { return b ? b->bytes : 0; }
+
+int pgpu_buf_upload(pgpu_buf* dst, size_t dst_off, const void* host, size_t bytes) {
+    if (!dst) return fail(nullptr, PGPU_ERR_ARG, "pgpu_buf_upload: null buffer");
+    pgpu_ctx* ctx = dst->ctx;
+    GUARD_BEGIN
+    REQUIRE(ctx, bytes == 0 || host, "pgpu_buf_upload: null host pointer");
+    REQUIRE(ctx, dst_off <= dst->bytes && bytes <= dst->bytes - dst_off, "pgpu_buf_upload: range outside the buffer");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    CU(ctx, cudaMemcpyAsync((uint8_t*)dst->ptr + dst_off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));   // the library keeps no host pointer past return
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_buf_download(const pgpu_buf* src, size_t src_off, void* host, size_t bytes) {
+    if (!src) return fail(nullptr, PGPU_ERR_ARG, "pgpu_buf_download: null buffer");
+    pgpu_ctx* ctx = src->ctx;
+    GUARD_BEGIN
+    REQUIRE(ctx, bytes == 0 || host, "pgpu_buf_download: null host pointer");
+    REQUIRE(ctx, src_off <= src->bytes && bytes <= src->bytes - src_off, "pgpu_buf_download: range outside the buffer");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    CU(ctx, cudaMemcpyAsync(host, (const uint8_t*)src->ptr + src_off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_ctx_sync(pgpu_ctx* ctx) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx, "pgpu_ctx_sync: null context");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(nullptr, PGPU_ERR_ARG, "pgpu_host_alloc: null argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, PGPU_ERR_CUDA, std::string("pgpu_host_alloc: ") + cudaGetErrorString(e));
+    return PGPU_OK;
+}
+
+int pgpu_host_free(void* p) {
+    if (!p) return PGPU_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail(nullptr, PGPU_ERR_CUDA, std::string("pgpu_host_free: ") + cudaGetErrorString(e));
+    return PGPU_OK;
+}
+
 // ---- host-buffer entry points
 int pgpu_encrypt_with_r(pgpu_ctx* ctx, size_t count, const void* m, const void* r, void* c) {
     GUARD_BEGIN
     REQUIRE(ctx, ctx && (count == 0 || (m && r && c)), "pgpu_encrypt_with_r: null argument");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
-    uint32_t* dm = io.in(0, m, count * wn);
-    uint32_t* dr = io.in(1, r, count * wn);
-    uint32_t* dc = io.out(2, count * w2);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = encrypt_dev(ctx, count, dm, dr, dc))) return rc; }
-    return io.finish(c, dc, count * w2);
+    ChunkedIo io;
+    io.add_in(m, wn); io.add_in(r, wn); io.add_out(c, w2);
+    io.align = resident_groups(ctx, ctx->m_n2);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* out) { return encrypt_dev(ctx, n, in[0], in[1], out[0]); });
     GUARD_END(ctx)
 }
 
@@ -301,14 +382,11 @@ int pgpu_encrypt_with_r_sk(pgpu_ctx* ctx, size_t count, const void* m, const voi
     if (!ctx->has_secret) return fail(ctx, PGPU_ERR_STATE, "EncryptWithR (secret key): no secret key loaded");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
-    uint32_t* dm = io.in(0, m, count * wn);
-    uint32_t* dr = io.in(1, r, count * wn);
-    uint32_t* dc = io.out(2, count * w2);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = encrypt_crt_dev(ctx, count, dm, dr, dc))) return rc; }
-    return io.finish(c, dc, count * w2);
+    ChunkedIo io;
+    io.add_in(m, wn); io.add_in(r, wn); io.add_out(c, w2);
+    io.align = resident_groups(ctx, ctx->m_p2.ready ? ctx->m_p2 : ctx->m_n2);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* out) { return encrypt_crt_dev(ctx, n, in[0], in[1], out[0]); });
     GUARD_END(ctx)
 }
 
@@ -317,14 +395,11 @@ int pgpu_encrypt_with_rn(pgpu_ctx* ctx, size_t count, const void* m, const void*
     REQUIRE(ctx, ctx && (count == 0 || (m && rn && c)), "pgpu_encrypt_with_rn: null argument");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
-    uint32_t* dm = io.in(0, m, count * wn);
-    uint32_t* dr = io.in(1, rn, count * w2);
-    uint32_t* dc = io.out(2, count * w2);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = encrypt_rn_dev(ctx, count, dm, dr, dc))) return rc; }
-    return io.finish(c, dc, count * w2);
+    ChunkedIo io;
+    io.add_in(m, wn); io.add_in(rn, w2); io.add_out(c, w2);
+    io.align = resident_groups(ctx, ctx->m_n2);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* out) { return encrypt_rn_dev(ctx, n, in[0], in[1], out[0]); });
     GUARD_END(ctx)
 }
 
@@ -333,13 +408,11 @@ int pgpu_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* m) {
     REQUIRE(ctx, ctx && (count == 0 || (m && c)), "pgpu_decrypt: null argument");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t wn = ctx->wn * 4, w2 = (size_t)ctx->m_n2.sh.S * 4;
-    uint32_t* dc = io.in(0, c, count * w2);
-    uint32_t* dm = io.out(1, count * wn);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = decrypt_dev(ctx, count, dc, dm))) return rc; }
-    return io.finish(m, dm, count * wn);
+    ChunkedIo io;
+    io.add_in(c, w2); io.add_out(m, wn);
+    io.align = resident_groups(ctx, ctx->m_p2.ready ? ctx->m_p2 : ctx->m_n2);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* out) { return decrypt_dev(ctx, n, in[0], out[0]); });
     GUARD_END(ctx)
 }
 
@@ -348,13 +421,11 @@ int pgpu_partial_decrypt(pgpu_ctx* ctx, size_t count, const void* c, void* out) 
     REQUIRE(ctx, ctx && (count == 0 || (out && c)), "pgpu_partial_decrypt: null argument");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t w2 = (size_t)ctx->m_n2.sh.S * 4;
-    uint32_t* dc = io.in(0, c, count * w2);
-    uint32_t* dout = io.out(1, count * w2);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = pdec_dev(ctx, count, dc, dout))) return rc; }
-    return io.finish(out, dout, count * w2);
+    ChunkedIo io;
+    io.add_in(c, w2); io.add_out(out, w2);
+    io.align = resident_groups(ctx, ctx->m_n2);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* o) { return pdec_dev(ctx, n, in[0], o[0]); });
     GUARD_END(ctx)
 }
 
@@ -366,14 +437,12 @@ int pgpu_modexp(pgpu_ctx* ctx, int modsel, size_t count, const void* base, const
     if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modexp: modulus not available for this key");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t w = (size_t)M->sh.S * 4;
-    uint32_t* db = io.in(0, base, count * w);
-    uint32_t* de = io.in(1, exp, count * exp_bytes);
-    uint32_t* dout = io.out(2, count * w);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = modexp_items_dev(ctx, *M, count, db, de, (uint32_t)(exp_bytes / 4), dout))) return rc; }
-    return io.finish(out, dout, count * w);
+    ChunkedIo io;
+    io.add_in(base, w); io.add_in(exp, exp_bytes); io.add_out(out, w);
+    io.align = resident_groups(ctx, *M);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* o) {
+        return modexp_items_dev(ctx, *M, n, in[0], in[1], (uint32_t)(exp_bytes / 4), o[0]); });
     GUARD_END(ctx)
 }
 
@@ -389,13 +458,11 @@ int pgpu_modexp_shared(pgpu_ctx* ctx, int modsel, size_t count, const void* base
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
     const BigU e = BigU::from_be(exp_be, exp_len);
-    HostIo io(ctx);
     const size_t w = (size_t)M->sh.S * 4;
-    uint32_t* db = io.in(0, base, count * w);
-    uint32_t* dout = io.out(2, count * w);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = modexp_shared_dev(ctx, *M, count, db, e, dout))) return rc; }
-    return io.finish(out, dout, count * w);
+    ChunkedIo io;
+    io.add_in(base, w); io.add_out(out, w);
+    io.align = resident_groups(ctx, *M);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* o) { return modexp_shared_dev(ctx, *M, n, in[0], e, o[0]); });
     GUARD_END(ctx)
 }
 
@@ -406,14 +473,11 @@ int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const vo
     if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_modmul: modulus not available for this key");
     if (count == 0) return PGPU_OK;
     int rc; if ((rc = set_device(ctx))) return rc;
-    HostIo io(ctx);
     const size_t w = (size_t)M->sh.S * 4;
-    uint32_t* da = io.in(0, a, count * w);
-    uint32_t* db = io.in(1, b, count * w);
-    uint32_t* dout = io.out(2, count * w);
-    if (io.rc) return io.rc;
-    { TimedScope ts(ctx); if ((rc = modmul_dev(ctx, *M, count, da, db, dout))) return rc; }
-    return io.finish(out, dout, count * w);
+    ChunkedIo io;
+    io.add_in(a, w); io.add_in(b, w); io.add_out(out, w);
+    io.align = resident_groups(ctx, *M);
+    return run_chunked(ctx, count, io, [&](size_t n, const uint32_t* const* in, uint32_t* const* o) { return modmul_dev(ctx, *M, n, in[0], in[1], o[0]); });
     GUARD_END(ctx)
 }
 
@@ -835,6 +899,41 @@ int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids,
     int rc; if ((rc = set_device(ctx))) return rc;
     TimedScope ts(ctx);
     return combine_dev(ctx, count, k, ids, (const uint32_t*)decs, (uint32_t*)m, share_stride);
+    GUARD_END(ctx)
+}
+
+int pgpu_combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, const uint8_t* ok,
+                              void* m, uint8_t* item_ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids) && (count == 0 || (decs && ok && m)), "pgpu_combine_verified_dev: null argument");
+    REQUIRE(ctx, share_stride == 0 || share_stride >= count, "pgpu_combine_verified_dev: share_stride must be at least count");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    size_t failed = 0;
+    if ((rc = combine_verified_dev(ctx, count, k, ids, (const uint32_t*)decs, share_stride, ok, (uint32_t*)m, item_ok, &failed))) return rc;
+    if (failed) return fail(ctx, PGPU_ERR_THRESHOLD, "Threshold not meet for " + std::to_string(failed) + " of " + std::to_string(count) + " ciphertexts");
+    return PGPU_OK;
+    GUARD_END(ctx)
+}
+
+int pgpu_combine_verified(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, const uint8_t* ok, void* m, uint8_t* item_ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 0 && (k == 0 || ids) && (count == 0 || k == 0 || (decs && ok)) && (count == 0 || m), "pgpu_combine_verified: null argument");
+    if (count == 0) return PGPU_OK;
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w2 = (size_t)ctx->m_n2.sh.S * 4, wn = ctx->wn * 4;
+    uint32_t* dd = io.in(0, k ? decs : (const void*)m, std::max<size_t>(count * (size_t)k, 1) * (k ? w2 : 1));
+    uint32_t* dok = io.in(1, k ? (const void*)ok : (const void*)m, std::max<size_t>(count * (size_t)k, 1));
+    uint32_t* dm = io.out(2, count * wn);
+    uint32_t* dit = io.out(3, count);
+    if (io.rc) return io.rc;
+    size_t failed = 0;
+    { TimedScope ts(ctx); if ((rc = combine_verified_dev(ctx, count, k, ids, dd, count, (const uint8_t*)dok, dm, (uint8_t*)dit, &failed))) return rc; }
+    if (item_ok) CU(ctx, cudaMemcpyAsync(item_ok, dit, count, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = io.finish(m, dm, count * wn))) return rc;
+    if (failed) return fail(ctx, PGPU_ERR_THRESHOLD, "Threshold not meet for " + std::to_string(failed) + " of " + std::to_string(count) + " ciphertexts");
+    return PGPU_OK;
     GUARD_END(ctx)
 }
 

@@ -818,6 +818,65 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
     return PGPU_OK;
 }
 
+// CombinePartialDecryptionsZKP (thresholdkey.go:164-172) for a batch.  The reference filters PER CIPHERTEXT: share j's
+// partial decryption of ciphertext i takes part iff its proof verified (ok[j*count + i] != 0).  Ciphertexts are grouped by
+// their set of surviving shares -- one CombinePartialDecryptions per distinct set, a single one when every proof holds --
+// and a ciphertext left with fewer than `threshold` shares gets a zero plaintext and item_ok = 0 where the reference
+// returns "Threshold not meet" for it.  *n_failed counts those.
+int combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, size_t share_stride, const uint8_t* ok,
+                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed) {
+    if (share_stride == 0) share_stride = count;
+    if (n_failed) *n_failed = 0;
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "CombinePartialDecryptionsZKP: no threshold key loaded");
+    if (k < 0 || k > 64) return fail(ctx, PGPU_ERR_ARG, "CombinePartialDecryptionsZKP: at most 64 shares per call");
+    if (count == 0) return PGPU_OK;
+    const uint32_t S = ctx->m_n2.sh.S;
+    const size_t h = ctx->wn;
+    std::vector<uint8_t> hok((size_t)k * count);
+    CU(ctx, cudaMemcpyAsync(hok.data(), ok, hok.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::map<uint64_t, std::vector<uint32_t>> groups;
+    for (size_t i = 0; i < count; ++i) {
+        uint64_t mask = 0;
+        for (int j = 0; j < k; ++j) if (hok[(size_t)j * count + i]) mask |= 1ull << j;
+        groups[mask].push_back((uint32_t)i);
+    }
+    const uint64_t full = k == 64 ? ~0ull : ((1ull << k) - 1);
+    std::vector<uint8_t> hitem(count, 1);
+    int rc;
+    size_t failed = 0;
+    if (groups.size() == 1 && groups.begin()->first == full) {
+        if ((rc = combine_dev(ctx, count, k, ids, decs, m_out, share_stride))) return rc;
+    } else {
+        CU(ctx, cudaMemsetAsync(m_out, 0, count * h * 4, ctx->stream));
+        for (auto& g : groups) {
+            std::vector<int> gids;
+            std::vector<int> gj;
+            for (int j = 0; j < k; ++j) if (g.first >> j & 1) { gids.push_back(ids[j]); gj.push_back(j); }
+            const std::vector<uint32_t>& idx = g.second;
+            if ((int)gids.size() < ctx->tk_w) {                                                    // thresholdkey.go:78-80
+                for (uint32_t i : idx) hitem[i] = 0;
+                failed += idx.size();
+                continue;
+            }
+            const size_t ng = idx.size();
+            DEVBUF(didx, ctx, ng); DEVBUF(packed, ctx, gids.size() * ng * S); DEVBUF(mg, ctx, ng * h);
+            if ((rc = upload(ctx, didx.p, idx))) return rc;
+            for (size_t jj = 0; jj < gj.size(); ++jj)
+                CU(ctx, gather_launch(decs + (size_t)gj[jj] * share_stride * S, S, didx.p, 1, packed.p + jj * ng * S, (uint32_t)ng, ctx->stream));
+            if ((rc = combine_dev(ctx, ng, (int)gids.size(), gids.data(), packed.p, mg.p, ng))) return rc;
+            CU(ctx, scatter_launch(mg.p, (uint32_t)h, didx.p, m_out, (uint32_t)ng, ctx->stream));
+            ctx->launches += gj.size() + 1;
+        }
+    }
+    if (item_ok) {
+        CU(ctx, cudaMemcpyAsync(item_ok, hitem.data(), count, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));          // hitem leaves scope
+    }
+    if (n_failed) *n_failed = failed;
+    return PGPU_OK;
+}
+
 // Encrypted dot product prod c[i]^k[i] (ConstMult + Add, operations.go:11-29,58-64) by Pippenger's bucket method: per
 // window of w bits every ciphertext is multiplied into the bucket of its digit (ONE multiplication per item and window,
 // no squarings); the buckets are private to a resident group, so the pass is race free and uniform.  Per pass the group
@@ -909,5 +968,83 @@ int HostIo::finish(void* host, const uint32_t* dev, size_t bytes) {
 }
 
 int set_device(pgpu_ctx* ctx) { CU(ctx, cudaSetDevice(ctx->device)); return PGPU_OK; }
+
+size_t resident_groups(const pgpu_ctx* ctx, const ModCtx& m) {
+    return (size_t)ctx->sms * (size_t)std::max(m.blocks_per_sm, 1) * (VM_BLOCK_THREADS / std::max(m.sh.tpi, 1));
+}
+
+// Items per chunk: whole rounds of the persistent grid (`align` resident groups), about 2^17 items (64 MB of 512-byte
+// records: large enough for full PCIe bandwidth, small enough that at least four chunks overlap in a 2^20 batch);
+// batches of up to two grids go in one piece.  PGPU_CHUNK_ITEMS overrides (0 = never chunk).
+size_t chunk_items(size_t count, size_t align) {
+    static const long forced = [] { const char* e = getenv("PGPU_CHUNK_ITEMS"); return e ? atol(e) : -1L; }();
+    if (forced == 0) return count;
+    if (forced > 0) return std::min((size_t)forced, count);        // tests: exact size, ragged against the grid
+    align = std::max<size_t>(align, 1);
+    if (count <= std::max(2 * align, (size_t)32768)) return count;
+    const size_t target = (size_t)1 << 17;
+    const size_t chunk = ((target + align - 1) / align) * align;
+    return std::min(chunk, count);
+}
+
+static int chunk_streams(pgpu_ctx* ctx) {
+    if (ctx->s_in) return PGPU_OK;
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_cmp[b], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+    }
+    return PGPU_OK;
+}
+
+int run_chunked(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
+                const std::function<int(size_t, const uint32_t* const*, uint32_t* const*)>& fn) {
+    if (count == 0) return PGPU_OK;
+    int rc;
+    if ((rc = chunk_streams(ctx))) return rc;
+    const size_t chunk = chunk_items(count, io.align);
+    const size_t n_chunks = (count + chunk - 1) / chunk;
+    const int n_buf = n_chunks > 1 ? 2 : 1;
+    // staging: slot b*5 + i for input i, b*5 + 3 + o for output o of buffer set b
+    uint32_t* din[2][ChunkedIo::MAX_IN] = {};
+    uint32_t* dout[2][ChunkedIo::MAX_OUT] = {};
+    for (int b = 0; b < n_buf; ++b) {
+        for (int i = 0; i < io.n_in; ++i) { void* d; if ((rc = stage(ctx, b * 5 + i, chunk * io.in_w[i], &d))) return rc; din[b][i] = (uint32_t*)d; }
+        for (int o = 0; o < io.n_out; ++o) { void* d; if ((rc = stage(ctx, b * 5 + 3 + o, chunk * io.out_w[o], &d))) return rc; dout[b][o] = (uint32_t*)d; }
+    }
+    auto items_of = [&](size_t k) { return std::min(chunk, count - k * chunk); };
+    auto h2d = [&](size_t k) -> int {
+        const int b = (int)(k & 1);
+        CU(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[b], 0));      // chunk k-2 (or whatever ran before this call) has consumed these inputs
+        for (int i = 0; i < io.n_in; ++i)
+            CU(ctx, cudaMemcpyAsync(din[b][i], (const uint8_t*)io.in[i] + k * chunk * io.in_w[i], items_of(k) * io.in_w[i], cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+        return PGPU_OK;
+    };
+    // anything already enqueued on the context's stream (a previous call's kernels reading the staging slots) comes first
+    CU(ctx, cudaEventRecord(ctx->ev_cmp[0], ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev_cmp[1], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[0], 0));
+    if ((rc = h2d(0))) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream);
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const int b = (int)(k & 1);
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (k >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));          // chunk k-2's results have left
+        if ((rc = fn(items_of(k), din[b], dout[b]))) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); cudaStreamSynchronize(ctx->stream); return rc; }
+        CU(ctx, cudaEventRecord(ctx->ev_cmp[b], ctx->stream));
+        if (k + 1 < n_chunks && (rc = h2d(k + 1))) return rc;
+        CU(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[b], 0));
+        for (int o = 0; o < io.n_out; ++o)
+            CU(ctx, cudaMemcpyAsync((uint8_t*)io.out[o] + k * chunk * io.out_w[o], dout[b][o], items_of(k) * io.out_w[o], cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+    }
+    if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_valid = true; }
+    CU(ctx, cudaStreamSynchronize(ctx->s_out));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PGPU_OK;
+}
 
 }  // namespace pgpu

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -117,9 +118,20 @@ struct pgpu_ctx {
     void* d_stage[16] = {};                 // 0-9: host-buffer staging (HostIo); 12-15: scratch of the device-side ops
     size_t stage_bytes[16] = {};
 
+    // chunked host path (ChunkedIo): copy streams and the events that order chunk k's H2D, kernels and D2H
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_cmp[2] = {}, ev_out[2] = {};
+
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+};
+
+// device buffer handle of the C ABI (pgpu_buf_alloc): owned by the context it was allocated on
+struct pgpu_buf {
+    pgpu_ctx* ctx = nullptr;
+    void* ptr = nullptr;
+    size_t bytes = 0;
 };
 
 namespace pgpu {
@@ -167,6 +179,24 @@ struct HostIo {
     uint32_t* out(int slot, size_t bytes);
     int finish(void* host, const uint32_t* dev, size_t bytes);
 };
+
+// Chunked, double-buffered host path of the blocking entry points whose items are independent: chunk k's kernels run
+// while chunk k+1 is copied in and chunk k-1 is copied out (three streams), and the staging memory is two chunks
+// instead of the whole batch.  With pageable host memory the copies block the calling thread, so the loop issues the
+// next H2D before the previous D2H (software pipelining) -- the kernels still overlap both.
+struct ChunkedIo {
+    static constexpr int MAX_IN = 3, MAX_OUT = 2;
+    const void* in[MAX_IN] = {};   size_t in_w[MAX_IN] = {};   int n_in = 0;     // host pointers, bytes per item
+    void* out[MAX_OUT] = {};       size_t out_w[MAX_OUT] = {}; int n_out = 0;
+    size_t align = 1;              // chunk sizes are multiples of this (resident groups of the kernel's persistent grid)
+    void add_in(const void* p, size_t w) { in[n_in] = p; in_w[n_in++] = w; }
+    void add_out(void* p, size_t w) { out[n_out] = p; out_w[n_out++] = w; }
+};
+size_t chunk_items(size_t count, size_t align);
+// fn(n, din, dout): enqueue the operation for n items on ctx->stream (device pointers of the chunk)
+int run_chunked(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
+                const std::function<int(size_t, const uint32_t* const*, uint32_t* const*)>& fn);
+size_t resident_groups(const pgpu_ctx* ctx, const ModCtx& m);
 
 bool pick_shape(size_t limbs, Shape& out);
 int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v);
@@ -218,6 +248,8 @@ int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const
 int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
                          const uint32_t* z, uint8_t* ok);
 int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out, size_t share_stride = 0);
+int combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, size_t share_stride, const uint8_t* ok,
+                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed);
 int set_device(pgpu_ctx* ctx);
 
 // ---- protocols.cu: level 2, alternative encryption, randomness extraction, nested operations, DDLEQ

@@ -16,10 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUITES = ["tests/test_gpu_golden.py", "tests/test_gpu_level2_ddleq.py", "tests/test_gpu_parity.py"]
 
 
-def _run(env_extra, select=None):
+def _run(env_extra, select=None, suites=SUITES):
     env = dict(os.environ)
     env.update(env_extra)
-    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + SUITES
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + list(suites)
     if select:
         cmd += ["-k", select]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
@@ -29,16 +29,16 @@ def _run(env_extra, select=None):
 
 def test_every_width_on_the_fp64_pipe():
     out = _run({"PGPU_SHAPE_32": "4,5,fp64", "PGPU_SHAPE_64": "4,10,fp64", "PGPU_SHAPE_96": "4,15,fp64",
-                "PGPU_SHAPE_128": "8,10,fp64", "PGPU_SHAPE_192": "8,15,fp64"})
+                "PGPU_SHAPE_128": "8,10,fp64", "PGPU_SHAPE_192": "8,15,fp64"},
+               select="golden or level2_encrypt or ddleq_prove or encrypt_decrypt_parity or partial_decrypt_parity or zkp_prove_verify or carry_chain or sub_and")
     assert " passed" in out
 
 
 def test_alternate_fp64_shapes():
-    out = _run({"PGPU_SHAPE_64": "8,5,fp64", "PGPU_SHAPE_96": "8,8,fp64", "PGPU_SHAPE_192": "16,8,fp64"},
-               select="golden or level2 or partial or encrypt")
+    out = _run({"PGPU_SHAPE_64": "8,5,fp64", "PGPU_SHAPE_96": "8,8,fp64", "PGPU_SHAPE_192": "16,8,fp64"}, suites=["tests/test_gpu_golden.py"])
     assert " passed" in out
 
 
 def test_every_width_on_the_integer_pipe():
-    out = _run({"PGPU_NO_FP64": "1"}, select="golden or encrypt or partial or zkp or decrypt")
+    out = _run({"PGPU_NO_FP64": "1"}, select="golden or encrypt_decrypt_parity or partial_decrypt_parity or carry_chain")
     assert " passed" in out

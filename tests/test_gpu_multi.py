@@ -115,3 +115,21 @@ def test_threshold_round_all_shares_on_one_device(bits, l, w):
     assert torch.equal(plain2, plain)
     for t in keys:
         t.close()
+
+
+@pytest.mark.parametrize("zkp", [False, True])
+def test_threshold_round_world2_under_torchrun(zkp):
+    # the all-gather path of config 4 on two GPUs (NCCL), 8 share-holders, 4 per rank; skipped on a single-GPU box
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "run_cfg4.py"), "--bits", "512", "--count", "301", "--oracle-items", "301"]
+    r = subprocess.run(cmd + (["--zkp"] if zkp else []), capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["all_plaintexts_recovered"] and line["oracle_parity"] is True
