@@ -215,7 +215,8 @@ def config4_leg(args, dist, rank, world, local, dev, barrier, max_over_ranks):
             "ms": total_ms, "ciphertexts_per_s": count / (total_ms * 1e-3), "partial_decryptions_per_s": l * count / (total_ms * 1e-3),
             "phases_ms": ph, "all_gather_share_of_step": ph["all_gather"] / total_ms if total_ms else None,
             "all_gather_bytes_per_gpu": {"sent": k * count * (w2 + 32 + t0.w_z), "received": l * count * (w2 + 32 + t0.w_z)},
-            "shares_verified": len(keep.get("ids", [])), "all_plaintexts_recovered": bad == 0.0,
+            "all_proofs_verified_on_rank0": bool(keep["ok"].all().item()) if keep.get("ok") is not None else None,
+            "all_plaintexts_recovered": bad == 0.0,
             "oracle_parity": {"items": ns, "fields": "c_i, E, Z of share-holder 1 against oracle/gmp_ref.c", "equal": bool(par)},
             "pdec_program": {"limbs": S3, "sqr": q3, "mul": m3, "mac32_per_item": mont_macs(S3, q3, m3)},
             "kernel": t0.kernel_shape(1),

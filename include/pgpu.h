@@ -262,6 +262,26 @@ int pgpu_combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids
 int pgpu_pdec_zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const void* c, const void* dec, const void* e,
                                    const void* z, uint8_t* ok);
 
+/* ---- several devices of one process: BASELINE config 4 (SURVEY.md 8b "Threading", 8e) -------------- */
+/* One context per device, each holding one share of the SAME threshold key (pgpu_ctx_set_threshold with its id and
+ * share).  pgpu_multi_create builds one NCCL communicator per device (ncclCommInitAll; NCCL is loaded at this call with
+ * dlopen("libnccl.so.2") and reported as PGPU_ERR_NCCL when absent).  The handle borrows the contexts: destroy it first. */
+typedef struct pgpu_multi pgpu_multi;
+int pgpu_multi_create(pgpu_multi** out, pgpu_ctx* const* ctxs, int n);
+int pgpu_multi_destroy(pgpu_multi* m);
+int pgpu_multi_size(const pgpu_multi* m);
+const char* pgpu_multi_last_error(const pgpu_multi* m);
+/* One threshold-decryption round over host buffers: c = count n2-width ciphertext records (read by every device);
+ * zkp_r = NULL (PartialDecrypt only, thresholdkey.go:192-201 + :149-161) or one pointer per context to count n2-width r
+ * records (PartialDecryptionWithZKP :225-255, VerifyProof :278-311, CombinePartialDecryptionsZKP :164-172 with its
+ * per-ciphertext filter).  Device g computes its share's partial decryptions (and proofs) of ALL ciphertexts, one
+ * ncclAllGather per field lands [share][ciphertext] on every device, device g verifies and combines ciphertext slice g.
+ * plain = count n-width records; item_ok (may be NULL) = 0 where fewer than `threshold` proofs verified, in which case the
+ * call returns PGPU_ERR_THRESHOLD after filling the rest.  Blocking; one host thread per device inside. */
+int pgpu_multi_threshold_round(pgpu_multi* m, size_t count, const void* c, const void* const* zkp_r, void* plain, uint8_t* item_ok);
+/* device milliseconds of the last round per phase (max over the devices): pdec, prove, all-gather, verify, combine */
+int pgpu_multi_last_phases_ms(const pgpu_multi* m, float* out5);
+
 /* ---- introspection used by bench.py ------------------------------------ */
 /* number of kernels this context has launched so far */
 int pgpu_ctx_launch_count(const pgpu_ctx* ctx, uint64_t* launches);

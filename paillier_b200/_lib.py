@@ -101,6 +101,12 @@ SIGNATURES = {
     "pgpu_combine_strided_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _sz, _p]),
     "pgpu_pdec_zkp_verify_dev": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
     "pgpu_pdec_zkp_verify_multi_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p, _p]),
+    "pgpu_multi_create": (C.c_int, [C.POINTER(_p), C.POINTER(_p), C.c_int]),
+    "pgpu_multi_destroy": (C.c_int, [_p]),
+    "pgpu_multi_size": (C.c_int, [_p]),
+    "pgpu_multi_last_error": (C.c_char_p, [_p]),
+    "pgpu_multi_threshold_round": (C.c_int, [_p, _sz, _p, C.POINTER(_p), _p, _p]),
+    "pgpu_multi_last_phases_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
     "pgpu_ctx_launch_count": (C.c_int, [_p, C.POINTER(C.c_uint64)]),
     "pgpu_ctx_program_cost": (C.c_int, [_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_ctx_kernel_shape": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -270,6 +270,7 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
             ev["all_gather"][1].record(stream)
             # ---- VerifyProof of every share for this rank's ciphertext slice
             ids = list(range(1, shares + 1))
+            ok = None
             ev["verify"][0].record(stream)
             if zkp_r is not None and n > 0:
                 rows = lambda buf, w: torch.cat([buf[(s * count + lo) * w:(s * count + hi) * w] for s in range(shares)])
@@ -278,27 +279,71 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
                 # (named tensors: a temporary would hand its memory back to torch's allocator before the kernels ran)
                 v_c, v_dec, v_e, v_z = c_dev[lo * w2:hi * w2].repeat(shares), rows(g_dec, w2), rows(g_e, 32), rows(g_z, wz)
                 check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(v_c), vp(v_dec), vp(v_e), vp(v_z), vp(ok)), t0._ctx)
-                verdict = ok.view(shares, n).all(dim=1)
             ev["verify"][1].record(stream)
-            if zkp_r is not None and n > 0:
-                ids = [s + 1 for s in range(shares) if bool(verdict[s].item())]
-            # ---- Combine the slice in place out of the gathered buffer
+            # ---- Combine the slice in place out of the gathered buffer; with proofs the reference's per-ciphertext filter
+            # (CombinePartialDecryptionsZKP, thresholdkey.go:164-172) picks the shares whose proof holds
             out = torch.empty(max(n, 1) * wn, dtype=torch.uint8, device=dev)
+            item_ok = torch.ones(max(n, 1), dtype=torch.uint8, device=dev)
+            idarr = (C.c_int * shares)(*ids)
             ev["combine"][0].record(stream)
             if n > 0:
-                if ids == list(range(1, shares + 1)):
-                    base, stride = g_dec[lo * w2:], count
+                base = g_dec[lo * w2:]
+                if ok is None:
+                    check(lib.pgpu_combine_strided_dev(t0._ctx, n, shares, idarr, vp(base), count, vp(out)), t0._ctx)
                 else:
-                    picked = [g_dec[((i - 1) * count + lo) * w2:((i - 1) * count + hi) * w2] for i in ids]
-                    base, stride = (torch.cat(picked) if picked else g_dec[:0]), n
-                idarr = (C.c_int * max(len(ids), 1))(*ids)
-                check(lib.pgpu_combine_strided_dev(t0._ctx, n, len(ids), idarr, vp(base), max(stride, n), vp(out)), t0._ctx)
+                    rc = lib.pgpu_combine_verified_dev(t0._ctx, n, shares, idarr, vp(base), count, vp(ok), vp(out), vp(item_ok))
+                    if rc not in (0, 6):              # PGPU_ERR_THRESHOLD: some ciphertexts lack valid shares, flagged in item_ok
+                        check(rc, t0._ctx)
             ev["combine"][1].record(stream)
         stream.synchronize()
         if keep is not None:
             keep["dec"], keep["e"], keep["z"], keep["ids"] = g_dec, g_e if zkp_r is not None else None, g_z if zkp_r is not None else None, ids
+            keep["ok"], keep["item_ok"] = ok, item_ok[:n]
     finally:
         for t in tsks:
             check(lib.pgpu_ctx_set_stream(t._ctx, None), t._ctx)
     phases = {name: a.elapsed_time(b) for name, (a, b) in ev.items()}
     return out[:n * wn], (lo, hi), phases
+
+
+class LibThresholdGroup:
+    """pgpu_multi_* (csrc/multi.cu): the threshold round of BASELINE config 4 inside the library, one ThresholdSecretKey
+    context per device of THIS process, NCCL communicators made with ncclCommInitAll.  This is what the Go drop-in calls
+    (one cgo call per round); `gpu_threshold_round_shares` above is the one-process-per-GPU form used under torchrun."""
+
+    def __init__(self, tsks):
+        from ._lib import check, lib
+        self.tsks = list(tsks)
+        arr = (C.c_void_p * len(self.tsks))(*[t._ctx for t in self.tsks])
+        self._h = C.c_void_p()
+        check(lib.pgpu_multi_create(C.byref(self._h), arr, len(self.tsks)))
+
+    def round(self, c, zkp_r=None):
+        """c: count n2-width ciphertext records (numpy uint8); zkp_r: one array of count n2-width r records per share-holder
+        or None -> (plaintext records, per-ciphertext flags, device milliseconds per phase)"""
+        import numpy as np
+        from ._lib import PGPU_ERR_THRESHOLD, PGPU_OK, PgpuError, lib
+        t0 = self.tsks[0]
+        c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)
+        count = c.size // t0.w_n2
+        plain = np.zeros(count * t0.w_n, dtype=np.uint8)
+        item_ok = np.zeros(count, dtype=np.uint8)
+        rp = None
+        if zkp_r is not None:
+            zkp_r = [np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in zkp_r]
+            if len(zkp_r) != len(self.tsks) or any(r.size != count * t0.w_n2 for r in zkp_r):
+                raise ValueError("one array of count n2-width records per share-holder")
+            rp = (C.c_void_p * len(zkp_r))(*[r.ctypes.data for r in zkp_r])
+        rc = lib.pgpu_multi_threshold_round(self._h, count, c.ctypes.data_as(C.c_void_p), rp, plain.ctypes.data_as(C.c_void_p),
+                                            item_ok.ctypes.data_as(C.c_void_p))
+        if rc not in (PGPU_OK, PGPU_ERR_THRESHOLD):
+            raise PgpuError(rc, (lib.pgpu_multi_last_error(self._h) or b"").decode("utf-8", "replace"))
+        ph = (C.c_float * 5)()
+        lib.pgpu_multi_last_phases_ms(self._h, ph)
+        return plain, item_ok, dict(zip(("pdec", "prove", "all_gather", "verify", "combine"), [float(x) for x in ph]))
+
+    def close(self):
+        from ._lib import lib
+        if self._h:
+            lib.pgpu_multi_destroy(self._h)
+            self._h = C.c_void_p()

@@ -133,3 +133,43 @@ def test_threshold_round_world2_under_torchrun(zkp):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["all_plaintexts_recovered"] and line["oracle_parity"] is True
+
+
+def _lib_group(bits, n_dev, l, w):
+    import random as _r
+    from paillier_b200.multi import LibThresholdGroup
+    p, q = synth.load_key(f"threshold_{bits}")
+    keys = []
+    for d in range(n_dev):
+        ks = ThresholdKeyGenerator(bits, l, w, rng=_r.Random(13)).with_safe_primes(p, q).GenerateKeys(device=d)
+        keys.append(ks[d])
+        for k in ks:
+            if k is not ks[d]:
+                k.close()
+    return p * q, keys, LibThresholdGroup(keys)
+
+
+@pytest.mark.parametrize("zkp", [False, True])
+def test_library_threshold_round(zkp):
+    # pgpu_multi_* (csrc/multi.cu): single-process ncclCommInitAll over the visible devices, one share-holder per device.
+    # On a one-GPU box this is a 1-of-1 key with a one-rank communicator; with more GPUs the all-gather crosses NVLink.
+    import numpy as np
+    from oracle import gmp_ref as G
+    n_dev = min(torch.cuda.device_count(), 8)
+    w = max(1, (5 * n_dev + 7) // 8)
+    n, keys, grp = _lib_group(512, n_dev, n_dev, w)
+    t0 = keys[0]
+    count = 257
+    m = synth.plaintexts(count, n, t0.w_n)
+    c = t0.encrypt_with_r_records(m, synth.randomness(count, n, t0.w_n))
+    rs = [synth.random_records(count, t0.w_n2, (n * n).bit_length() - 1, stream=40 + k.ID) for k in keys] if zkp else None
+    plain, item_ok, phases = grp.round(c, rs)
+    assert np.array_equal(plain, m) and item_ok.all()
+    assert set(phases) == {"pdec", "prove", "all_gather", "verify", "combine"}
+    # same plaintexts as the per-share host calls combined by pgpu_combine, and the partial decryptions are libgmp's
+    decs = [k.partial_decrypt_records(c) for k in keys]
+    assert np.array_equal(decs[0], G.partial_decrypt(n, keys[0].Share, n_dev, c, t0.w_n2))
+    assert np.array_equal(t0.combine_records([k.ID for k in keys], np.concatenate(decs)), plain)
+    grp.close()
+    for k in keys:
+        k.close()

@@ -446,3 +446,36 @@ def test_carry_chain_edge_values():
     for r in (1, n - 1, 2):
         assert sk.DecryptBatch(sk.EncryptWithRBatch(ms, [r] * len(ms))) == ms
     sk.close()
+
+
+def test_combine_zkp_filters_per_ciphertext():
+    # CombinePartialDecryptionsZKP (thresholdkey.go:164-172) drops a share PER CIPHERTEXT: one bad proof must not remove its
+    # server from the other ciphertexts.  6 servers, threshold 4, 12 ciphertexts:
+    #   ciphertext 2: server 1's proof tampered          -> combined from the 5 others
+    #   ciphertext 5: servers 2 and 3 tampered           -> combined from 4
+    #   ciphertext 7: servers 1, 2, 3 tampered           -> 3 < threshold: "Threshold not meet" for this one only
+    from paillier_b200._lib import PgpuError, PGPU_ERR_THRESHOLD
+    n, keys, okeys = _threshold_setup("threshold_512", 6, 4, 512)
+    tk = keys[0]
+    count = 12
+    ms = from_records(synth.plaintexts(count, n, tk.w_n), tk.w_n)
+    cs = [c.C for c in tk.EncryptWithRBatch(ms, from_records(synth.randomness(count, n, tk.w_n), tk.w_n))]
+    rs = from_records(synth.random_records(count, tk.w_n2, (n * n).bit_length() - 1, stream=23), tk.w_n2)
+    proofs = [list(k.PartialDecryptionWithZKPBatch(cs, rs)) for k in keys]
+    def tamper(server, item):
+        p = proofs[server][item]
+        proofs[server][item] = type(p)(p.ID, p.Decryption, p.E, p.Z + 1, p.C)
+    tamper(0, 2); tamper(1, 5); tamper(2, 5); tamper(0, 7); tamper(1, 7); tamper(2, 7)
+    got = tk.CombinePartialDecryptionsZKPBatch(proofs, strict=False)
+    assert got[7] is None
+    assert [g for i, g in enumerate(got) if i != 7] == [m for i, m in enumerate(ms) if i != 7]
+    with pytest.raises(PgpuError) as ei:
+        tk.CombinePartialDecryptionsZKPBatch(proofs)
+    assert ei.value.code == PGPU_ERR_THRESHOLD and "1 of 12" in str(ei.value)
+    # the oracle, ciphertext by ciphertext
+    otk = R.threshold_public_key(okeys[0])
+    for i in (2, 5):
+        shares = [R.PartialDecryptionZKP(ID=p[i].ID, Decryption=p[i].Decryption, Key=otk, E=p[i].E, Z=p[i].Z, C=p[i].C) for p in proofs]
+        assert R.combine_partial_decryptions_zkp(otk, shares) == ms[i]
+    for k in keys:
+        k.close()
