@@ -172,30 +172,38 @@ func (g *GPUContext) ConstMultBatch(cts []*Ciphertext, ks []*gmp.Int) ([]*Cipher
 	for i, ct := range cts {
 		vals[i] = ct.C
 	}
-	c, k := toRecords(vals, g.wN2), toRecords(kk, kBytes)
-	o := make([]byte, len(cts)*g.wN2)
-	if err := gpuErr(g.ctx, C.pgpu_const_mult(g.ctx, C.size_t(len(cts)), ptr(c), ptr(k), C.size_t(kBytes), ptr(o))); err != nil {
+	_, w, modsel, err := g.batchLevel(cts, "ConstMultBatch")
+	if err != nil {
+		return nil, err
+	}
+	c, k := toRecords(vals, w), toRecords(kk, kBytes)
+	o := make([]byte, len(cts)*w)
+	if err := gpuErr(g.ctx, C.pgpu_modexp(g.ctx, modsel, C.size_t(len(cts)), ptr(c), ptr(k), C.size_t(kBytes), ptr(o))); err != nil {
 		return nil, err
 	}
 	out := make([]*Ciphertext, len(cts))
-	for i, v := range fromRecords(o, g.wN2) {
+	for i, v := range fromRecords(o, w) {
 		out[i] = &Ciphertext{v, cts[i].Level, cts[i].EncMethod}
 	}
 	return out, nil
 }
 
-// AddBatch = PublicKey.Add(cts...) (operations.go:11-29) as one tree reduction.
+// AddBatch = PublicKey.Add(cts...) (operations.go:11-29) as one tree reduction; modulus and level of cts[0].
 func (g *GPUContext) AddBatch(cts []*Ciphertext) (*Ciphertext, error) {
 	vals := make([]*gmp.Int, len(cts))
 	for i, ct := range cts {
 		vals[i] = ct.C
 	}
-	c := toRecords(vals, g.wN2)
-	o := make([]byte, g.wN2)
-	if err := gpuErr(g.ctx, C.pgpu_add_reduce(g.ctx, C.size_t(len(cts)), ptr(c), ptr(o))); err != nil {
+	level, w, lv := EncLevelOne, g.wN2, C.int(1)
+	if len(cts) > 0 && cts[0].Level == EncLevelTwo {
+		level, w, lv = EncLevelTwo, g.wN3, C.int(2)
+	}
+	c := toRecords(vals, w)
+	o := make([]byte, w)
+	if err := gpuErr(g.ctx, C.pgpu_add_reduce_at_level(g.ctx, lv, C.size_t(len(cts)), ptr(c), ptr(o))); err != nil {
 		return nil, err
 	}
-	return &Ciphertext{fromRecords(o, g.wN2)[0], EncLevelOne, MixedEncryption}, nil
+	return &Ciphertext{fromRecords(o, w)[0], level, MixedEncryption}, nil
 }
 
 // NewGPUContext for a threshold key share (thresholdkey.go:26-42).

@@ -170,30 +170,67 @@ func (g *GPUContext) NestedDecryptBatch(cts []*Ciphertext) ([]*gmp.Int, error) {
 	return out, nil
 }
 
-func (g *GPUContext) pairwise(fn func(a, b, o []byte) C.int, as, bs []*Ciphertext) ([]*Ciphertext, error) {
+// batchLevel returns the encryption level shared by a batch (operations.go:11-64 take n^(s+1) from the ciphertext's
+// level, getModuliForLevel paillier.go:403-414): the record width, the modulus selector of the generic entry points.
+func (g *GPUContext) batchLevel(cts []*Ciphertext, what string) (EncryptionLevel, int, C.int, error) {
+	level := EncLevelOne
+	if len(cts) > 0 {
+		level = cts[0].Level
+	}
+	for _, c := range cts {
+		if c.Level != level {
+			return level, 0, 0, errors.New(what + ": one encryption level per batch")
+		}
+	}
+	if level == EncLevelOne {
+		return level, g.wN2, C.PGPU_MOD_N2, nil
+	}
+	if g.wN3 == 0 {
+		return level, 0, 0, errors.New(what + ": n^3 is wider than the built kernel shapes")
+	}
+	return level, g.wN3, C.PGPU_MOD_N3, nil
+}
+
+// AddPairs = N x PublicKey.Add(a_i, b_i) (operations.go:11-29): modulus and level of a_i, one level per batch.
+func (g *GPUContext) AddPairs(as, bs []*Ciphertext) ([]*Ciphertext, error) {
 	if len(as) != len(bs) {
 		return nil, errors.New("pairs")
 	}
-	a, b := toRecords(ctValues(as), g.wN2), toRecords(ctValues(bs), g.wN2)
-	o := make([]byte, len(as)*g.wN2)
-	if err := gpuErr(g.ctx, fn(a, b, o)); err != nil {
+	level, w, modsel, err := g.batchLevel(as, "AddPairs")
+	if err != nil {
 		return nil, err
 	}
-	return wrapCts(fromRecords(o, g.wN2), EncLevelOne, MixedEncryption), nil
+	a, b := toRecords(ctValues(as), w), toRecords(ctValues(bs), w)
+	o := make([]byte, len(as)*w)
+	if err := gpuErr(g.ctx, C.pgpu_modmul(g.ctx, modsel, C.size_t(len(as)), ptr(a), ptr(b), ptr(o))); err != nil {
+		return nil, err
+	}
+	return wrapCts(fromRecords(o, w), level, MixedEncryption), nil
 }
 
-// AddPairs = N x PublicKey.Add(a_i, b_i) (operations.go:11-29).
-func (g *GPUContext) AddPairs(as, bs []*Ciphertext) ([]*Ciphertext, error) {
-	return g.pairwise(func(a, b, o []byte) C.int {
-		return C.pgpu_add_pairs(g.ctx, C.size_t(len(as)), ptr(a), ptr(b), ptr(o))
-	}, as, bs)
-}
-
-// SubPairs = N x PublicKey.Sub(a_i, b_i) (operations.go:32-55).
+// SubPairs = N x PublicKey.Sub(a_i, b_i) (operations.go:32-55): modulus and level of a_i, one level per batch.
 func (g *GPUContext) SubPairs(as, bs []*Ciphertext) ([]*Ciphertext, error) {
-	return g.pairwise(func(a, b, o []byte) C.int {
-		return C.pgpu_sub_pairs(g.ctx, C.size_t(len(as)), ptr(a), ptr(b), ptr(o))
-	}, as, bs)
+	if len(as) != len(bs) {
+		return nil, errors.New("pairs")
+	}
+	level, w, modsel, err := g.batchLevel(as, "SubPairs")
+	if err != nil {
+		return nil, err
+	}
+	a, b := toRecords(ctValues(as), w), toRecords(ctValues(bs), w)
+	o := make([]byte, len(as)*w)
+	if level == EncLevelOne {
+		err = gpuErr(g.ctx, C.pgpu_sub_pairs(g.ctx, C.size_t(len(as)), ptr(a), ptr(b), ptr(o)))
+	} else if len(as) > 0 {
+		inv := make([]byte, len(b))
+		if err = gpuErr(g.ctx, C.pgpu_modinv(g.ctx, modsel, C.size_t(len(as)), ptr(b), ptr(inv))); err == nil {
+			err = gpuErr(g.ctx, C.pgpu_modmul(g.ctx, modsel, C.size_t(len(as)), ptr(a), ptr(inv), ptr(o)))
+		}
+	}
+	if err != nil {
+		return nil, err
+	}
+	return wrapCts(fromRecords(o, w), level, MixedEncryption), nil
 }
 
 // DotProduct = Add(ConstMult(c_i, k_i)...) with 64-bit scalars in one call (operations.go:11-29,58-64).

@@ -274,41 +274,64 @@ public:
         check(pgpu_encrypt_with_r(ctx_, ms.size(), m.data(), r.data(), c.data()));
         return wrap(detail::from_records(c, w_n2), EncLevelOne, RegularEncryption);
     }
-    // N x PublicKey.ConstMult with unsigned scalars (operations.go:58-64); k = 0 yields 1 like gmp's Exp
+    // operations.go:11-64 take n^(s+1) from the level of the (first) ciphertext (getModuliForLevel, paillier.go:403-414)
+    int batch_level(const std::vector<Ciphertext>& cts, const char* what) const {
+        const int level = cts.empty() ? (int)EncLevelOne : cts[0].Level;
+        for (const Ciphertext& c : cts)
+            if (c.Level != level) throw Error(PGPU_ERR_ARG, std::string(what) + ": one encryption level per batch");
+        return level;
+    }
+    static int level_modsel(int level) { return level == EncLevelOne ? PGPU_MOD_N2 : PGPU_MOD_N3; }
+
+    // N x PublicKey.ConstMult with unsigned scalars (operations.go:58-64) at the ciphertexts' level; k = 0 yields 1 like gmp's Exp
     std::vector<Ciphertext> ConstMultBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& ks) {
         if (cts.size() != ks.size()) throw Error(PGPU_ERR_ARG, "one scalar per ciphertext");
+        const int level = batch_level(cts, "ConstMultBatch");
+        const size_t w = cipher_width(level);
         size_t kb = 4;
         for (const Int& k : ks) kb = std::max(kb, (k.size() + 3) / 4 * 4);
-        auto c = detail::to_records(values(cts), w_n2), k = detail::to_records(ks, kb);
-        std::vector<uint8_t> o(cts.size() * w_n2);
-        check(pgpu_const_mult(ctx_, cts.size(), c.data(), k.data(), kb, o.data()));
-        auto out = wrap(detail::from_records(o, w_n2), EncLevelOne, RegularEncryption);
-        for (size_t i = 0; i < out.size(); ++i) { out[i].Level = cts[i].Level; out[i].EncMethod = cts[i].EncMethod; }
+        auto c = detail::to_records(values(cts), w), k = detail::to_records(ks, kb);
+        std::vector<uint8_t> o(cts.size() * w);
+        check(pgpu_modexp(ctx_, level_modsel(level), cts.size(), c.data(), k.data(), kb, o.data()));
+        auto out = wrap(detail::from_records(o, w), (EncryptionLevel)level, RegularEncryption);
+        for (size_t i = 0; i < out.size(); ++i) out[i].EncMethod = cts[i].EncMethod;
         return out;
     }
-    // PublicKey.Add(cts...) (operations.go:11-29)
+    // PublicKey.Add(cts...) (operations.go:11-29): modulus and level of cts[0]
     Ciphertext AddBatch(const std::vector<Ciphertext>& cts) {
-        auto c = detail::to_records(values(cts), w_n2);
-        std::vector<uint8_t> o(w_n2);
-        check(pgpu_add_reduce(ctx_, cts.size(), cts.empty() ? nullptr : c.data(), o.data()));
-        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption)[0];
+        const int level = cts.empty() ? (int)EncLevelOne : cts[0].Level;
+        const size_t w = cipher_width(level);
+        auto c = detail::to_records(values(cts), w);
+        std::vector<uint8_t> o(w);
+        check(pgpu_add_reduce_at_level(ctx_, level == EncLevelOne ? 1 : 2, cts.size(), cts.empty() ? nullptr : c.data(), o.data()));
+        return wrap(detail::from_records(o, w), (EncryptionLevel)level, MixedEncryption)[0];
     }
-    // N x PublicKey.Sub(a_i, b_i) (operations.go:32-55)
+    // N x PublicKey.Sub(a_i, b_i) (operations.go:32-55): modulus and level of a_i, one level per batch
     std::vector<Ciphertext> SubPairs(const std::vector<Ciphertext>& a, const std::vector<Ciphertext>& b) {
         if (a.size() != b.size()) throw Error(PGPU_ERR_ARG, "pairs");
-        auto ra = detail::to_records(values(a), w_n2), rb = detail::to_records(values(b), w_n2);
-        std::vector<uint8_t> o(a.size() * w_n2);
-        check(pgpu_sub_pairs(ctx_, a.size(), ra.data(), rb.data(), o.data()));
-        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
+        const int level = batch_level(a, "SubPairs");
+        const size_t w = cipher_width(level);
+        auto ra = detail::to_records(values(a), w), rb = detail::to_records(values(b), w);
+        std::vector<uint8_t> o(a.size() * w);
+        if (level == EncLevelOne) {
+            check(pgpu_sub_pairs(ctx_, a.size(), ra.data(), rb.data(), o.data()));
+        } else if (!a.empty()) {
+            std::vector<uint8_t> inv(rb.size());
+            check(pgpu_modinv(ctx_, PGPU_MOD_N3, a.size(), rb.data(), inv.data()));
+            check(pgpu_modmul(ctx_, PGPU_MOD_N3, a.size(), ra.data(), inv.data(), o.data()));
+        }
+        return wrap(detail::from_records(o, w), (EncryptionLevel)level, MixedEncryption);
     }
 
-    // N x PublicKey.Add(a_i, b_i) (operations.go:11-29)
+    // N x PublicKey.Add(a_i, b_i) (operations.go:11-29): modulus and level of a_i, one level per batch
     std::vector<Ciphertext> AddPairs(const std::vector<Ciphertext>& a, const std::vector<Ciphertext>& b) {
         if (a.size() != b.size()) throw Error(PGPU_ERR_ARG, "pairs");
-        auto ra = detail::to_records(values(a), w_n2), rb = detail::to_records(values(b), w_n2);
-        std::vector<uint8_t> o(a.size() * w_n2);
-        check(pgpu_add_pairs(ctx_, a.size(), ra.data(), rb.data(), o.data()));
-        return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
+        const int level = batch_level(a, "AddPairs");
+        const size_t w = cipher_width(level);
+        auto ra = detail::to_records(values(a), w), rb = detail::to_records(values(b), w);
+        std::vector<uint8_t> o(a.size() * w);
+        check(pgpu_modmul(ctx_, level_modsel(level), a.size(), ra.data(), rb.data(), o.data()));
+        return wrap(detail::from_records(o, w), (EncryptionLevel)level, MixedEncryption);
     }
     // Add(ConstMult(c_i, k_i)...) in one call: the encrypted dot product with 64-bit scalars
     Ciphertext DotProduct(const std::vector<Ciphertext>& cts, const std::vector<uint64_t>& ks) {

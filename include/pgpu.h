@@ -109,6 +109,9 @@ int pgpu_const_mult(pgpu_ctx* ctx, size_t count, const void* c, const void* k, s
 
 /* PublicKey.Add over a whole batch (operations.go:11-29): out = prod c[i] mod n^2. */
 int pgpu_add_reduce(pgpu_ctx* ctx, size_t count, const void* c, void* out);
+/* Add over a batch of ciphertexts of `level` (1: mod n^2, 2: mod n^3; operations.go:11-29 takes the modulus of
+ * cts[0].Level): records of the n2- / n3-width */
+int pgpu_add_reduce_at_level(pgpu_ctx* ctx, int level, size_t count, const void* c, void* out);
 /* PublicKey.Add(a[i], b[i]) element-wise: out[i] = a[i]*b[i] mod n^2. */
 int pgpu_add_pairs(pgpu_ctx* ctx, size_t count, const void* a, const void* b, void* out);
 /* Encrypted dot product: out = prod c[i]^k[i] mod n^2 (ConstMult + Add fused). */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "pgpu_decrypt": (C.c_int, [_p, _sz, _p, _p]),
     "pgpu_const_mult": (C.c_int, [_p, _sz, _p, _p, _sz, _p]),
     "pgpu_add_reduce": (C.c_int, [_p, _sz, _p, _p]),
+    "pgpu_add_reduce_at_level": (C.c_int, [_p, C.c_int, _sz, _p, _p]),
     "pgpu_add_pairs": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_dot_u64": (C.c_int, [_p, _sz, _p, _p, _p]),
     "pgpu_partial_decrypt": (C.c_int, [_p, _sz, _p, _p]),

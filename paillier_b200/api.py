@@ -288,32 +288,67 @@ class PublicKey:
                 rs[i] = draw()
         return self.EncryptWithRBatch(ms, rs)
 
+    # operations.go:11-64 take the modulus from the level of the (first) ciphertext: n^2 at level 1, n^3 at level 2
+    def _level_modulus(self, level: int):
+        """-> (modulus selector, record width, modulus) of getModuliForLevel(level) (paillier.go:403-414)"""
+        if level == ENC_LEVEL_ONE:
+            return MOD_N2, self.w_n2, self.N ** 2
+        if level == ENC_LEVEL_TWO:
+            if not self.w_n3:
+                raise PgpuError(_lib.PGPU_ERR_UNSUPPORTED, "n^3 is wider than the built kernel shapes")
+            return MOD_N3, self.w_n3, self.N ** 3
+        raise ValueError("unsupported encryption level")
+
+    @staticmethod
+    def _one_level(cts: Sequence[Ciphertext], what: str) -> int:
+        levels = {c.Level for c in cts}
+        if len(levels) > 1:
+            raise ValueError(f"{what}: one encryption level per batch")
+        return levels.pop() if levels else ENC_LEVEL_ONE
+
     def ConstMultBatch(self, cts: Sequence[Ciphertext], ks: Sequence[int]) -> List[Ciphertext]:
-        """N x PublicKey.ConstMult (operations.go:58-64); k <= 0 gives 1 like gmp's Exp"""
+        """N x PublicKey.ConstMult (operations.go:58-64) at the ciphertexts' level; k <= 0 gives 1 like gmp's Exp"""
         if len(cts) != len(ks):
             raise ValueError("one scalar per ciphertext")
+        modsel, width, mod = self._level_modulus(self._one_level(cts, "ConstMultBatch"))
         kmax = max([int(k) for k in ks] + [1])
         k_bytes = max(4, 4 * ((kmax.bit_length() + 31) // 32))
-        out = self.const_mult_records(to_records([c.C for c in cts], self.w_n2),
-                                      to_records([max(int(k), 0) for k in ks], k_bytes), k_bytes)
-        return [Ciphertext(v, ct.Level, ct.EncMethod) for v, ct in zip(from_records(out, self.w_n2), cts)]
+        base = to_records([c.C % mod for c in cts], width)
+        out = np.empty(len(cts) * width, dtype=np.uint8)
+        if len(cts):
+            check(lib.pgpu_modexp(self._ctx, modsel, len(cts), _ptr(base), _ptr(to_records([max(int(k), 0) for k in ks], k_bytes)), k_bytes, _ptr(out)),
+                  self._ctx)
+        return [Ciphertext(v, ct.Level, ct.EncMethod) for v, ct in zip(from_records(out, width), cts)]
 
     def AddBatch(self, cts: Sequence[Ciphertext]) -> Ciphertext:
-        """PublicKey.Add(cts...) (operations.go:11-29)"""
-        out = self.add_reduce_records(to_records([c.C for c in cts], self.w_n2))
-        return Ciphertext(from_records(out, self.w_n2)[0], ENC_LEVEL_ONE, MIXED)
+        """PublicKey.Add(cts...) (operations.go:11-29): the modulus and the result's level are those of cts[0]"""
+        level = cts[0].Level if len(cts) else ENC_LEVEL_ONE
+        modsel, width, mod = self._level_modulus(level)
+        rec = to_records([c.C % mod for c in cts], width)
+        out = np.empty(width, dtype=np.uint8)
+        check(lib.pgpu_add_reduce_at_level(self._ctx, level, len(cts), _ptr(rec) if len(cts) else None, _ptr(out)), self._ctx)
+        return Ciphertext(from_records(out, width)[0], level, MIXED)
 
     def AddPairs(self, a: Sequence[Ciphertext], b: Sequence[Ciphertext]) -> List[Ciphertext]:
-        """N x PublicKey.Add(a_i, b_i)"""
-        out = self.add_pairs_records(to_records([c.C for c in a], self.w_n2), to_records([c.C for c in b], self.w_n2))
-        return [Ciphertext(v, ENC_LEVEL_ONE, MIXED) for v in from_records(out, self.w_n2)]
+        """N x PublicKey.Add(a_i, b_i): modulus and level of a_i (one level per batch)"""
+        level = self._one_level(a, "AddPairs")
+        modsel, width, mod = self._level_modulus(level)
+        out = self.modmul_records(modsel, to_records([c.C % mod for c in a], width), to_records([c.C % mod for c in b], width), width)
+        return [Ciphertext(v, level, MIXED) for v in from_records(out, width)]
 
     def SubPairs(self, a: Sequence[Ciphertext], b: Sequence[Ciphertext]) -> List[Ciphertext]:
-        """N x PublicKey.Sub(a_i, b_i) (operations.go:32-55)"""
-        ar, br = to_records([c.C for c in a], self.w_n2), to_records([c.C for c in b], self.w_n2)
-        out = np.empty(len(a) * self.w_n2, dtype=np.uint8)
-        check(lib.pgpu_sub_pairs(self._ctx, len(a), _ptr(ar), _ptr(br), _ptr(out)), self._ctx)
-        return [Ciphertext(v, ENC_LEVEL_ONE, MIXED) for v in from_records(out, self.w_n2)]
+        """N x PublicKey.Sub(a_i, b_i) (operations.go:32-55): modulus and level of a_i (one level per batch)"""
+        level = self._one_level(a, "SubPairs")
+        modsel, width, mod = self._level_modulus(level)
+        ar, br = to_records([c.C % mod for c in a], width), to_records([c.C % mod for c in b], width)
+        out = np.empty(len(a) * width, dtype=np.uint8)
+        if level == ENC_LEVEL_ONE:
+            check(lib.pgpu_sub_pairs(self._ctx, len(a), _ptr(ar), _ptr(br), _ptr(out)), self._ctx)
+        elif len(a):
+            inv = np.empty_like(br)
+            check(lib.pgpu_modinv(self._ctx, modsel, len(a), _ptr(br), _ptr(inv)), self._ctx)
+            check(lib.pgpu_modmul(self._ctx, modsel, len(a), _ptr(ar), _ptr(inv), _ptr(out)), self._ctx)
+        return [Ciphertext(v, level, MIXED) for v in from_records(out, width)]
 
     def ModInverseBatch(self, xs: Sequence[int], modsel: int = MOD_N2) -> List[int]:
         """N x gmp.Int.ModInverse(x, mod); raises PgpuError(PGPU_ERR_NOT_INVERTIBLE) for a non-unit"""
@@ -592,10 +627,17 @@ class ThresholdPublicKey(PublicKey):
         ids = {p.ID for p in proofs}
         if len(ids) != 1:
             raise ValueError("VerifyProofBatch: one server id per batch")
-        ok = self.verify_proof_records(proofs[0].ID, to_records([p.C for p in proofs], self.w_n2),
-                                       to_records([p.Decryption for p in proofs], self.w_n2),
-                                       to_records([p.E for p in proofs], 32), to_records([p.Z for p in proofs], self.w_z))
-        return [bool(x) for x in ok]
+        # A value that does not fit its record cannot come from an honest prover (E is a SHA-256 digest, Z < 2^(8 w_z) for
+        # every r < n^2; c and c_i are residues mod n^2 in the reference's exponentiations): the reference's VerifyProof
+        # just returns false for such a proof, so it is answered without the GPU instead of raising.
+        n2 = self.N ** 2
+        fits = [0 <= p.E < (1 << 256) and 0 <= p.Z < (1 << (8 * self.w_z)) and p.C >= 0 and p.Decryption >= 0 for p in proofs]
+        val = lambda p, f, v: v if f else 0
+        ok = self.verify_proof_records(proofs[0].ID, to_records([val(p, f, p.C % n2) for p, f in zip(proofs, fits)], self.w_n2),
+                                       to_records([val(p, f, p.Decryption % n2) for p, f in zip(proofs, fits)], self.w_n2),
+                                       to_records([val(p, f, p.E) for p, f in zip(proofs, fits)], 32),
+                                       to_records([val(p, f, p.Z) for p, f in zip(proofs, fits)], self.w_z))
+        return [bool(x) and f for x, f in zip(ok, fits)]
 
     def combine_records(self, ids: Sequence[int], decs) -> np.ndarray:
         """decs: len(ids) consecutive batches of n2-width records (share j's batch first to last)"""

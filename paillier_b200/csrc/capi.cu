@@ -151,6 +151,9 @@ int pgpu_ctx_set_threshold(pgpu_ctx* ctx, int total_servers, int threshold, int 
     GUARD_BEGIN
     REQUIRE(ctx, ctx != nullptr, "null context");
     REQUIRE(ctx, total_servers >= 1 && total_servers <= 1000, "bad TotalNumberOfDecryptionServers");
+    REQUIRE(ctx, threshold >= 1 && threshold <= total_servers, "Threshold must be between 1 and TotalNumberOfDecryptionServers");
+    REQUIRE(ctx, !share_be || (id >= 1 && id <= total_servers), "the share-holder's id must be between 1 and TotalNumberOfDecryptionServers");
+    REQUIRE(ctx, id >= 0 && id <= total_servers, "bad server id");
     int rc; if ((rc = set_device(ctx))) return rc;
     ctx->tk_l = total_servers; ctx->tk_w = threshold; ctx->tk_id = id;
     ctx->tk_delta = BigU::factorial((unsigned)total_servers);
@@ -496,6 +499,23 @@ int pgpu_add_reduce(pgpu_ctx* ctx, size_t count, const void* c, void* out) {
     if (io.rc) return io.rc;
     { TimedScope ts(ctx); if ((rc = prod_dev(ctx, ctx->m_n2, count, dc, dout))) return rc; }
     return io.finish(out, dout, w2);
+    GUARD_END(ctx)
+}
+
+int pgpu_add_reduce_at_level(pgpu_ctx* ctx, int level, size_t count, const void* c, void* out) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && out && (count == 0 || c), "pgpu_add_reduce_at_level: null argument");
+    REQUIRE(ctx, level == 1 || level == 2, "pgpu_add_reduce_at_level: level must be 1 or 2");
+    ModCtx* M = select_mod(ctx, level == 1 ? PGPU_MOD_N2 : PGPU_MOD_N3);
+    if (!M) return fail(ctx, PGPU_ERR_UNSUPPORTED, "pgpu_add_reduce_at_level: modulus not available for this key");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    HostIo io(ctx);
+    const size_t w = (size_t)M->sh.S * 4;
+    uint32_t* dc = io.in(0, c ? c : out, std::max<size_t>(count, 1) * w);
+    uint32_t* dout = io.out(1, w);
+    if (io.rc) return io.rc;
+    { TimedScope ts(ctx); if ((rc = prod_dev(ctx, *M, count, dc, dout))) return rc; }
+    return io.finish(out, dout, w);
     GUARD_END(ctx)
 }
 

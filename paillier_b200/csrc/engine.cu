@@ -485,9 +485,15 @@ int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_
 
 // out[i] = base[i]^e mod M, one exponent for the whole batch (sliding window compiled on the host)
 int modexp_shared_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const BigU& e, uint32_t* out) {
+    // Ad-hoc exponents (a combine compiles one program per share and subset: 2*lambda_i) live in a small LRU of their own, so
+    // a workload with many distinct exponents never evicts the long-lived programs (mul, fix, powi, xr-*, ...) of prog_cache.
+    constexpr size_t POWS_CAPACITY = 256;
     const std::string key = "pows:" + std::to_string(M.sh.S) + ":" + e.hex();
     Program* P = cached_program(ctx, key);
-    if (!P) {
+    if (P) {
+        ctx->pows_lru.remove(key);
+        ctx->pows_lru.push_back(key);
+    } else {
         Program np;
         np.emit(OP_LDI, 0);
         np.emit(OP_MULC, K_R2); np.n_mul++;
@@ -496,12 +502,18 @@ int modexp_shared_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc&
         np.emit(OP_STO, 0);
         int rc = program_upload(ctx, np);
         if (rc) return rc;
-        if (ctx->prog_cache.size() > 64) {
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-            for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
-            ctx->prog_cache.clear();
+        while (ctx->pows_lru.size() >= POWS_CAPACITY) {
+            const std::string victim = ctx->pows_lru.front();
+            ctx->pows_lru.pop_front();
+            auto it = ctx->prog_cache.find(victim);
+            if (it != ctx->prog_cache.end()) {
+                CU(ctx, cudaStreamSynchronize(ctx->stream));        // a queued launch may still read the victim's ops
+                if (it->second.d_ops) cudaFree(it->second.d_ops);
+                ctx->prog_cache.erase(it);
+            }
         }
         P = &(ctx->prog_cache[key] = np);
+        ctx->pows_lru.push_back(key);
     }
     IoDesc ins[1] = {base};
     return run_vm(ctx, M, *P, count, ins, 1, out, M.sh.S, M.sh.S);
@@ -684,7 +696,15 @@ int sha_dev(pgpu_ctx* ctx, size_t count, int n_seg, const uint32_t* const* seg, 
     return PGPU_OK;
 }
 
-uint32_t z_limbs(const pgpu_ctx* ctx) { return (uint32_t)ctx->m_n2.sh.S + 16; }   // Z = r + E*delta*share < 2^(32*(S+16))
+// Limbs of a Z record: Z = r + E*delta*share (thresholdkey.go:313-317) with r < n^2, E < 2^256, share < n*m < n^2 and
+// delta = l!, i.e. fewer than 2*bitlen(n) + bitlen(l!) + 257 bits.  Never less than the S + 16 limbs of small l (so the
+// width of existing records is unchanged up to 57 servers); grows with l! beyond (the reference's tests use 100 servers).
+uint32_t z_limbs(const pgpu_ctx* ctx) {
+    const uint32_t S = (uint32_t)ctx->m_n2.sh.S;
+    const size_t bits = 2 * ctx->n.bitlen() + ctx->tk_delta.bitlen() + 257;
+    const uint32_t need = (uint32_t)((bits + 31) / 32);
+    return std::max(S + 16, (need + 3) / 4 * 4);
+}
 
 // ZKP transcript hash shared by prover and verifier: c^4 and c_i^2 enter unreduced (thresholdkey.go:241,248,319-326)
 int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* dec, uint32_t* e_out) {
@@ -706,7 +726,7 @@ int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t
     ModCtx& M = ctx->m_n2;
     const uint32_t S = M.sh.S;
     const BigU k = ctx->tk_delta * ctx->tk_share;
-    if (k.v.size() + 8 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "share too large for the Z record");
+    if (k.v.size() + 8 + 1 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_ARG, "PartialDecryptionWithZKP: the share is not below n^2");
     int rc;
     if (!dec_given && (rc = pdec_dev(ctx, count, c, dec))) return rc;
     DEVBUF(c4r, ctx, count * S); DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(v, ctx, S);
@@ -808,6 +828,11 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
     const uint32_t* cprime = pos.p;
     if (have_neg) {                                                          // negative exponent: ModInverse (exp, :132-138)
         if ((rc = modinv_batch_dev(ctx, M, count, neg.p, t.p, bad.p))) return rc;
+        uint32_t first_bad = 0xffffffffu;
+        CU(ctx, cudaMemcpyAsync(&first_bad, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (first_bad != 0xffffffffu)           // ModInverse of a non-unit is undefined in the reference (thresholdkey.go:132-138)
+            return fail(ctx, PGPU_ERR_NOT_INVERTIBLE, "CombinePartialDecryptions: a partial decryption of item " + std::to_string(first_bad) + " is not a unit mod n^2");
         if (have_pos) { if ((rc = modmul_dev(ctx, M, count, pos.p, t.p, pos.p))) return rc; }
         else cprime = t.p;
     }

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <list>
 #include <map>
 #include <string>
 #include <vector>
@@ -112,6 +113,7 @@ struct pgpu_ctx {
     pgpu::FixedTable fix_h1, fix_h2, fix_v;
     pgpu::Program prog_alt1, prog_alt2;
     std::map<std::string, pgpu::Program> prog_cache;
+    std::list<std::string> pows_lru;         // least recently used first: keys of the ad-hoc shared-exponent programs ("pows:...") in prog_cache
 
     // scratch
     uint32_t* d_table = nullptr; size_t table_limbs = 0;

@@ -234,3 +234,37 @@ def test_nested_randomize_three_routes(keys):
         os.environ.pop("PGPU_NO_DUAL_EXP", None)
         os.environ.pop("PGPU_NO_CRT_PROTOCOLS", None)
         pk.close()
+
+
+def test_homomorphic_ops_follow_the_ciphertext_level(keys):
+    # operations.go:11-64 take n^(s+1) from the level of the (first) ciphertext: Add / Sub / ConstMult at level 2 work
+    # mod n^3 and keep the level (the mirrors used n^2 regardless)
+    sk, osk, opk, rnd = keys
+    n, n2, n3 = sk.N, sk.N ** 2, sk.N ** 3
+    count = 7
+    ms = [rnd.randrange(n2) for _ in range(count)]
+    ks = [0, 1, 2, rnd.randrange(1 << 64), rnd.randrange(1 << 200), n - 1, 3]
+    cts = sk.EncryptWithRAtLevelBatch(ms, _units(rnd, n, count), ENC_LEVEL_TWO)
+    other = sk.EncryptWithRAtLevelBatch(ms[::-1], _units(rnd, n, count), ENC_LEVEL_TWO)
+    o2 = lambda c: R.Ciphertext(c.C, R.ENC_LEVEL_TWO, c.EncMethod)
+    cm = sk.ConstMultBatch(cts, ks)
+    assert [(c.C, c.Level) for c in cm] == [(R.const_mult(opk, o2(c), k).C, ENC_LEVEL_TWO) for c, k in zip(cts, ks)]
+    assert sk.DecryptBatch(cm[1:]) == [m * k % n2 for m, k in zip(ms[1:], ks[1:])]
+    tot = sk.AddBatch(cts)
+    assert (tot.C, tot.Level) == (R.add(opk, *[o2(c) for c in cts]).C, ENC_LEVEL_TWO)
+    assert sk.DecryptBatch([tot]) == [sum(ms) % n2]
+    ap = sk.AddPairs(cts, other)
+    assert [(c.C, c.Level) for c in ap] == [(R.add(opk, o2(a), o2(b)).C, ENC_LEVEL_TWO) for a, b in zip(cts, other)]
+    sp = sk.SubPairs(cts, other)
+    assert [(c.C, c.Level) for c in sp] == [(R.sub(opk, o2(a), o2(b)).C, ENC_LEVEL_TWO) for a, b in zip(cts, other)]
+    assert sk.DecryptBatch(sp) == [(a - b) % n2 for a, b in zip(ms, ms[::-1])]
+    # a level-1 batch still works mod n^2, and a batch mixing levels is refused
+    l1 = sk.EncryptWithRBatch([5, 6], _units(rnd, n, 2))
+    assert sk.AddBatch(l1).C == R.add(opk, *[R.Ciphertext(c.C) for c in l1]).C
+    with pytest.raises(ValueError):
+        sk.ConstMultBatch([cts[0], l1[0]], [1, 2])
+    with pytest.raises(ValueError):
+        sk.AddPairs([cts[0], l1[0]], [cts[1], l1[1]])
+    # Add takes the level of its first argument (operations.go:13): a level-1 value multiplied in mod n^3
+    mixed = sk.AddBatch([cts[0], l1[0]])
+    assert (mixed.C, mixed.Level) == (R.add(opk, o2(cts[0]), R.Ciphertext(l1[0].C)).C, ENC_LEVEL_TWO)

@@ -81,8 +81,31 @@ def test_combine_with_100_servers():
     with pytest.raises(PgpuError) as ei:
         keys[0].CombinePartialDecryptionsBatch(shares[:49])
     assert ei.value.code == PGPU_ERR_THRESHOLD
+    # proofs with 100 servers: delta = 100! has 525 bits, Z no longer fits the record of a small key (the record
+    # is sized from the key now); transcripts against the oracle, verification, an oversized E / Z is simply not a proof
+    zr = [rnd.randrange(n * n) for _ in cs]
+    zk = keys[60].PartialDecryptionWithZKPBatch(cs, zr)
+    for got, c, r in zip(zk, cs, zr):
+        o = R.partial_decryption_with_zkp(okeys[60], c, r)
+        assert (got.ID, got.Decryption, got.E, got.Z) == (o.ID, o.Decryption, o.E, o.Z)
+    assert keys[0].VerifyProofBatch(zk) == [True] * 3
+    huge = [type(zk[0])(zk[0].ID, zk[0].Decryption, zk[0].E, zk[0].Z + (1 << (8 * keys[0].w_z)), zk[0].C),
+            type(zk[1])(zk[1].ID, zk[1].Decryption, zk[1].E + (1 << 256), zk[1].Z, zk[1].C), zk[2]]
+    assert keys[0].VerifyProofBatch(huge) == [False, False, True]
+    zks = [keys[i].PartialDecryptionWithZKPBatch(cs, zr) for i in range(50)]
+    assert keys[0].CombinePartialDecryptionsZKPBatch(zks) == msgs
     for k in keys:
         k.close()
+
+
+def test_threshold_key_arguments_are_validated():
+    # pgpu_ctx_set_threshold: 1 <= threshold <= total, 1 <= id <= total for a share-holder
+    from paillier_b200.api import ThresholdSecretKey
+    from paillier_b200._lib import PGPU_ERR_ARG
+    for l, w, i in ((3, 0, 1), (3, 4, 1), (3, 2, 0), (3, 2, 4)):
+        with pytest.raises(PgpuError) as ei:
+            ThresholdSecretKey(3 * 5 * 7 * 11 + 2, l, w, 4, [4] * l, ID=i, Share=5)
+        assert ei.value.code == PGPU_ERR_ARG
 
 
 def test_zkp_and_verify_decryption():
