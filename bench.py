@@ -573,6 +573,54 @@ def main() -> None:
         breakdown["alt_enc_e2e_per_s"] = world * acount / max_over_ranks(adt)
         breakdown["alt_enc_items"] = acount
         apk.close()
+        # ---- light operations (1-3 multiplications per record): device-resident rate against the multiplier and HBM roofs,
+        # and end to end through the chunked host-buffer ABI (pinned memory) against the measured PCIe rate of this box
+        lcount_ = max(1, min(count, 1 << 19))
+        pin_big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dev_big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pcie = {}
+        for name, (dst, src) in (("h2d", (dev_big, pin_big)), ("d2h", (pin_big, dev_big))):
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); dst.copy_(src, non_blocking=True); e1.record(stream); e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            pcie[name + "_gbs"] = (256 << 20) / (best * 1e-3) / 1e9
+        del pin_big, dev_big
+        light = {"items": lcount_, "pcie": pcie}
+        rn_dev = torch.empty(lcount_ * w_n2, dtype=torch.uint8, device=dev)
+        check(lib.pgpu_encrypt_with_r_sk_dev(sk._ctx, lcount_, vp(torch.zeros(lcount_ * w_n, dtype=torch.uint8, device=dev)), vp(r_dev), vp(rn_dev)), sk._ctx)
+        o_dev = torch.empty(lcount_ * w_n2, dtype=torch.uint8, device=dev)
+        rn_host = rn_dev.cpu().pin_memory()
+        o_host = torch.empty(lcount_ * w_n2, dtype=torch.uint8).pin_memory()
+        hpl = lambda t: C.c_void_p(t.data_ptr())
+        ops = {
+            "add_pairs": (lambda: lib.pgpu_add_pairs_dev(sk._ctx, lcount_, vp(c_dev), vp(rn_dev), vp(o_dev)),
+                          lambda: lib.pgpu_add_pairs(sk._ctx, lcount_, hpl(c_host_l), hpl(rn_host), hpl(o_host)), 2 * w_n2, w_n2, 2),
+            "encrypt_with_rn": (lambda: lib.pgpu_encrypt_with_rn_dev(sk._ctx, lcount_, vp(m_dev), vp(rn_dev), vp(o_dev)),
+                                lambda: lib.pgpu_encrypt_with_rn(sk._ctx, lcount_, hpl(m_host), hpl(rn_host), hpl(o_host)), w_n + w_n2, w_n2, 3),
+        }
+        c_host_l = c_dev[:lcount_ * w_n2].cpu().pin_memory()
+        mulmac = 2.0 * S_ * S_ + S_ if (S_ := sk.program_cost(0)[0]) else 0
+        for name, (fdev, fhost, in_b, out_b, nmul) in ops.items():
+            for timed in (False, True):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); check(fdev(), sk._ctx); e1.record(stream)
+                barrier()
+            dms = max_over_ranks(e0.elapsed_time(e1))
+            for timed in (False, True):
+                barrier()
+                t0 = time.perf_counter(); check(fhost(), sk._ctx); hdt = time.perf_counter() - t0
+            hdt = max_over_ranks(hdt)
+            bound = max(lcount_ * in_b / (pcie["h2d_gbs"] * 1e9), lcount_ * out_b / (pcie["d2h_gbs"] * 1e9))
+            light[name] = {"device_items_per_s": lcount_ / (dms * 1e-3), "device_tmac32": nmul * mulmac * lcount_ / (dms * 1e-3) / 1e12,
+                           "device_hbm_gbs": lcount_ * (in_b + out_b) / (dms * 1e-3) / 1e9, "montgomery_muls_per_item": nmul,
+                           "e2e_items_per_s": lcount_ / hdt, "e2e_gbs_in": lcount_ * in_b / hdt / 1e9, "e2e_gbs_out": lcount_ * out_b / hdt / 1e9,
+                           "e2e_frac_of_pcie_bound": bound / hdt}
+        assert torch.equal(o_host, o_dev.cpu()), "host and device paths of EncryptWithRn differ"
+        breakdown["light_ops"] = light
+        del rn_dev, o_dev, rn_host, o_host, c_host_l
         # level 2 (mod n^3): EncryptWithRAtLevel + Decrypt (CRT over p^3, q^3) through the host-buffer ABI
         lcount = max(1, min(count, 1 << 15))
         l2m = torch.from_numpy(synth.random_records(lcount, w_n2, (n * n).bit_length() - 1, seed, stream=51)).pin_memory()
@@ -742,6 +790,12 @@ def main() -> None:
             pm = breakdown["pdec_program"]["mac32_per_item"]
             a = 2.1 * pm * breakdown["pdec_zkp_prove_per_s"] / world / 1e12
             other["pdec_zkp_prove 2048-bit n (~2.1 x the partial-decrypt work per item)"] = {"achieved": a, "frac": (a / peak_t) if peak_t else None}
+        for name in ("add_pairs", "encrypt_with_rn"):
+            lo_ = breakdown.get("light_ops", {}).get(name)
+            if lo_:
+                other["%s (device-resident, %d Montgomery multiplications per record)" % (name, lo_["montgomery_muls_per_item"])] = {
+                    "achieved": lo_["device_tmac32"], "frac": (lo_["device_tmac32"] / peak_t) if peak_t else None,
+                    "hbm_gbs": lo_["device_hbm_gbs"], "hbm_frac": (lo_["device_hbm_gbs"] / mp["hbm_gbs"]) if mp.get("hbm_gbs") else None}
         roofline = {
             "bound": "imad", "kernel": "%s (EncryptWithR launch)" % kname(shape_n2, S), "achieved": achieved, "peak": peak_t, "unit": "TMAC32/s",
             "frac": (achieved / peak_t) if peak_t else None,

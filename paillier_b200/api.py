@@ -326,7 +326,7 @@ class PublicKey:
         modsel, width, mod = self._level_modulus(level)
         rec = to_records([c.C % mod for c in cts], width)
         out = np.empty(width, dtype=np.uint8)
-        check(lib.pgpu_add_reduce_at_level(self._ctx, level, len(cts), _ptr(rec) if len(cts) else None, _ptr(out)), self._ctx)
+        check(lib.pgpu_add_reduce_at_level(self._ctx, level + 1, len(cts), _ptr(rec) if len(cts) else None, _ptr(out)), self._ctx)
         return Ciphertext(from_records(out, width)[0], level, MIXED)
 
     def AddPairs(self, a: Sequence[Ciphertext], b: Sequence[Ciphertext]) -> List[Ciphertext]:

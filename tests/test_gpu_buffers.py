@@ -97,16 +97,15 @@ sys.path.insert(0, %r)
 import numpy as np
 from oracle import gmp_ref as G
 from paillier_b200 import synth
-from paillier_b200.api import SecretKey
+from paillier_b200.api import PublicKey, SecretKey
 p, q = synth.load_key("paillier_2048"); n = p * q
 sk = SecretKey(n, p=p, q=q)
 count = 2311                                   # 10 chunks of 250 (rounded to whole grids: see chunk_items) and a ragged tail
 m = synth.plaintexts(count, n, sk.w_n); r = synth.randomness(count, n, sk.w_n)
-c = sk.encrypt_with_r_records(m, r)
+c = PublicKey.encrypt_with_r_records(sk, m, r)              # pgpu_encrypt_with_r
 assert np.array_equal(c, G.encrypt_with_r(n, m, r, sk.w_n)), "chunked EncryptWithR differs from libgmp"
 assert np.array_equal(sk.decrypt_records(c), m), "chunked Decrypt"
-c2 = sk.encrypt_with_r_sk_records(m, r) if hasattr(sk, "encrypt_with_r_sk_records") else c
-assert np.array_equal(c2, c)
+assert np.array_equal(sk.encrypt_with_r_records(m, r), c), "chunked EncryptWithR (key holder)"      # pgpu_encrypt_with_r_sk
 k = synth.scalars_u64(count)
 cm = sk.const_mult_records(c, k.view(np.uint8), 8)
 assert np.array_equal(cm, G.modexp(n * n, c, sk.w_n2, k.view(np.uint8), 8)), "chunked ConstMult"
