@@ -733,6 +733,40 @@ def main() -> None:
                   "note": "one batch split into contiguous slices, no collective on the data path; resident groups per GPU = "
                           "%d, so the last round of the persistent grid is partly idle at small slices" % sk_resident}
 
+    # ---- Add over a batch sharded across the ranks: per-rank tree product, all-gather of `world` records, one fold
+    sharded_add = None
+    if world > 1 and not args.no_extras:
+        from paillier_b200.multi import sharded_add as _sharded_add
+        acount = min(count, 1 << 18)
+        part = torch.empty(w_n2, dtype=torch.uint8, device=dev)
+        tot = torch.empty(w_n2, dtype=torch.uint8, device=dev)
+        def fold(parts):
+            check(lib.pgpu_add_reduce_dev(sk._ctx, world, vp(parts), vp(tot)), sk._ctx)
+            stream.synchronize()
+            return tot
+        for timed in (False, True):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            check(lib.pgpu_add_reduce_dev(sk._ctx, acount, vp(c_dev), vp(part)), sk._ctx)
+            stream.synchronize()
+            total_ct = _sharded_add(dist, rank, world, w_n2, part, fold)
+            e1.record(stream)
+            barrier()
+        ams = max_over_ranks(e0.elapsed_time(e1))
+        # every rank decrypts the total; it must be the sum of all ranks' plaintexts mod n
+        dsum = torch.empty(w_n, dtype=torch.uint8, device=dev)
+        check(lib.pgpu_decrypt_dev(sk._ctx, 1, vp(total_ct), vp(dsum)), sk._ctx)
+        stream.synchronize()
+        mine_sum = sum(int.from_bytes(m_host.numpy()[i * w_n:(i + 1) * w_n].tobytes(), "little") for i in range(acount)) % n
+        sums = torch.zeros(world * w_n, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(sums, torch.frombuffer(bytearray(mine_sum.to_bytes(w_n, "little")), dtype=torch.uint8).to(dev))
+        want = sum(int.from_bytes(sums[r_ * w_n:(r_ + 1) * w_n].cpu().numpy().tobytes(), "little") for r_ in range(world)) % n
+        got = int.from_bytes(dsum.cpu().numpy().tobytes(), "little")
+        assert got == want, "sharded Add: the decrypted total is not the sum of the plaintexts"
+        sharded_add = {"ciphertexts_per_gpu": acount, "ms": ams, "ciphertexts_per_s": world * acount / (ams * 1e-3),
+                       "exchange": "all-gather of %d records of %d bytes" % (world, w_n2), "decrypts_to_the_sum_of_all_plaintexts": True}
+
     # ---- BASELINE configs[3]: threshold round, 3072-bit n, 8 shares / threshold 5
     config4 = None
     if not args.no_extras and not args.no_config4 and 8 % world == 0:
@@ -860,7 +894,7 @@ def main() -> None:
                        "sharding": f"{world} independent per-GPU batches, no collective on the data path",
                        "kernels": {"n^2": kname(shape_n2, S), "p^2,q^2": kname(shape_p2, Sd)}},
             "breakdown": breakdown, "roofline": roofline, "cpu_baseline": cpu, "cpu_baselines": cpu_rows, "e2e": e2e, "clocks": clocks,
-            "strong": strong, "config4": config4,
+            "strong": strong, "sharded_add": sharded_add, "config4": config4,
             "gpu_launches": launches,
         }
         print(json.dumps(line), flush=True)

@@ -173,3 +173,25 @@ def test_library_threshold_round(zkp):
     grp.close()
     for k in keys:
         k.close()
+
+
+def test_library_threshold_round_matches_torchrun_path_on_two_gpus():
+    # pgpu_multi_* (single process, ncclCommInitAll) against the one-process-per-GPU path on the same 2-share key; skipped on
+    # a single-GPU box
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "run_cfg4.py")
+    common = ["--bits", "512", "--count", "301", "--shares", "2", "--threshold", "2", "--zkp", "--oracle-items", "64"]
+    r1 = subprocess.run([sys.executable, tool, "--impl", "lib"] + common, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r1.returncode == 0, r1.stdout[-2000:] + r1.stderr[-3000:]
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                         "--master-port", "29534", tool] + common, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-3000:]
+    for r in (r1, r2):
+        line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+        assert line["n_gpus"] == 2 and line["all_plaintexts_recovered"] and line["oracle_parity"] is True

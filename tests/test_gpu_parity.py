@@ -479,3 +479,34 @@ def test_combine_zkp_filters_per_ciphertext():
         assert R.combine_partial_decryptions_zkp(otk, shares) == ms[i]
     for k in keys:
         k.close()
+
+
+def test_dedicated_squaring_is_race_free_by_determinism(sk2048):
+    # compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer_unavailable.txt), so the shared-memory exchange of
+    # Mont::sqr (block products handed between the lanes of a group, __syncwarp() fences; 64-limb moduli = CRT Decrypt) is
+    # checked the other way: the same batch repeatedly, batches that leave 1, 2, ... 8 groups of a warp active, and the exchange
+    # switched off in a child process (PGPU_NO_SQR=1) must all give the bits libgmp gives.
+    import os
+    import subprocess
+    import sys
+    sk, osk = sk2048
+    n = sk.N
+    lam = osk.Lambda
+    count = 3001
+    m = synth.plaintexts(count, n, sk.w_n)
+    c = sk.encrypt_with_r_records(m, synth.randomness(count, n, sk.w_n))
+    ref = G.decrypt(n, lam, c[:512 * sk.w_n2], sk.w_n)
+    first = sk.decrypt_records(c)
+    assert np.array_equal(first, m) and np.array_equal(first[:512 * sk.w_n], ref)
+    for _ in range(6):
+        assert np.array_equal(sk.decrypt_records(c), first)
+    for k in (1, 2, 3, 5, 7, 8, 9, 31, 33):
+        assert np.array_equal(sk.decrypt_records(c[:k * sk.w_n2]), m[:k * sk.w_n])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = ("import sys; sys.path.insert(0, %r)\n"
+             "import numpy as np\nfrom paillier_b200 import synth\nfrom paillier_b200.api import SecretKey\n"
+             "p, q = synth.load_key('paillier_2048'); sk = SecretKey(p * q, p=p, q=q)\n"
+             "m = synth.plaintexts(3001, sk.N, sk.w_n); c = sk.encrypt_with_r_records(m, synth.randomness(3001, sk.N, sk.w_n))\n"
+             "assert np.array_equal(sk.decrypt_records(c), m)\nprint('ok')\n" % root)
+    r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, PGPU_NO_SQR="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

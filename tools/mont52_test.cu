@@ -173,6 +173,41 @@ static bool run_shape(int sms, int mod_bits) {
     CK(cudaFuncGetAttributes(&fa52, k_rate52<TPI, L, S32>)); CK(cudaFuncGetAttributes(&fa32, k_rate32<TPI32, L32>));
     fprintf(stderr, "  rate: FP64 %dx%d %.1f M mul/s (%d regs, %d blocks/SM)   IMAD %dx%d %.1f M mul/s (%d regs, %d blocks/SM)   ratio %.3f\n",
             TPI, L, r52 / 1e6, fa52.numRegs, occ52, TPI32, L32, r32 / 1e6, fa32.numRegs, occ32, r52 / r32);
+    // ---- both multipliers at once: `a` integer-pipe blocks and `b` FP64-pipe blocks per SM on two streams (do the IMAD.WIDE
+    // pipe and the FP64 + ALU pipes overlap across warps?)
+    if (getenv("MONT52_MIX")) {
+        cudaStream_t s1, s2;
+        CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
+        uint32_t* d_out2; CK(cudaMalloc(&d_out2, (size_t)grid_groups * 4 * S32 * 4));
+        const int combos[][2] = {{1, 1}, {1, 2}, {2, 1}, {1, 3}, {2, 2}};
+        for (auto& cb : combos) {
+            const int a = cb[0], b = cb[1];
+            if (a > occ32 || b > occ52) continue;
+            // multiplications per kernel in proportion to its stand-alone rate per block, so that both finish together
+            const double per_block32 = r32 / (double)(sms * occ32), per_block52 = r52 / (double)(sms * occ52);
+            const int n32 = 1500, n52 = (int)(n32 * (per_block52 / (128 / TPI)) / (per_block32 / (128 / TPI32)));
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+            double best = 1e30;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaDeviceSynchronize());
+                CK(cudaEventRecord(e0, s1));
+                CK(cudaStreamWaitEvent(s2, e0, 0));
+                k_rate32<TPI32, L32><<<sms * a, 128, 0, s1>>>(d_mod, np0, d_a, d_out, n32);
+                k_rate52<TPI, L, S32><<<sms * b, 128, 0, s2>>>(d_mod, np0, d_a, d_out2, n52);
+                CK(cudaEventRecord(e1, s2));
+                CK(cudaStreamWaitEvent(s1, e1, 0));
+                CK(cudaEventRecord(e1, s1));
+                CK(cudaEventSynchronize(e1));
+                float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (ms < best) best = ms;
+            }
+            const double muls = (double)sms * a * (128 / TPI32) * n32 + (double)sms * b * gpb * n52;
+            fprintf(stderr, "  mix: %d integer + %d FP64 blocks/SM: %.1f M mul/s combined (%.3f x the better one alone)\n", a, b, muls / (best * 1e-3) / 1e6,
+                    muls / (best * 1e-3) / std::max(r52, r32));
+        }
+        cudaFree(d_out2);
+    }
     char buf[512];
     snprintf(buf, sizeof buf, "%s{\"mod_bits\": %d, \"fp64_shape\": \"%dx%d\", \"fp64_mmul_per_s\": %.2f, \"fp64_regs\": %d, \"fp64_blocks_per_sm\": %d, "
              "\"imad_shape\": \"%dx%d\", \"imad_mmul_per_s\": %.2f, \"imad_regs\": %d, \"ratio\": %.4f, \"parity_mismatches\": %d}",

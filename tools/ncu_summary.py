@@ -1,4 +1,5 @@
-"""Summarise .ncu-rep files (ncu --set full captures) into one JSON: python tools/ncu_summary.py out.json rep1.ncu-rep [rep2 ...]
+"""Summarise .ncu-rep files (ncu --set full captures) or their `--page raw --csv` exports into one JSON:
+    python tools/ncu_summary.py out.json rep1.ncu-rep|rep1_raw.csv [...]
 Per kernel launch: duration, registers, occupancy, pipe utilisation, executed instructions per pipe, stall reasons per issue,
 DRAM bytes.  Needs `ncu` on PATH (reads the reports with --page raw --csv)."""
 import csv, io, json, subprocess, sys
@@ -16,7 +17,10 @@ STALLS = "smsp__average_warps_issue_stalled_"
 
 
 def summarise(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []

@@ -16,6 +16,57 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def main_lib(args):
+    """the same round through pgpu_multi_threshold_round: one process, one share-holder per visible GPU"""
+    import time
+    import numpy as np
+    import torch
+    from oracle import gmp_ref as G
+    from paillier_b200 import synth
+    from paillier_b200.keygen import ThresholdKeyGenerator
+    from paillier_b200.multi import LibThresholdGroup
+    n_dev = args.shares
+    if torch.cuda.device_count() < n_dev:
+        raise SystemExit(f"--impl lib needs {n_dev} visible GPUs (one share-holder per GPU)")
+    p, q = synth.load_key(f"threshold_{args.bits}")
+    n = p * q
+    keys = []
+    for d in range(n_dev):
+        ks = ThresholdKeyGenerator(args.bits, args.shares, args.threshold, rng=random.Random(5)).with_safe_primes(p, q).GenerateKeys(device=d)
+        keys.append(ks[d])
+        for k in ks:
+            if k is not ks[d]:
+                k.close()
+    t0 = keys[0]
+    count = args.count
+    m = synth.plaintexts(count, n, t0.w_n)
+    c = t0.encrypt_with_r_records(m, synth.randomness(count, n, t0.w_n))
+    zr = [synth.random_records(count, t0.w_n2, (n * n).bit_length() - 1, stream=70 + k.ID) for k in keys] if args.zkp else None
+    grp = LibThresholdGroup(keys)
+    small = min(count, 64)
+    grp.round(c[:small * t0.w_n2], [z[:small * t0.w_n2] for z in zr] if zr else None)          # warm-up
+    t_0 = time.perf_counter()
+    plain, item_ok, phases = grp.round(c, zr)
+    dt = time.perf_counter() - t_0
+    ok = bool(np.array_equal(plain, m) and item_ok.all())
+    par = None
+    if args.oracle_items:
+        ns = min(count, args.oracle_items)
+        ref = G.partial_decrypt(n, t0.Share, args.shares, c[:ns * t0.w_n2], t0.w_n2)
+        par = bool(np.array_equal(ref, t0.partial_decrypt_records(c[:ns * t0.w_n2])))
+    print(json.dumps({"workload": f"config[3] through pgpu_multi_*: {args.bits}-bit n, {args.shares} shares (threshold {args.threshold}) on {n_dev} GPU(s) "
+                                  f"of one process, PartialDecrypt{' + proofs' if args.zkp else ''} over {count} ciphertexts per share-holder",
+                      "impl": "lib", "n_gpus": n_dev, "count": count, "ms": dt * 1e3, "ciphertexts_per_s": count / dt,
+                      "partial_decryptions_per_s": args.shares * count / dt, "phases_ms": phases,
+                      "note": "ms is host wall time of the blocking call, H2D of the ciphertexts and D2H of the plaintexts included",
+                      "all_plaintexts_recovered": ok, "oracle_parity": par}), flush=True)
+    grp.close()
+    for k in keys:
+        k.close()
+    if not ok or par is False:
+        sys.exit(1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bits", type=int, default=3072, choices=[512, 2048, 3072])
@@ -24,7 +75,12 @@ def main():
     ap.add_argument("--threshold", type=int, default=5)
     ap.add_argument("--zkp", action="store_true")
     ap.add_argument("--oracle-items", type=int, default=16)
+    ap.add_argument("--impl", default="torch", choices=["torch", "lib"],
+                    help="torch: one process per GPU under torchrun (torch.distributed all-gather); lib: ONE process, pgpu_multi_* "
+                         "(ncclCommInitAll inside the library), --shares share-holders on --shares GPUs")
     args = ap.parse_args()
+    if args.impl == "lib":
+        return main_lib(args)
     import numpy as np
     import torch
     import torch.distributed as dist
