@@ -291,6 +291,66 @@ def cpu_baselines_leg(sk, n, p, q, w_n, w_n2, c_host_np, extras_keep, breakdown)
 
 
 
+def config1_leg(local):
+    """BASELINE configs[0]: 1024-bit n, KeyGen + Encrypt / Decrypt / Add round trip over 10^4 random plaintexts ON THE CPU
+    (paillier_test.go:52-63, operations_test.go:11-28).  Two CPU lines as BASELINE.md promised -- the libgmp call sequence on
+    all cores and the Python restatement on one core (a sample) -- and the same batch through the C ABI beside them."""
+    import random
+    import numpy as np
+    from oracle import gmp_ref as G
+    from oracle import paillier_ref as R
+    from paillier_b200 import synth
+    from paillier_b200.api import PublicKey, SecretKey, from_records
+    count = 10_000
+    p, q = synth.load_key("paillier_1024")
+    n, lam = p * q, (p - 1) * (q - 1)
+    w = 128
+    cores = G.cores()
+    m = synth.plaintexts(count, n, w, synth.SEED + 11)
+    r = synth.randomness(count, n, w, synth.SEED + 11)
+    t0 = time.perf_counter(); c = G.encrypt_with_r(n, m, r, w, threads=cores)
+    t1 = time.perf_counter(); d = G.decrypt(n, lam, c, w, threads=cores)
+    t2 = time.perf_counter(); tot = G.add_reduce(n * n, c, 2 * w, threads=cores)
+    t3 = time.perf_counter()
+    assert np.array_equal(d, m)
+    out = {"workload": "config[0]: 1024-bit n, 10^4 plaintexts, Encrypt + Decrypt + Add round trip", "items": count,
+           "libgmp": {"cores": cores, "enc_per_s": count / (t1 - t0), "dec_per_s": count / (t2 - t1), "add_terms_per_s": count / (t3 - t2),
+                      "round_trip_items_per_s": count / (t3 - t0)}}
+    # Python restatement (CPython ints), one core, first 200 items
+    ns = 200
+    osk, opk = R.keygen_from_primes(p, q)
+    ms, rs = from_records(m[:ns * w], w), from_records(r[:ns * w], w)
+    t0 = time.perf_counter(); ocs = [R.encrypt_with_r(opk, a, b) for a, b in zip(ms, rs)]
+    t1 = time.perf_counter(); ods = [R.decrypt(osk, ct) for ct in ocs]
+    t2 = time.perf_counter(); osum = R.add(opk, *ocs)
+    t3 = time.perf_counter()
+    assert ods == ms and [ct.C for ct in ocs] == from_records(c[:ns * 2 * w], 2 * w)
+    out["python_oracle"] = {"cores": 1, "sample": ns, "enc_per_s": ns / (t1 - t0), "dec_per_s": ns / (t2 - t1), "add_terms_per_s": ns / (t3 - t2),
+                            "round_trip_items_per_s": ns / (t3 - t0)}
+    # KeyGen (paillier.go:106-179) restated on the CPU: two 512-bit primes = 3 mod 4 by trial + Miller-Rabin (oracle's ProbablyPrime stand-in)
+    rng = random.Random(synth.SEED + 12)
+    t0 = time.perf_counter()
+    primes = []
+    while len(primes) < 2:
+        cand = rng.getrandbits(512) | (3 << 510) | 3
+        if R._is_probable_prime(cand) and cand not in primes:
+            primes.append(cand)
+    out["python_oracle"]["keygen_s"] = time.perf_counter() - t0
+    # the same batch on the GPU through the host-buffer C ABI
+    sk = SecretKey(n, p=p, q=q, device=local)
+    PublicKey.encrypt_with_r_records(sk, m[:64 * w], r[:64 * w])
+    t0 = time.perf_counter(); gc = PublicKey.encrypt_with_r_records(sk, m, r)
+    t1 = time.perf_counter(); gd = sk.decrypt_records(gc)
+    t2 = time.perf_counter(); gt = sk.add_reduce_records(gc)
+    t3 = time.perf_counter()
+    assert np.array_equal(gc, c) and np.array_equal(gd, m) and np.array_equal(gt, tot), "config 1: GPU results differ from libgmp"
+    assert R.decrypt(osk, R.Ciphertext(from_records(gt, 2 * w)[0])) == sum(from_records(m, w)) % n
+    out["b200_e2e"] = {"enc_per_s": count / (t1 - t0), "dec_per_s": count / (t2 - t1), "add_terms_per_s": count / (t3 - t2),
+                       "round_trip_items_per_s": count / (t3 - t0), "bit_exact_with_libgmp": True}
+    sk.close()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -857,6 +917,7 @@ def main() -> None:
                                              "throttling each other (profiles/r02_fp64_experiments.md)"}
         cpu = None
         cpu_rows = None
+        config1 = None
         if not args.no_extras:
             from oracle import gmp_ref as G
             cores = G.cores()
@@ -878,6 +939,7 @@ def main() -> None:
             nd = 256 * cores
             c_np = c_dev[:nd * w_n2].cpu().numpy()
             cpu_rows, ref_dot = cpu_baselines_leg(sk, n, p, q, w_n, w_n2, c_np, extras_keep, breakdown)
+            config1 = config1_leg(local)
             # the dot-product sample, recomputed on the GPU over the same terms, must equal the libgmp fold
             kd = torch.from_numpy(synth.scalars_u64(nd).view(np.int64).copy()).to(dev)
             dd = torch.empty(w_n2, dtype=torch.uint8, device=dev)
@@ -894,7 +956,7 @@ def main() -> None:
                        "sharding": f"{world} independent per-GPU batches, no collective on the data path",
                        "kernels": {"n^2": kname(shape_n2, S), "p^2,q^2": kname(shape_p2, Sd)}},
             "breakdown": breakdown, "roofline": roofline, "cpu_baseline": cpu, "cpu_baselines": cpu_rows, "e2e": e2e, "clocks": clocks,
-            "strong": strong, "sharded_add": sharded_add, "config4": config4,
+            "strong": strong, "sharded_add": sharded_add, "config4": config4, "config1": config1,
             "gpu_launches": launches,
         }
         print(json.dumps(line), flush=True)

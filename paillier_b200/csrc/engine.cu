@@ -570,8 +570,11 @@ int prod_dev(pgpu_ctx* ctx, ModCtx& M, size_t count, const uint32_t* in, uint32_
     }
     // final correction: the partial product carries W^-T (W = 2^(32*S), the radix of prod_reduce_kernel); one more
     // Montgomery multiply of the exponentiation kernel (radix R) by W^T * R restores it
-    const BigU fix = (BigU::modexp(M.W1, BigU(T), M.N) * M.R1) % M.N;
-    if ((rc = set_kconst(ctx, M, K_FIX, fix))) return rc;
+    if (M.fix_T != T + 1) {                         // the constant depends on the batch geometry only: keep it across calls
+        const BigU fix = (BigU::modexp(M.W1, BigU(T), M.N) * M.R1) % M.N;
+        if ((rc = set_kconst(ctx, M, K_FIX, fix))) return rc;
+        M.fix_T = T + 1;
+    }
     const std::string key = "fix:" + std::to_string(M.sh.S);
     Program* P = cached_program(ctx, key);
     if (!P) {

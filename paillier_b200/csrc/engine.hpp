@@ -58,6 +58,7 @@ struct ModCtx {
     int blocks_per_sm = 0;
     Shape sh_items{};               // shape for programs with per-item exponents (more warps in flight hide the table loads)
     int blocks_per_sm_items = 0;
+    uint64_t fix_T = 0;             // prod_dev: K_FIX currently holds W^(fix_T - 1) * R (0: not set)
 };
 
 // fixed-base comb table for OP_FIXW: row k holds base^(d * 2^(w*k)), d = 0 .. 2^w-1, Montgomery form

@@ -31,6 +31,11 @@ def summarise(path):
             if name in KEEP or (name.startswith(STALLS) and name.endswith("_per_issue_active.ratio")):
                 if val not in ("", "n/a"):
                     k[name] = (val + " " + unit).strip()
+        # ncu sometimes returns "-nan" for every derived counter of a launch it could not replay consistently: keep the
+        # duration, drop the counters, and say so
+        if any(v.startswith("-nan") or v.startswith("nan") for v in k.values()):
+            k = {n: v for n, v in k.items() if not (v.startswith("-nan") or v.startswith("nan"))}
+            k["note"] = "ncu returned nan for the derived counters of this launch"
         res.append(k)
     return res
 
