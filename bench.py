@@ -658,7 +658,7 @@ def main() -> None:
             "add_pairs": (lambda: lib.pgpu_add_pairs_dev(sk._ctx, lcount_, vp(c_dev), vp(rn_dev), vp(o_dev)),
                           lambda: lib.pgpu_add_pairs(sk._ctx, lcount_, hpl(c_host_l), hpl(rn_host), hpl(o_host)), 2 * w_n2, w_n2, 2),
             "encrypt_with_rn": (lambda: lib.pgpu_encrypt_with_rn_dev(sk._ctx, lcount_, vp(m_dev), vp(rn_dev), vp(o_dev)),
-                                lambda: lib.pgpu_encrypt_with_rn(sk._ctx, lcount_, hpl(m_host), hpl(rn_host), hpl(o_host)), w_n + w_n2, w_n2, 3),
+                                lambda: lib.pgpu_encrypt_with_rn(sk._ctx, lcount_, hpl(m_host), hpl(rn_host), hpl(o_host)), w_n + w_n2, w_n2, 2),
         }
         c_host_l = c_dev[:lcount_ * w_n2].cpu().pin_memory()
         mulmac = 2.0 * S_ * S_ + S_ if (S_ := sk.program_cost(0)[0]) else 0

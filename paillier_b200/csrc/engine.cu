@@ -1001,16 +1001,16 @@ size_t resident_groups(const pgpu_ctx* ctx, const ModCtx& m) {
     return (size_t)ctx->sms * (size_t)std::max(m.blocks_per_sm, 1) * (VM_BLOCK_THREADS / std::max(m.sh.tpi, 1));
 }
 
-// Items per chunk: whole rounds of the persistent grid (`align` resident groups), about 2^17 items (64 MB of 512-byte
-// records: large enough for full PCIe bandwidth, small enough that at least four chunks overlap in a 2^20 batch);
-// batches of up to two grids go in one piece.  PGPU_CHUNK_ITEMS overrides (0 = never chunk).
+// Items per chunk: whole rounds of the persistent grid (`align` resident groups), about 2^15 items (16 MB of 512-byte
+// records: large enough for the full PCIe rate, small enough that a 2^16 batch of a light operation already overlaps its
+// copies); batches of up to two grids go in one piece.  PGPU_CHUNK_ITEMS overrides (0 = never chunk).
 size_t chunk_items(size_t count, size_t align) {
     static const long forced = [] { const char* e = getenv("PGPU_CHUNK_ITEMS"); return e ? atol(e) : -1L; }();
     if (forced == 0) return count;
     if (forced > 0) return std::min((size_t)forced, count);        // tests: exact size, ragged against the grid
     align = std::max<size_t>(align, 1);
-    if (count <= std::max(2 * align, (size_t)32768)) return count;
-    const size_t target = (size_t)1 << 17;
+    if (count <= 2 * align) return count;
+    const size_t target = (size_t)1 << 15;
     const size_t chunk = ((target + align - 1) / align) * align;
     return std::min(chunk, count);
 }
