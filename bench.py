@@ -338,7 +338,8 @@ def config1_leg(local):
     out["python_oracle"]["keygen_s"] = time.perf_counter() - t0
     # the same batch on the GPU through the host-buffer C ABI
     sk = SecretKey(n, p=p, q=q, device=local)
-    PublicKey.encrypt_with_r_records(sk, m[:64 * w], r[:64 * w])
+    warm = PublicKey.encrypt_with_r_records(sk, m[:64 * w], r[:64 * w])          # programs, tables, staging buffers
+    sk.decrypt_records(warm); sk.add_reduce_records(warm)
     t0 = time.perf_counter(); gc = PublicKey.encrypt_with_r_records(sk, m, r)
     t1 = time.perf_counter(); gd = sk.decrypt_records(gc)
     t2 = time.perf_counter(); gt = sk.add_reduce_records(gc)
