@@ -61,7 +61,7 @@ int pgpu_ctx_create(pgpu_ctx** out, int device, const uint8_t* n_be, size_t n_le
         if (pick_shape(ctx->n3.v.size(), s3)) { if ((rc = modctx_init(ctx, ctx->m_n3, ctx->n3))) return bail(rc); }
     }
     // n * R^2 mod n^2 for the g = n+1 shortcut
-    if ((rc = set_kconst_both(ctx, ctx->m_n2, K_NR2, [&](const ModCtx& M) { return (ctx->n * M.R2) % ctx->n2; }))) return bail(rc);
+    if ((rc = set_kconst(ctx, ctx->m_n2, K_NR2, (ctx->n * ctx->m_n2.R2) % ctx->n2))) return bail(rc);
     if ((rc = build_encrypt(ctx))) return bail(rc);
     if ((rc = setup_level2(ctx))) return bail(rc);
     *out = ctx;

@@ -53,33 +53,9 @@ int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v) {
     return upload(ctx, m.d_kconst + (size_t)slot * m.sh.S, v.limbs(m.sh.S));
 }
 
-int set_kconst_both(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const std::function<BigU(const ModCtx&)>& value) {
-    int rc = set_kconst(ctx, m, slot, value(m));
-    if (!rc && m.twin) rc = set_kconst(ctx, *m.twin, slot, value(*m.twin));
-    return rc;
-}
-
-static int modctx_init_shape(pgpu_ctx* ctx, ModCtx& m, const BigU& N, const Shape& sh);
-
 int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
     if (!N.is_odd()) return fail(ctx, PGPU_ERR_ARG, "modulus must be odd");
-    Shape sh;
-    if (!pick_shape(N.v.size(), sh)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus wider than the built kernel shapes");
-    int rc = modctx_init_shape(ctx, m, N, sh);
-    if (rc) return rc;
-    static const bool no_twin = getenv("PGPU_NO_TWIN") != nullptr;
-    if (m.sh.fp64 && !no_twin) {
-        Shape si;
-        if (int_shape(N.v.size(), si) && vm_occupancy(si) > 0) {
-            m.twin = new ModCtx();
-            if ((rc = modctx_init_shape(ctx, *m.twin, N, si))) { modctx_free(*m.twin); delete m.twin; m.twin = nullptr; return rc; }
-        }
-    }
-    return PGPU_OK;
-}
-
-static int modctx_init_shape(pgpu_ctx* ctx, ModCtx& m, const BigU& N, const Shape& sh) {
-    m.sh = sh;
+    if (!pick_shape(N.v.size(), m.sh)) return fail(ctx, PGPU_ERR_UNSUPPORTED, "modulus wider than the built kernel shapes");
     m.N = N;
     int_shape(N.v.size(), m.sh32);
     const BigU R = BigU::pow2((size_t)m.sh.rbits());
@@ -109,7 +85,6 @@ static int modctx_init_shape(pgpu_ctx* ctx, ModCtx& m, const BigU& N, const Shap
 }
 
 void modctx_free(ModCtx& m) {
-    if (m.twin) { modctx_free(*m.twin); delete m.twin; }
     if (m.d_mod) cudaFree(m.d_mod);
     if (m.d_kconst) cudaFree(m.d_kconst);
     m = ModCtx();
@@ -206,12 +181,10 @@ int ensure_table(pgpu_ctx* ctx, size_t limbs) {
     return PGPU_OK;
 }
 
-int run_vm(pgpu_ctx* ctx, const ModCtx& m_in, const Program& prog, size_t count,
+int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
            const IoDesc* ins, int n_in, uint32_t* out, uint32_t out_stride, uint32_t out_limbs,
            const ExpDesc& ex, uint32_t* out2, uint32_t out2_stride, int force_blocks) {
     if (count == 0) return PGPU_OK;
-    // per-item exponents and no table state shared with other launches: the integer-pipe twin serves it (see ModCtx::twin)
-    const ModCtx& m = (prog.per_item && m_in.twin && force_blocks <= 0 && !prog.uses_fixed) ? *m_in.twin : m_in;
     if (count > 0x7fffffffu) return fail(ctx, PGPU_ERR_ARG, "batch too large");
     const bool items_shape = prog.per_item && force_blocks <= 0;
     const Shape& sh = items_shape ? m.sh_items : m.sh;
@@ -323,7 +296,7 @@ int setup_encrypt_crt(pgpu_ctx* ctx) {
     if (!BigU::modinv(q2 % p2, p2, q2inv)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
     int rc;
     if ((rc = set_kconst(ctx, P2, K_CRT, q2inv))) return rc;
-    if ((rc = set_kconst_both(ctx, N2, K_CRT, [&](const ModCtx& M) { return (q2 * M.R2) % M.N; }))) return rc;
+    if ((rc = set_kconst(ctx, N2, K_CRT, (q2 * N2.R2) % N2.N))) return rc;
     {   // x_q = r^n mod q^2.  in0 = r
         Program& P = ctx->prog_encq;
         program_free(P);

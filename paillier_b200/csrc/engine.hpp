@@ -42,12 +42,7 @@ struct Program {
     uint32_t* d_ops = nullptr;
     uint32_t n_sqr = 0, n_mul = 0, tbl_entries = 0;
     bool per_item = false;          // uses OP_WIN: table entries picked by per-item exponent bits
-    bool uses_fixed = false;        // uses OP_FIXW: reads a fixed-base table built in the Montgomery form of the context's own radix
-    void emit(uint32_t code, uint32_t arg) {
-        ops.push_back(vm_op(code, arg));
-        if (code == OP_WIN) per_item = true;
-        if (code == OP_FIXW) uses_fixed = true;
-    }
+    void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); if (code == OP_WIN) per_item = true; }
     void use_slot(uint32_t s) { tbl_entries = std::max(tbl_entries, s + 1); }
 };
 
@@ -64,11 +59,6 @@ struct ModCtx {
     Shape sh_items{};               // shape for programs with per-item exponents (more warps in flight hide the table loads)
     int blocks_per_sm_items = 0;
     uint64_t fix_T = 0;             // prod_dev: K_FIX currently holds W^(fix_T - 1) * R (0: not set)
-    // An FP64-pipe context keeps an integer-pipe twin of the same modulus (own radix, own constants): programs with per-item
-    // exponents (OP_WIN: ConstMult, the ZKP's (c^4)^r and verification powers) run on it -- measured equal or faster there,
-    // while the shared-exponent programs gain on the FP64 pipe (profiles/r02_fp64_experiments.md).  Results are canonical
-    // residues, so which of the two computed one is not observable.
-    ModCtx* twin = nullptr;
 };
 
 // fixed-base comb table for OP_FIXW: row k holds base^(d * 2^(w*k)), d = 0 .. 2^w-1, Montgomery form
@@ -214,8 +204,6 @@ size_t resident_groups(const pgpu_ctx* ctx, const ModCtx& m);
 bool pick_shape(size_t limbs, Shape& out);
 int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v);
 int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v);
-// a constant that depends on the Montgomery radix: value(M) is evaluated for the context and for its twin
-int set_kconst_both(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const std::function<BigU(const ModCtx&)>& value);
 int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N);
 void modctx_free(ModCtx& m);
 int choose_window(size_t bits);

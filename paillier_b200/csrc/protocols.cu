@@ -114,8 +114,8 @@ void protocols_free(pgpu_ctx* ctx) {
 int setup_level2(pgpu_ctx* ctx) {
     int rc;
     ModCtx &M1 = ctx->m_n, &M2 = ctx->m_n2, &M3 = ctx->m_n3;
-    if ((rc = set_kconst_both(ctx, M2, K_NM, [&](const ModCtx& M) { return to_mont(M, ctx->n); }))) return rc;
-    if ((rc = set_kconst_both(ctx, M2, K_NSM, [&](const ModCtx& M) { return to_mont(M, ctx->n); }))) return rc;
+    if ((rc = set_kconst(ctx, M2, K_NM, to_mont(M2, ctx->n)))) return rc;
+    if ((rc = set_kconst(ctx, M2, K_NSM, to_mont(M2, ctx->n)))) return rc;
     if ((rc = set_kconst(ctx, M1, K_R4, (M1.R3 * M1.W1) % M1.N))) return rc;      // W^2 * R^2: third chunk of a record
     {   // Randomize with the r supplied: c * r^n mod n^2 (operations.go:67-69 = Add(ct, EncryptWithR(0, r)))
         Program& P = ctx->prog_rand;
