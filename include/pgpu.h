@@ -211,7 +211,8 @@ int pgpu_modmul(pgpu_ctx* ctx, int modsel, size_t count, const void* a, const vo
 /* SURVEY.md 8(b) "Ownership" / 8(f) rank 1: ciphertexts stay on the device between calls (Encrypt -> ConstMult -> Add ->
  * Decrypt without PCIe round trips, the callers of operations.go:11-64).  A pgpu_buf is device memory on the context's
  * device; pgpu_buf_ptr() is what the *_dev entry points below take.  Upload / download block until the copy is done (no
- * host pointer is retained); pgpu_buf_free waits for the work enqueued on the context before releasing the memory. */
+ * host pointer is retained); pgpu_buf_free waits for the work enqueued on the context before releasing the memory.  Free
+ * every buffer before pgpu_ctx_destroy of the context it was allocated on. */
 typedef struct pgpu_buf pgpu_buf;
 int pgpu_buf_alloc(pgpu_ctx* ctx, size_t bytes, pgpu_buf** out);
 int pgpu_buf_free(pgpu_buf* buf);

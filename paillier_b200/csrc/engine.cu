@@ -1027,11 +1027,25 @@ static int chunk_streams(pgpu_ctx* ctx) {
     return PGPU_OK;
 }
 
+static int run_chunked_impl(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
+                            const std::function<int(size_t, const uint32_t* const*, uint32_t* const*)>& fn);
+
 int run_chunked(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
                 const std::function<int(size_t, const uint32_t* const*, uint32_t* const*)>& fn) {
     if (count == 0) return PGPU_OK;
     int rc;
     if ((rc = chunk_streams(ctx))) return rc;
+    rc = run_chunked_impl(ctx, count, io, fn);
+    if (rc) {
+        // whatever failed, no copy may still be reading or writing the caller's buffers when the call returns
+        cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); cudaStreamSynchronize(ctx->stream);
+    }
+    return rc;
+}
+
+static int run_chunked_impl(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
+                            const std::function<int(size_t, const uint32_t* const*, uint32_t* const*)>& fn) {
+    int rc;
     const size_t chunk = chunk_items(count, io.align);
     const size_t n_chunks = (count + chunk - 1) / chunk;
     const int n_buf = n_chunks > 1 ? 2 : 1;
@@ -1061,7 +1075,7 @@ int run_chunked(pgpu_ctx* ctx, size_t count, const ChunkedIo& io,
         const int b = (int)(k & 1);
         CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         if (k >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));          // chunk k-2's results have left
-        if ((rc = fn(items_of(k), din[b], dout[b]))) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); cudaStreamSynchronize(ctx->stream); return rc; }
+        if ((rc = fn(items_of(k), din[b], dout[b]))) return rc;
         CU(ctx, cudaEventRecord(ctx->ev_cmp[b], ctx->stream));
         if (k + 1 < n_chunks && (rc = h2d(k + 1))) return rc;
         CU(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[b], 0));

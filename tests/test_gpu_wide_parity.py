@@ -120,7 +120,7 @@ def test_ddleq_64_statements_secpar_8_at_2048_bits():
     assert sk.VerifyDDLEQProofBatch(ct1, ct2, proofs) == [True] * count
     jobs = [(p, q, secpar, ct1[i].C, ct2[i].C, As[i], Bs[i], xs[i], ys[i]) for i in range(count)]
     procs = max(1, min(len(os.sched_getaffinity(0)), 32))
-    with mp.get_context("fork").Pool(procs) as pool:
+    with mp.get_context("spawn").Pool(procs) as pool:      # (spawn: the test process is multi-threaded once CUDA is up)
         refs = pool.map(_oracle_prove, jobs, chunksize=1)
     chal = set()
     for pr, ref in zip(proofs, refs):
