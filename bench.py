@@ -794,6 +794,10 @@ def main() -> None:
                   "note": "one batch split into contiguous slices, no collective on the data path; resident groups per GPU = "
                           "%d, so the last round of the persistent grid is partly idle at small slices" % sk_resident}
 
+    if world == 1 and not args.no_extras and count == args.strong_count:
+        strong = {"value": value, "unit": UNIT, "scaling": "strong", "items_total": count, "items_per_gpu": count, "ms_per_step": ms_per_step,
+                  "steps": args.steps, "note": "one GPU: the strong-scaling batch is the headline step itself"}
+
     # ---- Add over a batch sharded across the ranks: per-rank tree product, all-gather of `world` records, one fold
     sharded_add = None
     if world > 1 and not args.no_extras:
