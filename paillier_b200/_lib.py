@@ -79,6 +79,7 @@ SIGNATURES = {
     "pgpu_ctx_z_width": (C.c_int, [_p, C.POINTER(_sz)]),
     "pgpu_pdec_zkp_verify": (C.c_int, [_p, _sz, C.c_int, _p, _p, _p, _p, _p]),
     "pgpu_combine": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p]),
+    "pgpu_pdec_zkp_verify_shared_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p, _p]),
     "pgpu_combine_verified": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _p, _p, _p]),
     "pgpu_combine_verified_dev": (C.c_int, [_p, _sz, C.c_int, C.POINTER(C.c_int), _p, _sz, _p, _p, _p]),
     "pgpu_pdec_zkp_prove_dev": (C.c_int, [_p, _sz, _p, _p, _p, _p, _p]),

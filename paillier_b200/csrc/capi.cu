@@ -922,6 +922,16 @@ int pgpu_combine_strided_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids,
     GUARD_END(ctx)
 }
 
+int pgpu_pdec_zkp_verify_shared_dev(pgpu_ctx* ctx, size_t n, int k, const int* ids, const void* c, const void* dec, const void* e, const void* z,
+                                    uint8_t* ok) {
+    GUARD_BEGIN
+    REQUIRE(ctx, ctx && k >= 1 && ids && (n == 0 || (c && dec && e && z && ok)), "pgpu_pdec_zkp_verify_shared_dev: null argument");
+    int rc; if ((rc = set_device(ctx))) return rc;
+    TimedScope ts(ctx);
+    return zkp_verify_shared_dev(ctx, n, k, ids, (const uint32_t*)c, (const uint32_t*)dec, (const uint32_t*)e, (const uint32_t*)z, ok);
+    GUARD_END(ctx)
+}
+
 int pgpu_combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const void* decs, size_t share_stride, const uint8_t* ok,
                               void* m, uint8_t* item_ok) {
     GUARD_BEGIN

@@ -200,7 +200,7 @@ int run_vm(pgpu_ctx* ctx, const ModCtx& m, const Program& prog, size_t count,
     for (int i = 0; i < n_in; ++i) { P.in[i] = ins[i].ptr; P.in_stride[i] = ins[i].stride; P.in_limbs[i] = ins[i].limbs; P.in_div[i] = std::max<uint32_t>(ins[i].div, 1); }
     P.out[0] = out; P.out_stride[0] = out_stride; P.out_limbs[0] = out_limbs;
     P.out[1] = out2; P.out_stride[1] = out2_stride; P.out_limbs[1] = m.sh.S;
-    P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed;
+    P.exp = ex.ptr; P.exp_stride = ex.stride; P.exp_bits = ex.bits; P.fixed = ex.fixed; P.exp_sub = ex.sub;
     P.n_groups = (uint32_t)blocks * gpb;
     { static const bool no_sqr = getenv("PGPU_NO_SQR") != nullptr; P.flags = no_sqr ? 1u : 0u; }
     const size_t tbl_limbs = (size_t)std::max<uint32_t>(prog.tbl_entries, 1) * P.n_groups * sh.tbl_limbs();
@@ -481,6 +481,63 @@ int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_
                      bool broadcast_base) {
     return modexp_items_io(ctx, M, count, IoDesc{base, broadcast_base ? 0u : (uint32_t)M.sh.S, (uint32_t)M.sh.S},
                            ExpDesc{exp, exp_limbs, 32 * exp_limbs, nullptr}, out);
+}
+
+// Shared-base multi-exponentiation: k exponents per base, item-major (record i*k + s).  VerifyProof of the k share-holders'
+// proofs for one ciphertext raises the same c^4 to k different Z (thresholdkey.go:293-302): right to left, the chain
+// c^4, (c^4)^(2^w), (c^4)^(2^(2w)), ... is squared ONCE per ciphertext and every exponent s multiplies it into the bucket of its
+// digit (one multiplication per window and exponent, OP_BKT with sub = s); per exponent the buckets are then folded into
+// prod_d T[d]^d with the running-product trick.  nwin*w squarings + k*(nwin + 2*2^w) multiplications per base instead of
+// k*(nwin*w + nwin + 2^w): 3.7x fewer for k = 8 at 6656-bit exponents.
+int modexp_multi_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, uint32_t k, const uint32_t* base, uint32_t pre, const uint32_t* exp, uint32_t exp_limbs,
+                     uint32_t* out) {
+    if (k == 0 || count == 0) return PGPU_OK;
+    if (k > 8) return fail(ctx, PGPU_ERR_ARG, "modexp_multi: at most 8 exponents per base");
+    const uint32_t S = M.sh.S, bits = 32 * exp_limbs;
+    int w = 1;
+    // (w <= 6: 8 x 65 buckets of 768 B per resident group are 1.9 GB at 6144 bits; w = 7 would save 1 % for twice that)
+    { double best = 1e300; for (int c = 1; c <= 6; ++c) { const double cost = (double)k * ((double)bits / c + 2.0 * (1u << c)); if (cost < best) { best = cost; w = c; } } }
+    const uint32_t nb = 1u << w, per = nb + 1, nwin = (bits + w - 1) / w;
+    const uint32_t CH = k * per, RUN = CH + 1, ACC = CH + 2;
+    const std::string key = "multi:" + std::to_string(S) + ":" + std::to_string(k) + ":" + std::to_string(bits) + ":" + std::to_string(pre);
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDC, K_R1);
+        for (uint32_t s = 0; s < k; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
+        np.use_slot(ACC);
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        if (pre == 2) { np.emit(OP_SQR, 1); np.n_sqr += 1; }
+        if (pre == 4) { np.emit(OP_SQR, 2); np.n_sqr += 2; }
+        for (uint32_t win = 0; win < nwin; ++win) {
+            np.emit(OP_STT, CH);                                                              // the chain value of this window
+            for (uint32_t s = 0; s < k; ++s) {
+                np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (s << 24)); np.n_mul++;     // T[s][digit] *= chain
+                if (s + 1 < k || win + 1 < nwin) np.emit(OP_LDT, CH);
+            }
+            if (win + 1 < nwin) { np.emit(OP_SQR, (uint32_t)w); np.n_sqr += w; }
+        }
+        for (uint32_t s = 0; s < k; ++s) {
+            // run = T[nb-1]; acc = run; for d = nb-2 .. 1: run *= T[d]; acc *= run          (acc = prod_d T[d]^d)
+            np.emit(OP_LDT, s * per + nb - 1);
+            if (nb > 2) {
+                np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
+                for (uint32_t d = nb - 2; d >= 1; --d) {
+                    np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
+                    np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
+                }
+            }
+            np.emit(OP_MULC, K_ONE); np.n_mul++;
+            np.emit(OP_STOO, (s << 2) | 0u);
+        }
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{base, S, S}};
+    ExpDesc ex{exp, k * exp_limbs, bits, nullptr, exp_limbs};
+    return run_vm(ctx, M, *P, count, ins, 1, out, k * S, S, ex);
 }
 
 // out[i] = base[i]^e mod M, one exponent for the whole batch (sliding window compiled on the host)
@@ -787,6 +844,60 @@ int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, 
     return PGPU_OK;
 }
 
+// VerifyProof (thresholdkey.go:278-311) of the proofs of k servers for the SAME n ciphertexts -- what the combiner of a
+// threshold round does.  Records are item-major: proof p = i*k + j is server ids[j]'s proof for ciphertext i (c holds n
+// records, dec / e / z / ok hold n*k).  The k powers (c^4)^Z of one ciphertext share their squarings (modexp_multi_dev);
+// everything else is as in zkp_verify_multi_dev.
+int zkp_verify_shared_dev(pgpu_ctx* ctx, size_t n, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
+                          const uint32_t* z, uint8_t* ok) {
+    if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "VerifyProof: no threshold key loaded");
+    if (k < 1 || k > 8) return fail(ctx, PGPU_ERR_ARG, "VerifyProof (shared ciphertexts): 1 to 8 servers per call");
+    for (int j = 0; j < k; ++j)
+        if (ids[j] < 1 || (size_t)ids[j] > ctx->tk_vi.size())
+            return fail(ctx, PGPU_ERR_ARG, "VerifyProof: no verification key for this server id");
+    const size_t count = n * (size_t)k;
+    if (count == 0) return PGPU_OK;
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S, ZL = z_limbs(ctx);
+    int rc;
+    DEVBUF(t0, ctx, count * S); DEVBUF(t1, ctx, count * S); DEVBUF(t2, ctx, count * S);
+    DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(kvi, ctx, (size_t)k * S); DEVBUF(vrep, ctx, count * S);
+    DEVBUF(bad, ctx, 1); DEVBUF(e2, ctx, count * 8);
+    {
+        std::vector<uint32_t> vk;
+        for (int j = 0; j < k; ++j) { auto l = ctx->tk_vi[ids[j] - 1].limbs(S); vk.insert(vk.end(), l.begin(), l.end()); }
+        if ((rc = upload(ctx, kvi.p, vk))) return rc;
+        CU(ctx, repeat_launch(kvi.p, (uint32_t)k * S, (uint32_t)n, vrep.p, (uint32_t)n, ctx->stream));      // v_i of proof i*k + j = kvi[j]
+    }
+    // a = (c^4)^Z * ((c_i^2)^E)^-1 mod n^2        verifyPart1 :293-302
+    if ((rc = modexp_multi_dev(ctx, M, n, (uint32_t)k, c, 4, z, ZL, t1.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, dec, dec, t0.p))) return rc;
+    if ((rc = modexp_items_dev(ctx, M, count, t0.p, e, 8, t2.p))) return rc;
+    if ((rc = modinv_batch_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, a.p))) return rc;
+    // b = V^Z * (v_i^E)^-1 mod n^2                verifyPart2 :304-311
+    if ((rc = ensure_fix_v(ctx))) return rc;
+    if ((rc = modexp_fixed_dev(ctx, M, ctx->fix_v, count, ExpDesc{z, ZL, 32 * ZL, nullptr}, t1.p))) return rc;   // V^Z (fixed base)
+    if ((rc = modexp_items_dev(ctx, M, count, vrep.p, e, 8, t2.p))) return rc;
+    if ((rc = modinv_batch_dev(ctx, M, count, t2.p, t0.p, bad.p))) return rc;
+    if ((rc = modmul_dev(ctx, M, count, t1.p, t0.p, b.p))) return rc;
+    // E' = SHA-256(a || b || c^4 || c_i^2) with the unreduced c^4 of ciphertext p / k
+    {
+        DEVBUF(c2, ctx, n * 2 * S); DEVBUF(c4, ctx, n * 4 * S); DEVBUF(ci2, ctx, count * 2 * S);
+        if ((rc = bigmul_dev(ctx, n, c, S, c, S, c2.p))) return rc;
+        if ((rc = bigmul_dev(ctx, n, c2.p, 2 * S, c2.p, 2 * S, c4.p))) return rc;
+        if ((rc = bigmul_dev(ctx, count, dec, S, dec, S, ci2.p))) return rc;
+        const uint32_t* seg[4] = {a.p, b.p, c4.p, ci2.p};
+        const uint32_t stride[4] = {S, S, 4 * S, 2 * S};
+        const int limbs[4] = {(int)S, (int)S, (int)(4 * S), (int)(2 * S)};
+        const uint32_t div[4] = {1, 1, (uint32_t)k, 1};
+        if ((rc = sha_dev(ctx, count, 4, seg, stride, limbs, e2.p, div))) return rc;
+    }
+    CU(ctx, equal_launch(e, e2.p, 8, (uint32_t)count, ok, ctx->stream));
+    ctx->launches++;
+    return PGPU_OK;
+}
+
 // VerifyProof (thresholdkey.go:278-311) for proofs of one server
 int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const uint32_t* dec, const uint32_t* e, const uint32_t* z, uint8_t* ok) {
     return zkp_verify_multi_dev(ctx, count, 1, &id, c, dec, e, z, ok);
@@ -852,7 +963,7 @@ int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32
 // and a ciphertext left with fewer than `threshold` shares gets a zero plaintext and item_ok = 0 where the reference
 // returns "Threshold not meet" for it.  *n_failed counts those.
 int combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, size_t share_stride, const uint8_t* ok,
-                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed) {
+                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed, bool ok_item_major) {
     if (share_stride == 0) share_stride = count;
     if (n_failed) *n_failed = 0;
     if (!ctx->has_threshold) return fail(ctx, PGPU_ERR_STATE, "CombinePartialDecryptionsZKP: no threshold key loaded");
@@ -866,7 +977,7 @@ int combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, con
     std::map<uint64_t, std::vector<uint32_t>> groups;
     for (size_t i = 0; i < count; ++i) {
         uint64_t mask = 0;
-        for (int j = 0; j < k; ++j) if (hok[(size_t)j * count + i]) mask |= 1ull << j;
+        for (int j = 0; j < k; ++j) if (hok[ok_item_major ? i * (size_t)k + j : (size_t)j * count + i]) mask |= 1ull << j;
         groups[mask].push_back((uint32_t)i);
     }
     const uint64_t full = k == 64 ? ~0ull : ((1ull << k) - 1);

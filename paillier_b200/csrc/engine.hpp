@@ -155,7 +155,7 @@ std::string& thread_error();
 
 struct IoDesc { const uint32_t* ptr; uint32_t stride, limbs; uint32_t div = 1; };   // item i reads record i / div
 // per-item exponents (OP_WIN / OP_FIXW): records `stride` limbs apart of which the low `bits` bits count
-struct ExpDesc { const uint32_t* ptr = nullptr; uint32_t stride = 0, bits = 0; const uint32_t* fixed = nullptr; };
+struct ExpDesc { const uint32_t* ptr = nullptr; uint32_t stride = 0, bits = 0; const uint32_t* fixed = nullptr; uint32_t sub = 0; };   // sub: limbs between the exponents of one item (OP_BKT)
 
 // stream-ordered temporary device buffer
 struct DevBuf {
@@ -232,6 +232,10 @@ Program* cached_program(pgpu_ctx* ctx, const std::string& key);
 int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const uint32_t* exp, uint32_t exp_limbs, uint32_t* out,
                      bool broadcast_base = false);
 int modexp_shared_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* base, const BigU& e, uint32_t* out);
+// out[i*k + s] = (base[i]^pre)^(exp[i*k + s]) for k exponents per base (item-major records): the squarings are shared by the k
+// exponentiations (right-to-left, bucket method), pre = 1, 2 or 4 squares the base first
+int modexp_multi_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, uint32_t k, const uint32_t* base, uint32_t pre, const uint32_t* exp, uint32_t exp_limbs,
+                     uint32_t* out);
 int modmul_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_t* a, const uint32_t* b, uint32_t* out);
 // the same three with explicit record descriptors (narrower records, broadcast, one record per `div` items)
 int modexp_items_io(pgpu_ctx* ctx, const ModCtx& M, size_t count, const IoDesc& base, const ExpDesc& exp, uint32_t* out);
@@ -250,9 +254,12 @@ int zkp_verify_dev(pgpu_ctx* ctx, size_t count, int id, const uint32_t* c, const
 // share j's batch starts at record j*share_stride (0 = count: tightly packed)
 int zkp_verify_multi_dev(pgpu_ctx* ctx, size_t n_per_id, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
                          const uint32_t* z, uint8_t* ok);
+// the same verdicts for k servers' proofs of the SAME n ciphertexts, records item-major (proof i*k + j), shared squarings
+int zkp_verify_shared_dev(pgpu_ctx* ctx, size_t n, int k, const int* ids, const uint32_t* c, const uint32_t* dec, const uint32_t* e,
+                          const uint32_t* z, uint8_t* ok);
 int combine_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, uint32_t* m_out, size_t share_stride = 0);
 int combine_verified_dev(pgpu_ctx* ctx, size_t count, int k, const int* ids, const uint32_t* decs, size_t share_stride, const uint8_t* ok,
-                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed);
+                         uint32_t* m_out, uint8_t* item_ok, size_t* n_failed, bool ok_item_major = false);   // ok[i*k + j] instead of ok[j*count + i]
 int set_device(pgpu_ctx* ctx);
 
 // ---- protocols.cu: level 2, alternative encryption, randomness extraction, nested operations, DDLEQ

@@ -80,7 +80,7 @@ struct DeviceRound {
     uint32_t S = 0, ZL = 0;
     size_t h = 0;
     cudaEvent_t ev[6] = {};
-    std::unique_ptr<DevBuf> dc, dec, dr, de, dz, vc, vdec, ve, vz, dok, dm, dit;
+    std::unique_ptr<DevBuf> dc, dec, dr, de, dz, vc, vdec, ve, vz, dok, dm, dit, didx;
 
     DeviceRound(pgpu_ctx* c, int g_, int G_, size_t count_, bool zkp_) : ctx(c), g(g_), G(G_), count(count_), zkp(zkp_) {
         lo = (count / G) * g + std::min<size_t>(g, count % G);
@@ -140,7 +140,19 @@ struct DeviceRound {
         cudaStream_t st = ctx->stream;
         int rc;
         if (n == 0) { CU(ctx, cudaEventRecord(ev[4], st)); CU(ctx, cudaEventRecord(ev[5], st)); return PGPU_OK; }
-        if (zkp) {
+        const bool shared = G <= 8 && !getenv("PGPU_NO_SHARED_VERIFY");
+        if (zkp && shared) {
+            // item-major copies of this slice's proofs (record i*G + s <- gathered row s, ciphertext lo + i): the G proofs of one
+            // ciphertext raise the same c^4 to G different Z and share the squarings (zkp_verify_shared_dev)
+            std::vector<uint32_t> idx(n * (size_t)G);
+            for (size_t i = 0; i < n; ++i) for (int s = 0; s < G; ++s) idx[i * G + s] = (uint32_t)((size_t)s * count + lo + i);
+            if ((rc = buf(didx, idx.size()))) return rc;
+            if ((rc = upload(ctx, didx->p, idx))) return rc;
+            CU(ctx, gather_launch(dec->p, S, didx->p, 1, vdec->p, (uint32_t)idx.size(), st));
+            CU(ctx, gather_launch(de->p, 8, didx->p, 1, ve->p, (uint32_t)idx.size(), st));
+            CU(ctx, gather_launch(dz->p, ZL, didx->p, 1, vz->p, (uint32_t)idx.size(), st));
+            if ((rc = zkp_verify_shared_dev(ctx, n, G, ids.data(), dc->p + lo * S, vdec->p, ve->p, vz->p, (uint8_t*)dok->p))) return rc;
+        } else if (zkp) {
             for (int s = 0; s < G; ++s) {
                 CU(ctx, cudaMemcpyAsync(vc->p + (size_t)s * n * S, dc->p + lo * S, n * S * 4, cudaMemcpyDeviceToDevice, st));
                 CU(ctx, cudaMemcpyAsync(vdec->p + (size_t)s * n * S, dec->p + ((size_t)s * count + lo) * S, n * S * 4, cudaMemcpyDeviceToDevice, st));
@@ -150,7 +162,7 @@ struct DeviceRound {
             if ((rc = zkp_verify_multi_dev(ctx, n, G, ids.data(), vc->p, vdec->p, ve->p, vz->p, (uint8_t*)dok->p))) return rc;
         }
         CU(ctx, cudaEventRecord(ev[4], st));
-        if (zkp) rc = combine_verified_dev(ctx, n, G, ids.data(), dec->p + lo * S, count, (const uint8_t*)dok->p, dm->p, (uint8_t*)dit->p, n_failed);
+        if (zkp) rc = combine_verified_dev(ctx, n, G, ids.data(), dec->p + lo * S, count, (const uint8_t*)dok->p, dm->p, (uint8_t*)dit->p, n_failed, shared);
         else rc = combine_dev(ctx, n, G, ids.data(), dec->p + lo * S, dm->p, count);
         if (rc) return rc;
         CU(ctx, cudaEventRecord(ev[5], st));

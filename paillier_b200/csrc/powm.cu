@@ -184,9 +184,10 @@ __device__ __forceinline__ void vm_run(const VmParams& P) {
                     M.store_full(active ? P.out[a] + (size_t)item * P.out_stride[a] + (size_t)off * S : dump, x);
                 } break;
                 case OP_BKT: {
-                    const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu;
+                    const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, sub = arg >> 24;
                     // idle groups must not touch the buckets: they multiply into the spare entry 2^w
-                    bkt = active ? exp_bits(P.exp + (size_t)item * P.exp_stride, P.exp_bits, pos, w) : (1u << w);
+                    const uint32_t d = active ? exp_bits(P.exp + (size_t)item * P.exp_stride + (size_t)sub * P.exp_sub, P.exp_bits, pos, w) : (1u << w);
+                    bkt = sub * ((1u << w) + 1u) + d;
                     M.load_tbl(y, tbl + bkt * tbl_entry_stride);
                     nmul = 1;
                 } break;

@@ -36,7 +36,8 @@ enum VmOp : uint32_t {
     OP_STOO  = 18, // out[arg & 1][item, off = arg >> 2] = x
     // bucket accumulation (Pippenger multi-exponentiation of the encrypted dot product): the group's table is state
     // that persists from item to item
-    OP_BKT   = 19, // d = bits(exp[item], pos, w); T[d] = x = mont(x, T[d]), arg = pos | w<<20
+    OP_BKT   = 19, // d = bits(exp[item] + sub*exp_sub, pos, w); T[sub*(2^w+1) + d] = x = mont(x, T[...]), arg = pos | w<<20 | sub<<24
+                   // (sub = 0: the dot product's buckets; sub < 8: one bucket set per exponent of a shared-base multi-exponentiation)
 };
 
 // 5-bit opcode, 27-bit argument
@@ -63,6 +64,7 @@ struct VmParams {
     const uint32_t* exp;               // per-item exponents for OP_WIN / OP_FIXW
     uint32_t exp_stride;               // limbs between exponent records
     uint32_t exp_bits;                 // bits of an exponent record that count (higher bits read as 0)
+    uint32_t exp_sub;                  // OP_BKT: limbs between the `sub` exponents of one item
     const uint32_t* fixed;             // fixed-base table for OP_FIXW: records of S limbs, Montgomery form
     uint32_t* table;                   // scratch: [entry][group][S]
     uint32_t n_groups;                 // number of resident groups (table slots)

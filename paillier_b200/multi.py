@@ -19,6 +19,7 @@ CPU tensors in tests (tests/test_multi_gloo.py); `gpu_threshold_round` binds the
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 
@@ -273,12 +274,20 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
             ok = None
             ev["verify"][0].record(stream)
             if zkp_r is not None and n > 0:
-                rows = lambda buf, w: torch.cat([buf[(s * count + lo) * w:(s * count + hi) * w] for s in range(shares)])
-                ok = torch.zeros(shares * n, dtype=torch.uint8, device=dev)
                 idarr = (C.c_int * shares)(*ids)
-                # (named tensors: a temporary would hand its memory back to torch's allocator before the kernels ran)
-                v_c, v_dec, v_e, v_z = c_dev[lo * w2:hi * w2].repeat(shares), rows(g_dec, w2), rows(g_e, 32), rows(g_z, wz)
-                check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(v_c), vp(v_dec), vp(v_e), vp(v_z), vp(ok)), t0._ctx)
+                if shares <= 8 and not os.environ.get("PGPU_NO_SHARED_VERIFY"):
+                    # the k proofs of one ciphertext raise the same c^4 to k different Z: item-major records, shared squarings
+                    im = lambda buf, w: buf.view(shares, count, w)[:, lo:hi].transpose(0, 1).contiguous().view(-1)
+                    v_c, v_dec, v_e, v_z = c_dev[lo * w2:hi * w2], im(g_dec, w2), im(g_e, 32), im(g_z, wz)
+                    ok_im = torch.zeros(n * shares, dtype=torch.uint8, device=dev)
+                    check(lib.pgpu_pdec_zkp_verify_shared_dev(t0._ctx, n, shares, idarr, vp(v_c), vp(v_dec), vp(v_e), vp(v_z), vp(ok_im)), t0._ctx)
+                    ok = ok_im.view(n, shares).t().contiguous().view(-1)           # share-major for the combiner
+                else:
+                    rows = lambda buf, w: torch.cat([buf[(s * count + lo) * w:(s * count + hi) * w] for s in range(shares)])
+                    ok = torch.zeros(shares * n, dtype=torch.uint8, device=dev)
+                    # (named tensors: a temporary would hand its memory back to torch's allocator before the kernels ran)
+                    v_c, v_dec, v_e, v_z = c_dev[lo * w2:hi * w2].repeat(shares), rows(g_dec, w2), rows(g_e, 32), rows(g_z, wz)
+                    check(lib.pgpu_pdec_zkp_verify_multi_dev(t0._ctx, n, shares, idarr, vp(v_c), vp(v_dec), vp(v_e), vp(v_z), vp(ok)), t0._ctx)
             ev["verify"][1].record(stream)
             # ---- Combine the slice in place out of the gathered buffer; with proofs the reference's per-ciphertext filter
             # (CombinePartialDecryptionsZKP, thresholdkey.go:164-172) picks the shares whose proof holds

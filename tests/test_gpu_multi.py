@@ -195,3 +195,41 @@ def test_library_threshold_round_matches_torchrun_path_on_two_gpus():
     for r in (r1, r2):
         line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
         assert line["n_gpus"] == 2 and line["all_plaintexts_recovered"] and line["oracle_parity"] is True
+
+
+@pytest.mark.parametrize("bits,l,w,count", [(512, 4, 3, 37), (2048, 8, 5, 9)])
+def test_shared_ciphertext_verification_matches_per_server_verification(bits, l, w, count):
+    # pgpu_pdec_zkp_verify_shared_dev (the k proofs of one ciphertext share the squarings of (c^4)^Z) against N x VerifyProof per
+    # server, honest and tampered proofs alike
+    import ctypes as C
+    import numpy as np
+    from paillier_b200._lib import check, lib
+    p, q = synth.load_key(f"threshold_{bits}")
+    n = p * q
+    keys = ThresholdKeyGenerator(bits, l, w, rng=random.Random(21)).with_safe_primes(p, q).GenerateKeys()
+    t0 = keys[0]
+    c = t0.encrypt_with_r_records(synth.plaintexts(count, n, t0.w_n), synth.randomness(count, n, t0.w_n))
+    c[:t0.w_n2] = 0; c[0] = 1                                                  # c = 1 rides along
+    proofs = [k.zkp_prove_records(c, synth.random_records(count, t0.w_n2, (n * n).bit_length() - 1, stream=90 + k.ID)) for k in keys]
+    dec = np.stack([pr[0].reshape(count, -1) for pr in proofs], axis=1).copy()   # [ciphertext][share][bytes]
+    e = np.stack([pr[1].reshape(count, -1) for pr in proofs], axis=1).copy()
+    z = np.stack([pr[2].reshape(count, -1) for pr in proofs], axis=1).copy()
+    z[3, 1, 0] ^= 1                       # server 2's Z for ciphertext 3
+    e[5, 0, 7] ^= 0x10                    # server 1's E for ciphertext 5
+    dec[6, l - 1, 2] ^= 4                 # the last server's partial decryption of ciphertext 6
+    dev = torch.device("cuda", 0)
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).to(dev)
+    c_d, dec_d, e_d, z_d = td(c), td(dec), td(e), td(z)
+    ok = torch.zeros(count * l, dtype=torch.uint8, device=dev)
+    ids = (C.c_int * l)(*[k.ID for k in keys])
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(lib.pgpu_pdec_zkp_verify_shared_dev(t0._ctx, count, l, ids, vp(c_d), vp(dec_d), vp(e_d), vp(z_d), vp(ok)), t0._ctx)
+    check(lib.pgpu_ctx_sync(t0._ctx), t0._ctx)
+    got = ok.cpu().numpy().reshape(count, l)
+    for j, k in enumerate(keys):
+        want = t0.verify_proof_records(k.ID, c, dec[:, j].copy(), e[:, j].copy(), z[:, j].copy())
+        assert np.array_equal(got[:, j], want)
+    bad = {(3, 1), (5, 0), (6, l - 1)}
+    assert all(bool(got[i, j]) == ((i, j) not in bad) for i in range(count) for j in range(l))
+    for k in keys:
+        k.close()
