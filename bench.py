@@ -213,7 +213,9 @@ def config4_leg(args, dist, rank, world, local, dev, barrier, max_over_ranks):
                         "every ciphertext, all-gather, VerifyProof x 8 and Combine of each rank's slice" % (world, k),
             "ciphertexts": count, "ciphertexts_note": "2^18 per share-holder at 8 GPUs; min(2^18, 2^15 * N) otherwise so that the leg fits the bench budget",
             "ms": total_ms, "ciphertexts_per_s": count / (total_ms * 1e-3), "partial_decryptions_per_s": l * count / (total_ms * 1e-3),
-            "phases_ms": ph, "all_gather_share_of_step": ph["all_gather"] / total_ms if total_ms else None,
+            "phases_ms": ph, "phases_note": "pdec is empty: with proofs the partial decryption comes out of the proof's launch (c^(2*delta*s) and (c^4)^r "
+                                            "share their squarings); verify raises c^4 to the 8 share-holders' Z with shared squarings",
+            "all_gather_share_of_step": ph["all_gather"] / total_ms if total_ms else None,
             "all_gather_bytes_per_gpu": {"sent": k * count * (w2 + 32 + t0.w_z), "received": l * count * (w2 + 32 + t0.w_z)},
             "all_proofs_verified_on_rank0": bool(keep["ok"].all().item()) if keep.get("ok") is not None else None,
             "all_plaintexts_recovered": bad == 0.0,

@@ -780,6 +780,63 @@ int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t*
     return sha_dev(ctx, count, 4, seg, stride, limbs, e_out);
 }
 
+// PartialDecrypt and the proof's a = (c^4)^r in ONE launch (thresholdkey.go:199 and :241-242): both are powers of c --
+// c^(2*delta*share) with the key's exponent and c^(4r) with the item's r -- so right to left they share the squaring chain
+// c, c^2, c^4, ...: per window of w bits the chain value goes into the bucket of the key exponent's digit (known to the host:
+// a static table index) and, two squarings later, into the bucket of r's digit (OP_BKT); the two bucket sets are folded
+// into prod_d T[d]^d.  ~6160 squarings + 2*(nwin + 2^(w+1)) multiplications instead of two exponentiations of ~7000 each.
+static int pdec_and_a_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* a) {
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const BigU e1 = ctx->tk_share * (BigU(2) * ctx->tk_delta);
+    const uint32_t rbits = 32 * S;
+    const size_t bits = std::max<size_t>(e1.bitlen(), rbits);
+    int w = 3;
+    { double best = 1e300; for (int cnd = 3; cnd <= 6; ++cnd) { const double cost = 2.0 * ((double)bits / cnd + 2.0 * (1u << cnd)); if (cost < best) { best = cost; w = cnd; } } }
+    const uint32_t nb = 1u << w, per = nb + 1, nwin = (uint32_t)((bits + w - 1) / w);
+    const uint32_t CH = 2 * per, RUN = CH + 1, ACC = CH + 2;
+    const std::string key = "pdz:" + std::to_string(S) + ":" + e1.hex();
+    Program* P = cached_program(ctx, key);
+    if (!P) {
+        Program np;
+        np.emit(OP_LDC, K_R1);
+        for (uint32_t s = 0; s < 2; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
+        np.use_slot(ACC);
+        np.emit(OP_LDI, 0);
+        np.emit(OP_MULC, K_R2); np.n_mul++;
+        for (uint32_t win = 0; win < nwin; ++win) {
+            uint32_t d1 = 0;
+            for (int b = w - 1; b >= 0; --b) d1 = (d1 << 1) | (e1.bit((size_t)win * w + b) ? 1u : 0u);
+            if (d1) {                                                     // chain = c^(2^(w*win)): the key exponent's digit
+                np.emit(OP_STT, CH);
+                np.emit(OP_MULT, d1); np.n_mul++;
+                np.emit(OP_STT, d1);
+                np.emit(OP_LDT, CH);
+            }
+            np.emit(OP_SQR, 2); np.n_sqr += 2;                            // chain = (c^4)^(2^(w*win)): r's digit
+            np.emit(OP_STT, CH);
+            np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (1u << 24)); np.n_mul++;
+            if (win + 1 < nwin) { np.emit(OP_LDT, CH); np.emit(OP_SQR, (uint32_t)w - 2); np.n_sqr += w - 2; }
+        }
+        for (uint32_t s = 0; s < 2; ++s) {
+            np.emit(OP_LDT, s * per + nb - 1);
+            np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
+            for (uint32_t d = nb - 2; d >= 1; --d) {
+                np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
+                np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
+            }
+            np.emit(OP_MULC, K_ONE); np.n_mul++;
+            np.emit(OP_STOO, s);                                          // out[0] = c_i, out[1] = a
+        }
+        int rc = program_upload(ctx, np);
+        if (rc) return rc;
+        P = &(ctx->prog_cache[key] = np);
+    }
+    IoDesc ins[1] = {{c, S, S}};
+    ExpDesc ex{r, S, rbits, nullptr, 0};
+    return run_vm(ctx, M, *P, count, ins, 1, dec, S, S, ex, a, S);
+}
+
 // PartialDecryptionWithZKP (thresholdkey.go:225-255), r supplied
 int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* e, uint32_t* z, bool dec_given) {
     if (!ctx->has_share) return fail(ctx, PGPU_ERR_STATE, "PartialDecryptionWithZKP: no threshold share loaded");
@@ -788,13 +845,18 @@ int zkp_prove_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t
     const BigU k = ctx->tk_delta * ctx->tk_share;
     if (k.v.size() + 8 + 1 > z_limbs(ctx)) return fail(ctx, PGPU_ERR_ARG, "PartialDecryptionWithZKP: the share is not below n^2");
     int rc;
-    if (!dec_given && (rc = pdec_dev(ctx, count, c, dec))) return rc;
+    static const bool no_fused = getenv("PGPU_NO_FUSED_PROVE") != nullptr;
     DEVBUF(c4r, ctx, count * S); DEVBUF(a, ctx, count * S); DEVBUF(b, ctx, count * S); DEVBUF(v, ctx, S);
     DEVBUF(kd, ctx, k.v.size() + 1);
     if ((rc = upload(ctx, v.p, ctx->tk_v.limbs(S)))) return rc;
     if ((rc = upload(ctx, kd.p, k.limbs(k.v.size() + 1)))) return rc;
-    if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), c4r.p))) return rc;           // c^4 mod n^2: (c^4)^r = (c^4 mod n^2)^r
-    if ((rc = modexp_items_dev(ctx, M, count, c4r.p, r, S, a.p))) return rc;             // a = (c^4)^r        :242
+    if (!dec_given && !no_fused) {
+        if ((rc = pdec_and_a_dev(ctx, count, c, r, dec, a.p))) return rc;                // c_i :199 and a = (c^4)^r :242, shared squarings
+    } else {
+        if (!dec_given && (rc = pdec_dev(ctx, count, c, dec))) return rc;
+        if ((rc = modexp_shared_dev(ctx, M, count, c, BigU(4), c4r.p))) return rc;       // c^4 mod n^2: (c^4)^r = (c^4 mod n^2)^r
+        if ((rc = modexp_items_dev(ctx, M, count, c4r.p, r, S, a.p))) return rc;         // a = (c^4)^r        :242
+    }
     if ((rc = ensure_fix_v(ctx))) return rc;
     if ((rc = modexp_fixed_dev(ctx, M, ctx->fix_v, count, ExpDesc{r, S, 32 * S, nullptr}, b.p))) return rc;   // b = V^r (fixed base) :245
     if ((rc = zkp_hash_dev(ctx, count, a.p, b.p, c, dec, e))) return rc;                 // E                  :250

@@ -115,10 +115,11 @@ struct DeviceRound {
         CU(ctx, cudaMemcpyAsync(dc->p, c, count * S * 4, cudaMemcpyHostToDevice, st));
         if (zkp) CU(ctx, cudaMemcpyAsync(dr->p, r, count * S * 4, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaEventRecord(ev[0], st));
-        if ((rc = pdec_dev(ctx, count, dc->p, dec->p + (size_t)g * count * S))) return rc;
+        // with proofs the partial decryption comes out of the proof's launch (shared squarings): the "pdec" phase is empty
+        if (!zkp && (rc = pdec_dev(ctx, count, dc->p, dec->p + (size_t)g * count * S))) return rc;
         CU(ctx, cudaEventRecord(ev[1], st));
         if (zkp && (rc = zkp_prove_dev(ctx, count, dc->p, dr->p, dec->p + (size_t)g * count * S, de->p + (size_t)g * count * 8,
-                                        dz->p + (size_t)g * count * ZL, true))) return rc;
+                                        dz->p + (size_t)g * count * ZL, false))) return rc;
         CU(ctx, cudaEventRecord(ev[2], st));
         return PGPU_OK;
     }

@@ -242,19 +242,25 @@ def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: 
     try:
         with torch.cuda.stream(stream):
             dec = torch.empty(k * count * w2, dtype=torch.uint8, device=dev)
-            ev["pdec"][0].record(stream)
-            for j, t in enumerate(tsks):
-                check(lib.pgpu_partial_decrypt_dev(t._ctx, count, vp(c_dev), vp(dec[j * count * w2:])), t._ctx)
-            ev["pdec"][1].record(stream)
             e = z = None
+            fused = zkp_r is not None and not os.environ.get("PGPU_NO_FUSED_PROVE")
+            ev["pdec"][0].record(stream)
+            if not fused:
+                for j, t in enumerate(tsks):
+                    check(lib.pgpu_partial_decrypt_dev(t._ctx, count, vp(c_dev), vp(dec[j * count * w2:])), t._ctx)
+            ev["pdec"][1].record(stream)
             ev["prove"][0].record(stream)
             if zkp_r is not None:
                 e = torch.empty(k * count * 32, dtype=torch.uint8, device=dev)
                 z = torch.empty(k * count * wz, dtype=torch.uint8, device=dev)
                 for j, t in enumerate(tsks):
                     # (slices of live tensors: their storage stays allocated)
-                    check(lib.pgpu_pdec_zkp_prove_given_dev(t._ctx, count, vp(c_dev), vp(zkp_r[j]), vp(dec[j * count * w2:]),
-                                                            vp(e[j * count * 32:]), vp(z[j * count * wz:])), t._ctx)
+                    if fused:      # PartialDecrypt and (c^4)^r in one launch with shared squarings: the "pdec" phase is empty
+                        check(lib.pgpu_pdec_zkp_prove_dev(t._ctx, count, vp(c_dev), vp(zkp_r[j]), vp(dec[j * count * w2:]),
+                                                          vp(e[j * count * 32:]), vp(z[j * count * wz:])), t._ctx)
+                    else:
+                        check(lib.pgpu_pdec_zkp_prove_given_dev(t._ctx, count, vp(c_dev), vp(zkp_r[j]), vp(dec[j * count * w2:]),
+                                                                vp(e[j * count * 32:]), vp(z[j * count * wz:])), t._ctx)
             ev["prove"][1].record(stream)
             # ---- the one exchange of the path: [share][ciphertext] on every rank
             ev["all_gather"][0].record(stream)
