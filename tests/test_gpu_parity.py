@@ -510,3 +510,39 @@ def test_dedicated_squaring_is_race_free_by_determinism(sk2048):
              "assert np.array_equal(sk.decrypt_records(c), m)\nprint('ok')\n" % root)
     r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, PGPU_NO_SQR="1"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def test_fused_prove_equals_separate_exponentiations():
+    # PartialDecryptionWithZKP computes c^(2*delta*s) and (c^4)^r in one launch with shared squarings; with
+    # PGPU_NO_FUSED_PROVE=1 (child process) it runs the two exponentiations separately: same (c_i, E, Z), and both equal libgmp's
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = ("import sys, hashlib, random; sys.path.insert(0, %r)\n"
+            "from paillier_b200 import synth\nfrom paillier_b200.keygen import ThresholdKeyGenerator\n"
+            "p, q = synth.load_key('threshold_2048'); n = p * q\n"
+            "tsk = ThresholdKeyGenerator(2048, 8, 5, rng=random.Random(5)).with_safe_primes(p, q).GenerateKeys()[3]\n"
+            "c = tsk.encrypt_with_r_records(synth.plaintexts(700, n, tsk.w_n), synth.randomness(700, n, tsk.w_n))\n"
+            "r = synth.random_records(700, tsk.w_n2, 2 * n.bit_length() - 2, stream=44)\n"
+            "print('DIGEST', hashlib.sha256(b''.join(x.tobytes() for x in tsk.zkp_prove_records(c, r))).hexdigest())\n" % root)
+    digests = []
+    for env in ({}, {"PGPU_NO_FUSED_PROVE": "1"}):
+        r = subprocess.run([sys.executable, "-c", prog], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        digests.append([l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1]
+    import random
+    p, q, n = _key("threshold_2048")
+    from paillier_b200.keygen import ThresholdKeyGenerator
+    keys = ThresholdKeyGenerator(2048, 8, 5, rng=random.Random(5)).with_safe_primes(p, q).GenerateKeys()
+    tsk = keys[3]
+    for k in keys:
+        if k is not tsk:
+            k.close()
+    c = tsk.encrypt_with_r_records(synth.plaintexts(700, n, tsk.w_n), synth.randomness(700, n, tsk.w_n))
+    r = synth.random_records(700, tsk.w_n2, 2 * n.bit_length() - 2, stream=44)
+    ref = G.pdec_zkp(n, tsk.Share, 8, tsk.VerificationKey, c, r, tsk.w_n2, tsk.w_z)
+    assert "DIGEST " + hashlib.sha256(b"".join(x.tobytes() for x in ref)).hexdigest() == digests[0]
+    tsk.close()
