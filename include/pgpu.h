@@ -314,6 +314,15 @@ int pgpu_ctx_last_kernel_ms(pgpu_ctx* ctx, float* ms);
 int pgpu_selftest_bn(int op, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len,
                      const uint8_t* m, size_t m_len, uint8_t* out, size_t* out_len);
 
+/* host interpreter of the exponentiation programs the library compiles, for the CPU test suite (no GPU, not used by any
+ * other entry point): kind 0 = sliding window over the shared exponent shared_exp_be -> base^e; 1 = fixed windows over the
+ * per-item exponent item_exps[0..exp_limbs) -> base^exp; 2 = shared-base multi-exponentiation of k exponents (item_exps =
+ * k records of exp_limbs little-endian limbs) -> (base^pre)^exp_s; 3 = PartialDecrypt fused with the proof's power ->
+ * base^e and (base^4)^exp.  out = *n_out big-endian records of mod_len bytes; n_sqr / n_mul = the program's cost. */
+int pgpu_selftest_program(int kind, const uint8_t* mod_be, size_t mod_len, const uint8_t* base_be, size_t base_len,
+                          const uint8_t* shared_exp_be, size_t shared_len, const uint32_t* item_exps, uint32_t exp_limbs, uint32_t k, uint32_t pre,
+                          uint8_t* out, size_t out_cap, uint32_t* n_out, uint32_t* n_sqr, uint32_t* n_mul);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,8 @@ SIGNATURES = {
     "pgpu_ctx_kernel_shape": (C.c_int, [_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pgpu_ctx_enable_timing": (C.c_int, [_p, C.c_int]),
     "pgpu_ctx_last_kernel_ms": (C.c_int, [_p, C.POINTER(C.c_float)]),
+    "pgpu_selftest_program": (C.c_int, [C.c_int, _u8p, _sz, _u8p, _sz, _u8p, _sz, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _sz,
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_selftest_bn": (C.c_int, [C.c_int, _u8p, _sz, _u8p, _sz, _u8p, _sz, C.c_char_p, C.POINTER(_sz)]),
 }
 

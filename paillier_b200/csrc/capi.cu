@@ -7,6 +7,59 @@ using namespace pgpu;
 #define g_err (::pgpu::thread_error())
 
 // =========================================================== extern "C" API
+// Host interpreter of the micro-programs (vm.h) on BigU integers, for the CPU test suite only (tests/test_host_programs.py):
+// the exponentiation schedules the host compiles -- sliding window over a shared exponent, fixed windows over per-item exponents,
+// the right-to-left bucket programs of the proofs -- are executed with plain modular arithmetic (Montgomery radix 1) and compared
+// with pow().  It checks the COMPILER of the programs without a GPU; no entry point of the product routes through it.
+namespace {
+uint32_t host_exp_bits(const uint32_t* e, uint32_t nbits, uint32_t pos, uint32_t w) {
+    if (pos >= nbits) return 0;
+    const uint32_t limb = pos >> 5, sh = pos & 31, nlimbs = (nbits + 31) >> 5;
+    uint64_t v = e[limb];
+    if (sh + w > 32 && limb + 1 < nlimbs) v |= (uint64_t)e[limb + 1] << 32;
+    uint32_t r = (uint32_t)(v >> sh) & ((1u << w) - 1u);
+    if (pos + w > nbits) r &= (1u << (nbits - pos)) - 1u;
+    return r;
+}
+
+int host_vm_run(const Program& P, const BigU& N, const BigU& in0, const uint32_t* exps, uint32_t exp_limbs, uint32_t exp_sub, std::vector<BigU>& outs) {
+    const uint32_t nbits = 32 * exp_limbs;
+    std::map<uint32_t, BigU> T;
+    BigU x;
+    auto mulmod = [&](const BigU& a, const BigU& b) { return (a * b) % N; };
+    auto kconst = [&](uint32_t slot, BigU& v) { if (slot == K_R1 || slot == K_R2 || slot == K_ONE) { v = BigU(1); return true; } return false; };
+    for (uint32_t op : P.ops) {
+        const uint32_t code = op >> 27, arg = op & 0x07ffffffu;
+        uint32_t nsq = 0; bool mul = false; BigU y; uint32_t bkt = 0xffffffffu;
+        switch (code) {
+            case OP_END: return PGPU_OK;
+            case OP_LDI: if (arg != 0) return PGPU_ERR_UNSUPPORTED; x = in0; break;
+            case OP_LDC: if (!kconst(arg, x)) return PGPU_ERR_UNSUPPORTED; break;
+            case OP_LDT: x = T[arg]; break;
+            case OP_STT: T[arg] = x; break;
+            case OP_STO: if (outs.size() < 1) outs.resize(1); outs[0] = x % N; break;
+            case OP_STOO: { const uint32_t slot = (arg & 1u) ? 1u : (arg >> 2);        // out[1][item] or out[0][item, off]
+                            if (outs.size() <= slot) outs.resize(slot + 1); outs[slot] = x % N; } break;
+            case OP_SQR: nsq = arg; break;
+            case OP_MULT: y = T[arg]; mul = true; break;
+            case OP_MULC: if (!kconst(arg, y)) return PGPU_ERR_UNSUPPORTED; mul = true; break;
+            case OP_WIN: { const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, tbase = arg >> 24;
+                           y = T[tbase + host_exp_bits(exps, nbits, pos, w)]; nsq = w; mul = true; } break;
+            case OP_SQMT: y = T[arg >> 12]; nsq = arg & 0xfffu; mul = true; break;
+            case OP_BKT: { const uint32_t pos = arg & 0xfffffu, w = (arg >> 20) & 0xfu, sub = arg >> 24;
+                           bkt = sub * ((1u << w) + 1u) + host_exp_bits(exps + (size_t)sub * exp_sub, nbits, pos, w);      // VmParams::exp_sub
+                           y = T[bkt]; mul = true; } break;
+            default: return PGPU_ERR_UNSUPPORTED;
+        }
+        for (uint32_t i = 0; i < nsq; ++i) x = mulmod(x, x);
+        if (mul) x = mulmod(x, y);
+        if (bkt != 0xffffffffu) T[bkt] = x;
+    }
+    return PGPU_OK;
+}
+}  // namespace
+
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -1066,6 +1119,38 @@ int pgpu_selftest_bn(int op, const uint8_t* a, size_t a_len, const uint8_t* b, s
     if (nbytes > *out_len) return fail(nullptr, PGPU_ERR_ARG, "output buffer too small");
     for (size_t i = 0; i < nbytes; ++i) out[nbytes - 1 - i] = (uint8_t)(r.v[i / 4] >> (8 * (i % 4)));
     *out_len = nbytes;
+    return PGPU_OK;
+    GUARD_END(nullptr)
+}
+
+int pgpu_selftest_program(int kind, const uint8_t* mod_be, size_t mod_len, const uint8_t* base_be, size_t base_len,
+                          const uint8_t* shared_exp_be, size_t shared_len, const uint32_t* item_exps, uint32_t exp_limbs, uint32_t k, uint32_t pre,
+                          uint8_t* out, size_t out_cap, uint32_t* n_out, uint32_t* n_sqr, uint32_t* n_mul) {
+    GUARD_BEGIN
+    REQUIRE(nullptr, mod_be && base_be && out && n_out, "null argument");
+    const BigU N = BigU::from_be(mod_be, mod_len), base = BigU::from_be(base_be, base_len), e = BigU::from_be(shared_exp_be, shared_len);
+    REQUIRE(nullptr, !N.is_zero(), "zero modulus");
+    Program P;
+    switch (kind) {
+        case 0: P.emit(OP_LDI, 0); P.emit(OP_MULC, K_R2); emit_pow_shared(P, e, 0); P.emit(OP_MULC, K_ONE); P.emit(OP_STO, 0); break;
+        case 1: REQUIRE(nullptr, item_exps && exp_limbs, "no exponent"); P.emit(OP_LDI, 0); P.emit(OP_MULC, K_R2); emit_pow_items(P, 32 * exp_limbs, 0);
+                P.emit(OP_MULC, K_ONE); P.emit(OP_STO, 0); break;
+        case 2: REQUIRE(nullptr, item_exps && exp_limbs && k >= 1 && k <= 8, "1 to 8 exponents"); build_multi_program(P, k, 32 * exp_limbs, pre); break;
+        case 3: REQUIRE(nullptr, item_exps && exp_limbs, "no exponent"); build_pdec_a_program(P, e, 32 * exp_limbs); break;
+        default: return fail(nullptr, PGPU_ERR_ARG, "bad program kind");
+    }
+    P.ops.push_back(vm_op(OP_END, 0));
+    std::vector<BigU> outs;
+    const int rc = host_vm_run(P, N, base, item_exps, exp_limbs, kind == 2 ? exp_limbs : 0u, outs);
+    if (rc) return fail(nullptr, rc, "host interpreter: op not supported");
+    REQUIRE(nullptr, outs.size() * mod_len <= out_cap, "output buffer too small");
+    for (size_t j = 0; j < outs.size(); ++j) {
+        std::vector<uint32_t> l = outs[j].limbs((mod_len + 3) / 4);
+        for (size_t i = 0; i < mod_len; ++i) out[j * mod_len + (mod_len - 1 - i)] = (uint8_t)(l[i / 4] >> (8 * (i % 4)));
+    }
+    *n_out = (uint32_t)outs.size();
+    if (n_sqr) *n_sqr = P.n_sqr;
+    if (n_mul) *n_mul = P.n_mul;
     return PGPU_OK;
     GUARD_END(nullptr)
 }

@@ -489,48 +489,60 @@ int modexp_items_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, const uint32_
 // digit (one multiplication per window and exponent, OP_BKT with sub = s); per exponent the buckets are then folded into
 // prod_d T[d]^d with the running-product trick.  nwin*w squarings + k*(nwin + 2*2^w) multiplications per base instead of
 // k*(nwin*w + nwin + 2^w): 3.7x fewer for k = 8 at 6656-bit exponents.
+// window width of the bucket method for k exponents of `bits` bits
+// (w <= 6: 8 x 65 buckets of 768 B per resident group are 1.9 GB at 6144 bits; w = 7 would save 1 % for twice that)
+static int multi_window(uint32_t k, uint32_t bits) {
+    int w = 1;
+    double best = 1e300;
+    for (int c = 1; c <= 6; ++c) { const double cost = (double)k * ((double)bits / c + 2.0 * (1u << c)); if (cost < best) { best = cost; w = c; } }
+    return w;
+}
+
+// in0 = base (plain); out[0][item*k + s] = (base^pre)^(exp_s), exp_s = exponent s of the item (OP_BKT with sub = s)
+void build_multi_program(Program& np, uint32_t k, uint32_t bits, uint32_t pre) {
+    const int w = multi_window(k, bits);
+    const uint32_t nb = 1u << w, per = nb + 1, nwin = (bits + w - 1) / w;
+    const uint32_t CH = k * per, RUN = CH + 1, ACC = CH + 2;
+    np.emit(OP_LDC, K_R1);
+    for (uint32_t s = 0; s < k; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
+    np.use_slot(ACC);
+    np.emit(OP_LDI, 0);
+    np.emit(OP_MULC, K_R2); np.n_mul++;
+    if (pre == 2) { np.emit(OP_SQR, 1); np.n_sqr += 1; }
+    if (pre == 4) { np.emit(OP_SQR, 2); np.n_sqr += 2; }
+    for (uint32_t win = 0; win < nwin; ++win) {
+        np.emit(OP_STT, CH);                                                              // the chain value of this window
+        for (uint32_t s = 0; s < k; ++s) {
+            np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (s << 24)); np.n_mul++;     // T[s][digit] *= chain
+            if (s + 1 < k || win + 1 < nwin) np.emit(OP_LDT, CH);
+        }
+        if (win + 1 < nwin) { np.emit(OP_SQR, (uint32_t)w); np.n_sqr += w; }
+    }
+    for (uint32_t s = 0; s < k; ++s) {
+        // run = T[nb-1]; acc = run; for d = nb-2 .. 1: run *= T[d]; acc *= run          (acc = prod_d T[d]^d)
+        np.emit(OP_LDT, s * per + nb - 1);
+        if (nb > 2) {
+            np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
+            for (uint32_t d = nb - 2; d >= 1; --d) {
+                np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
+                np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
+            }
+        }
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STOO, (s << 2) | 0u);
+    }
+}
+
 int modexp_multi_dev(pgpu_ctx* ctx, const ModCtx& M, size_t count, uint32_t k, const uint32_t* base, uint32_t pre, const uint32_t* exp, uint32_t exp_limbs,
                      uint32_t* out) {
     if (k == 0 || count == 0) return PGPU_OK;
     if (k > 8) return fail(ctx, PGPU_ERR_ARG, "modexp_multi: at most 8 exponents per base");
     const uint32_t S = M.sh.S, bits = 32 * exp_limbs;
-    int w = 1;
-    // (w <= 6: 8 x 65 buckets of 768 B per resident group are 1.9 GB at 6144 bits; w = 7 would save 1 % for twice that)
-    { double best = 1e300; for (int c = 1; c <= 6; ++c) { const double cost = (double)k * ((double)bits / c + 2.0 * (1u << c)); if (cost < best) { best = cost; w = c; } } }
-    const uint32_t nb = 1u << w, per = nb + 1, nwin = (bits + w - 1) / w;
-    const uint32_t CH = k * per, RUN = CH + 1, ACC = CH + 2;
     const std::string key = "multi:" + std::to_string(S) + ":" + std::to_string(k) + ":" + std::to_string(bits) + ":" + std::to_string(pre);
     Program* P = cached_program(ctx, key);
     if (!P) {
         Program np;
-        np.emit(OP_LDC, K_R1);
-        for (uint32_t s = 0; s < k; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
-        np.use_slot(ACC);
-        np.emit(OP_LDI, 0);
-        np.emit(OP_MULC, K_R2); np.n_mul++;
-        if (pre == 2) { np.emit(OP_SQR, 1); np.n_sqr += 1; }
-        if (pre == 4) { np.emit(OP_SQR, 2); np.n_sqr += 2; }
-        for (uint32_t win = 0; win < nwin; ++win) {
-            np.emit(OP_STT, CH);                                                              // the chain value of this window
-            for (uint32_t s = 0; s < k; ++s) {
-                np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (s << 24)); np.n_mul++;     // T[s][digit] *= chain
-                if (s + 1 < k || win + 1 < nwin) np.emit(OP_LDT, CH);
-            }
-            if (win + 1 < nwin) { np.emit(OP_SQR, (uint32_t)w); np.n_sqr += w; }
-        }
-        for (uint32_t s = 0; s < k; ++s) {
-            // run = T[nb-1]; acc = run; for d = nb-2 .. 1: run *= T[d]; acc *= run          (acc = prod_d T[d]^d)
-            np.emit(OP_LDT, s * per + nb - 1);
-            if (nb > 2) {
-                np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
-                for (uint32_t d = nb - 2; d >= 1; --d) {
-                    np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
-                    np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
-                }
-            }
-            np.emit(OP_MULC, K_ONE); np.n_mul++;
-            np.emit(OP_STOO, (s << 2) | 0u);
-        }
+        build_multi_program(np, k, bits, pre);
         int rc = program_upload(ctx, np);
         if (rc) return rc;
         P = &(ctx->prog_cache[key] = np);
@@ -785,49 +797,54 @@ int zkp_hash_dev(pgpu_ctx* ctx, size_t count, const uint32_t* a, const uint32_t*
 // c, c^2, c^4, ...: per window of w bits the chain value goes into the bucket of the key exponent's digit (known to the host:
 // a static table index) and, two squarings later, into the bucket of r's digit (OP_BKT); the two bucket sets are folded
 // into prod_d T[d]^d.  ~6160 squarings + 2*(nwin + 2^(w+1)) multiplications instead of two exponentiations of ~7000 each.
-static int pdec_and_a_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* a) {
-    ModCtx& M = ctx->m_n2;
-    const uint32_t S = M.sh.S;
-    const BigU e1 = ctx->tk_share * (BigU(2) * ctx->tk_delta);
-    const uint32_t rbits = 32 * S;
+// in0 = c (plain); out[0] = c^e1, out[1] = (c^4)^(item exponent of rbits bits)
+void build_pdec_a_program(Program& np, const BigU& e1, uint32_t rbits) {
     const size_t bits = std::max<size_t>(e1.bitlen(), rbits);
     int w = 3;
     { double best = 1e300; for (int cnd = 3; cnd <= 6; ++cnd) { const double cost = 2.0 * ((double)bits / cnd + 2.0 * (1u << cnd)); if (cost < best) { best = cost; w = cnd; } } }
     const uint32_t nb = 1u << w, per = nb + 1, nwin = (uint32_t)((bits + w - 1) / w);
     const uint32_t CH = 2 * per, RUN = CH + 1, ACC = CH + 2;
+    np.emit(OP_LDC, K_R1);
+    for (uint32_t s = 0; s < 2; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
+    np.use_slot(ACC);
+    np.emit(OP_LDI, 0);
+    np.emit(OP_MULC, K_R2); np.n_mul++;
+    for (uint32_t win = 0; win < nwin; ++win) {
+        uint32_t d1 = 0;
+        for (int b = w - 1; b >= 0; --b) d1 = (d1 << 1) | (e1.bit((size_t)win * w + b) ? 1u : 0u);
+        if (d1) {                                                     // chain = c^(2^(w*win)): the key exponent's digit
+            np.emit(OP_STT, CH);
+            np.emit(OP_MULT, d1); np.n_mul++;
+            np.emit(OP_STT, d1);
+            np.emit(OP_LDT, CH);
+        }
+        np.emit(OP_SQR, 2); np.n_sqr += 2;                            // chain = (c^4)^(2^(w*win)): r's digit
+        np.emit(OP_STT, CH);
+        np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (1u << 24)); np.n_mul++;
+        if (win + 1 < nwin) { np.emit(OP_LDT, CH); np.emit(OP_SQR, (uint32_t)w - 2); np.n_sqr += w - 2; }
+    }
+    for (uint32_t s = 0; s < 2; ++s) {
+        np.emit(OP_LDT, s * per + nb - 1);
+        np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
+        for (uint32_t d = nb - 2; d >= 1; --d) {
+            np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
+            np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
+        }
+        np.emit(OP_MULC, K_ONE); np.n_mul++;
+        np.emit(OP_STOO, s);                                          // out[0] = c_i, out[1] = a
+    }
+}
+
+static int pdec_and_a_dev(pgpu_ctx* ctx, size_t count, const uint32_t* c, const uint32_t* r, uint32_t* dec, uint32_t* a) {
+    ModCtx& M = ctx->m_n2;
+    const uint32_t S = M.sh.S;
+    const BigU e1 = ctx->tk_share * (BigU(2) * ctx->tk_delta);
+    const uint32_t rbits = 32 * S;
     const std::string key = "pdz:" + std::to_string(S) + ":" + e1.hex();
     Program* P = cached_program(ctx, key);
     if (!P) {
         Program np;
-        np.emit(OP_LDC, K_R1);
-        for (uint32_t s = 0; s < 2; ++s) for (uint32_t d = 0; d <= nb; ++d) np.emit(OP_STT, s * per + d);       // every bucket = 1
-        np.use_slot(ACC);
-        np.emit(OP_LDI, 0);
-        np.emit(OP_MULC, K_R2); np.n_mul++;
-        for (uint32_t win = 0; win < nwin; ++win) {
-            uint32_t d1 = 0;
-            for (int b = w - 1; b >= 0; --b) d1 = (d1 << 1) | (e1.bit((size_t)win * w + b) ? 1u : 0u);
-            if (d1) {                                                     // chain = c^(2^(w*win)): the key exponent's digit
-                np.emit(OP_STT, CH);
-                np.emit(OP_MULT, d1); np.n_mul++;
-                np.emit(OP_STT, d1);
-                np.emit(OP_LDT, CH);
-            }
-            np.emit(OP_SQR, 2); np.n_sqr += 2;                            // chain = (c^4)^(2^(w*win)): r's digit
-            np.emit(OP_STT, CH);
-            np.emit(OP_BKT, (win * w) | ((uint32_t)w << 20) | (1u << 24)); np.n_mul++;
-            if (win + 1 < nwin) { np.emit(OP_LDT, CH); np.emit(OP_SQR, (uint32_t)w - 2); np.n_sqr += w - 2; }
-        }
-        for (uint32_t s = 0; s < 2; ++s) {
-            np.emit(OP_LDT, s * per + nb - 1);
-            np.emit(OP_STT, RUN); np.emit(OP_STT, ACC);
-            for (uint32_t d = nb - 2; d >= 1; --d) {
-                np.emit(OP_LDT, RUN); np.emit(OP_MULT, s * per + d); np.n_mul++; np.emit(OP_STT, RUN);
-                np.emit(OP_MULT, ACC); np.n_mul++; np.emit(OP_STT, ACC);
-            }
-            np.emit(OP_MULC, K_ONE); np.n_mul++;
-            np.emit(OP_STOO, s);                                          // out[0] = c_i, out[1] = a
-        }
+        build_pdec_a_program(np, e1, rbits);
         int rc = program_upload(ctx, np);
         if (rc) return rc;
         P = &(ctx->prog_cache[key] = np);

@@ -209,6 +209,8 @@ void modctx_free(ModCtx& m);
 int choose_window(size_t bits);
 void emit_pow_shared(Program& P, const BigU& e, uint32_t tb);
 void emit_pow_items(Program& P, size_t exp_bits, uint32_t tb);
+void build_multi_program(Program& P, uint32_t k, uint32_t bits, uint32_t pre);
+void build_pdec_a_program(Program& P, const BigU& e1, uint32_t rbits);
 int program_upload(pgpu_ctx* ctx, Program& P);
 void program_free(Program& P);
 int ensure_table(pgpu_ctx* ctx, size_t limbs);
