@@ -207,7 +207,6 @@ func (t *ThresholdGroup) Decrypt(cs []*gmp.Int, zkpR [][]*gmp.Int) (plain []*gmp
 	m := make([]byte, count*g.wN)
 	itemOK := make([]byte, count)
 	var rp *unsafe.Pointer
-	var keep [][]byte
 	if zkpR != nil {
 		if len(zkpR) != int(C.pgpu_multi_size(t.m)) {
 			return nil, nil, errors.New("one slice of randomness per share-holder")
@@ -221,7 +220,6 @@ func (t *ThresholdGroup) Decrypt(cs []*gmp.Int, zkpR [][]*gmp.Int) (plain []*gmp
 			arr[j] = rec
 		}
 		rp = &arr[0]
-		_ = keep
 	}
 	rc := C.pgpu_multi_threshold_round(t.m, C.size_t(count), ptr(c), rp, ptr(m), (*C.uint8_t)(ptr(itemOK)))
 	if rc != C.PGPU_OK && rc != C.PGPU_ERR_THRESHOLD {
