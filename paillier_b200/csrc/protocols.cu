@@ -44,10 +44,12 @@ int fixed_table_build(pgpu_ctx* ctx, const ModCtx& M, const BigU& base, uint32_t
     fixed_table_free(T);
     if (exp_bits == 0) return fail(ctx, PGPU_ERR_ARG, "fixed-base table for an empty exponent");
     const uint32_t S = M.sh.S;
+    // widest window whose table stays below the cap (PGPU_FIXED_TABLE_MB, default 32 = L2-resident); one multiplication per window
+    static const size_t cap_mb = [] { const char* e = getenv("PGPU_FIXED_TABLE_MB"); const long v = e ? atol(e) : 32; return (size_t)(v < 1 ? 1 : v); }();
     uint32_t w = 1;
     for (uint32_t c = 2; c <= 8; ++c) {
         const size_t nwin = (exp_bits + c - 1) / c;
-        if ((nwin << c) * S * 4 <= ((size_t)32 << 20)) w = c;
+        if ((nwin << c) * S * 4 <= (cap_mb << 20)) w = c;
     }
     const uint32_t nwin = (exp_bits + w - 1) / w, per = 1u << w;
     const uint32_t el = (w * (nwin - 1)) / 32 + 1;
