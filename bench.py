@@ -694,6 +694,12 @@ def main() -> None:
                 light[name]["e2e_pageable_items_per_s"] = lcount_ / pg
         assert torch.equal(o_host, o_dev.cpu()), "host and device paths of EncryptWithRn differ"
         breakdown["light_ops"] = light
+        try:     # AltEncryptWithR end to end (measured above, unchunked host path) against the same PCIe bound
+            ab = max(breakdown["alt_enc_items"] * 2 * w_n / (pcie["h2d_gbs"] * 1e9), breakdown["alt_enc_items"] * w_n2 / (pcie["d2h_gbs"] * 1e9))
+            light["alt_encrypt"] = {"e2e_items_per_s": breakdown["alt_enc_e2e_per_s"], "e2e_frac_of_pcie_bound": ab / (breakdown["alt_enc_items"] / breakdown["alt_enc_e2e_per_s"] * world),
+                                    "note": "~205 fixed-base multiplications per item: bound by the multiplier, not by the link"}
+        except Exception:
+            pass
         del rn_dev, o_dev, rn_host, o_host, c_host_l
         # level 2 (mod n^3): EncryptWithRAtLevel + Decrypt (CRT over p^3, q^3) through the host-buffer ABI
         lcount = max(1, min(count, 1 << 15))
