@@ -12,7 +12,12 @@
 //                                                   <- paillier.go:344-372, operations.go:75-91, ddleq.go:27-153
 //   paillier::SafePrimeScan / MillerRabinBatch      <- safe_prime.go:170-278
 //   paillier::ThresholdSecretKey::PartialDecryptBatch / PartialDecryptionWithZKPBatch  <- thresholdkey.go:192-255
-//   paillier::ThresholdPublicKey::VerifyProofBatch / CombinePartialDecryptionsBatch    <- thresholdkey.go:149-172,278-311
+//   paillier::ThresholdPublicKey::VerifyProofBatch / CombinePartialDecryptionsBatch / CombinePartialDecryptionsZKPBatch /
+//     VerifyDecryptionBatch                                                             <- thresholdkey.go:149-189,278-311
+//   paillier::ThresholdSecretKey::GetPublicKey / VerifyPartialDecryption                <- thresholdkey.go:213-222,258-275
+//   the callers that draw their own randomness (paillier::RandomSource, default the OS CSPRNG) or take an argument list:
+//   PublicKey::EncryptBatch / EncryptAtLevelBatch / NestedEncryptBatch / AltEncryptAtLevelBatch / EncryptZero*Batch /
+//     EncryptOne*Batch / RandomizeBatch / NestedRandomizeBatch / SubBatch  <- paillier.go:192-203,244-289, operations.go:32-55,67-118
 //
 // Big integers cross this layer as paillier::Int = big-endian magnitude bytes, exactly what gmp.Int.Bytes() returns
 // (zero is the empty string).  The layer only marshals to the fixed-width little-endian records of the C ABI; all
@@ -20,6 +25,9 @@
 // code; the reference's error strings ("Threshold not meet", ...) are the message.
 #pragma once
 #include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -102,7 +110,52 @@ inline void reduce_pow2(Int& x, unsigned bits) {
     while (z < x.size() && x[z] == 0) ++z;
     x.erase(x.begin(), x.begin() + z);
 }
+// big-endian magnitudes without leading zeros: a < b
+inline bool less(const Int& a, const Int& b) { return a.size() != b.size() ? a.size() < b.size() : a < b; }
+// a * b on big-endian magnitudes (schoolbook; key set-up only: n^2 for the range of a proof's r)
+inline Int mul(const Int& a, const Int& b) {
+    if (a.empty() || b.empty()) return {};
+    std::vector<uint32_t> acc(a.size() + b.size(), 0);           // little-endian byte columns
+    for (size_t i = 0; i < a.size(); ++i)
+        for (size_t j = 0; j < b.size(); ++j) {
+            const size_t k = i + j;
+            acc[k] += (uint32_t)a[a.size() - 1 - i] * b[b.size() - 1 - j];
+            if (acc[k] >> 24) { acc[k + 1] += acc[k] >> 8; acc[k] &= 0xff; }
+        }
+    Int out(acc.size());
+    uint32_t carry = 0;
+    for (size_t k = 0; k < acc.size(); ++k) { carry += acc[k]; out[acc.size() - 1 - k] = (uint8_t)carry; carry >>= 8; }
+    size_t z = 0;
+    while (z < out.size() && out[z] == 0) ++z;
+    out.erase(out.begin(), out.begin() + z);
+    return out;
+}
 }  // namespace detail
+
+// Source of random bytes for the methods that draw their own randomness (the reference reads crypto/rand.Reader,
+// utils.go:26-49): fills `len` bytes.  The default reads the operating system's CSPRNG.
+using RandomSource = std::function<void(uint8_t*, size_t)>;
+inline void os_random(uint8_t* out, size_t len) {
+    std::FILE* f = std::fopen("/dev/urandom", "rb");
+    const size_t got = f ? std::fread(out, 1, len, f) : 0;
+    if (f) std::fclose(f);
+    if (got != len) throw Error(PGPU_ERR_STATE, "cannot read /dev/urandom");
+}
+// uniform in [0, bound) by rejection, as crypto/rand.Int does (utils.go:26-33)
+inline Int random_below(const Int& bound, const RandomSource& rnd) {
+    if (bound.empty()) throw Error(PGPU_ERR_ARG, "random_below: bound must be positive");
+    unsigned top_bits = 0;
+    for (uint8_t t = bound[0]; t; t >>= 1) ++top_bits;
+    for (;;) {
+        Int r(bound.size());
+        rnd(r.data(), r.size());
+        r[0] &= (uint8_t)((1u << top_bits) - 1);
+        size_t z = 0;
+        while (z < r.size() && r[z] == 0) ++z;
+        r.erase(r.begin(), r.begin() + z);
+        if (detail::less(r, bound)) return r;
+    }
+}
 
 // Wire format of a Ciphertext: Go's encoding/gob stream of struct{C *gmp.Int; Level, EncMethod int} written by a fresh
 // encoder (paillier.go:374-401).  Restated from the encoding/gob specification and ncw/gmp's Int.GobEncode
@@ -322,6 +375,22 @@ public:
         }
         return wrap(detail::from_records(o, w), (EncryptionLevel)level, MixedEncryption);
     }
+    // PublicKey.Sub(cts...) (operations.go:32-55): cts[0] * prod_{i>0} cts[i]^-1 modulo n^(s+1) of cts[0].Level.  The inverses
+    // of the reference's loop are taken once, of the product of cts[1:] (the same canonical residue); a single argument comes
+    // back as it is (:34).  Error(PGPU_ERR_NOT_INVERTIBLE) where ModInverse has no result.
+    Ciphertext SubBatch(const std::vector<Ciphertext>& cts) {
+        if (cts.empty()) throw Error(PGPU_ERR_ARG, "Sub needs at least one ciphertext");
+        const int level = cts[0].Level;
+        if (cts.size() == 1) return Ciphertext{cts[0].C, level, MixedEncryption};
+        const size_t w = cipher_width(level);
+        auto first = detail::to_records({cts[0].C}, w);
+        auto rest = detail::to_records(values(std::vector<Ciphertext>(cts.begin() + 1, cts.end())), w);
+        std::vector<uint8_t> prod(w), inv(w), o(w);
+        check(pgpu_add_reduce_at_level(ctx_, level == EncLevelOne ? 1 : 2, cts.size() - 1, rest.data(), prod.data()));
+        check(pgpu_modinv(ctx_, level_modsel(level), 1, prod.data(), inv.data()));
+        check(pgpu_modmul(ctx_, level_modsel(level), 1, first.data(), inv.data(), o.data()));
+        return wrap(detail::from_records(o, w), level, MixedEncryption)[0];
+    }
 
     // N x PublicKey.Add(a_i, b_i) (operations.go:11-29): modulus and level of a_i, one level per batch
     std::vector<Ciphertext> AddPairs(const std::vector<Ciphertext>& a, const std::vector<Ciphertext>& b) {
@@ -378,13 +447,79 @@ public:
         check(pgpu_alt_encrypt_with_r_at_level(ctx_, level + 1, ms.size(), m.data(), r.data(), c.data()));
         return wrap(detail::from_records(c, cipher_width(level)), level, AlternativeEncryption);
     }
-    // N x PublicKey.Randomize (operations.go:67-69) with the r of the fresh Encrypt(0) supplied
+    // N x PublicKey.Randomize (operations.go:67-69) with the r of the fresh Encrypt(0) supplied.  Add takes the modulus from
+    // ct.Level while Encrypt(0) is always a level-1 ciphertext: a level-2 ct is multiplied by r^n mod n^2 modulo n^3.
     std::vector<Ciphertext> RandomizeWithRBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& rs) {
         if (cts.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per ciphertext");
+        const int level = batch_level(cts, "RandomizeWithRBatch");
+        if (level == EncLevelTwo) {
+            auto zero = detail::to_records(values(EncryptWithRBatch(std::vector<Int>(rs.size()), rs)), w_n3);
+            auto c = detail::to_records(values(cts), w_n3);
+            std::vector<uint8_t> o(cts.size() * w_n3);
+            if (!cts.empty()) check(pgpu_modmul(ctx_, PGPU_MOD_N3, cts.size(), c.data(), zero.data(), o.data()));
+            return wrap(detail::from_records(o, w_n3), EncLevelTwo, MixedEncryption);
+        }
         auto c = detail::to_records(values(cts), w_n2), r = detail::to_records(rs, w_n);
         std::vector<uint8_t> o(cts.size() * w_n2);
         check(pgpu_randomize_with_r(ctx_, cts.size(), c.data(), r.data(), o.data()));
         return wrap(detail::from_records(o, w_n2), EncLevelOne, MixedEncryption);
+    }
+
+    // ---- the callers that draw their own randomness -------------------------------------------------------------------
+    // count x GetRandomNumberInMultiplicativeGroup(n) (utils.go:36-49): uniform below n, redrawn on 0 or gcd(n, r) != 1.  The
+    // unit test of the whole batch is one batched ModInverse mod n on the GPU; only after a failure are the items checked
+    // one by one to find the ones to redraw.
+    std::vector<Int> DrawUnits(size_t count, const RandomSource& rnd = os_random) {
+        std::vector<Int> rs(count);
+        for (Int& r : rs) do r = random_below(N, rnd); while (r.empty());
+        size_t w = 0;
+        check(pgpu_ctx_mod_width(ctx_, PGPU_MOD_N, &w));
+        while (count) {
+            auto rec = detail::to_records(rs, w);
+            std::vector<uint8_t> inv(rec.size());
+            const int rc = pgpu_modinv(ctx_, PGPU_MOD_N, count, rec.data(), inv.data());
+            if (rc == PGPU_OK) break;
+            if (rc != PGPU_ERR_NOT_INVERTIBLE) check(rc);
+            for (size_t i = 0; i < count; ++i) {
+                const int one = pgpu_modinv(ctx_, PGPU_MOD_N, 1, rec.data() + i * w, inv.data());
+                if (one == PGPU_ERR_NOT_INVERTIBLE) do rs[i] = random_below(N, rnd); while (rs[i].empty());
+                else check(one);
+            }
+        }
+        return rs;
+    }
+    // N x PublicKey.EncryptAtLevel (paillier.go:258-269) / Encrypt (:192-194) / NestedEncrypt (:200-203)
+    std::vector<Ciphertext> EncryptAtLevelBatch(const std::vector<Int>& ms, int level, const RandomSource& rnd = os_random) {
+        return EncryptWithRAtLevelBatch(ms, DrawUnits(ms.size(), rnd), level);
+    }
+    std::vector<Ciphertext> EncryptBatch(const std::vector<Int>& ms, const RandomSource& rnd = os_random) { return EncryptAtLevelBatch(ms, EncLevelOne, rnd); }
+    std::vector<Ciphertext> NestedEncryptBatch(const std::vector<Int>& ms, const RandomSource& rnd = os_random) {
+        return EncryptAtLevelBatch(values(EncryptAtLevelBatch(ms, EncLevelOne, rnd)), EncLevelTwo, rnd);
+    }
+    // N x PublicKey.AltEncryptAtLevel (paillier.go:244-255): r from Z*_n as there, reduced mod K by AltEncryptWithRAtLevel
+    std::vector<Ciphertext> AltEncryptAtLevelBatch(const std::vector<Int>& ms, int level, const RandomSource& rnd = os_random) {
+        auto rs = DrawUnits(ms.size(), rnd);
+        return AltEncryptWithRAtLevelBatch(ms, rs, level);
+    }
+    // count x EncryptZero / EncryptOne (AtLevel) (paillier.go:272-289)
+    std::vector<Ciphertext> EncryptZeroAtLevelBatch(size_t count, int level, const RandomSource& rnd = os_random) {
+        return EncryptAtLevelBatch(std::vector<Int>(count), level, rnd);
+    }
+    std::vector<Ciphertext> EncryptOneAtLevelBatch(size_t count, int level, const RandomSource& rnd = os_random) {
+        return EncryptAtLevelBatch(std::vector<Int>(count, Int{1}), level, rnd);
+    }
+    std::vector<Ciphertext> EncryptZeroBatch(size_t count, const RandomSource& rnd = os_random) { return EncryptZeroAtLevelBatch(count, EncLevelOne, rnd); }
+    std::vector<Ciphertext> EncryptOneBatch(size_t count, const RandomSource& rnd = os_random) { return EncryptOneAtLevelBatch(count, EncLevelOne, rnd); }
+    // N x PublicKey.Randomize (operations.go:67-69) with the r of each fresh Encrypt(0) drawn here
+    std::vector<Ciphertext> RandomizeBatch(const std::vector<Ciphertext>& cts, const RandomSource& rnd = os_random) {
+        return RandomizeWithRBatch(cts, DrawUnits(cts.size(), rnd));
+    }
+    // N x PublicKey.NestedRandomize (operations.go:96-118): a, b drawn from Z*_n (:105-106) and returned like there
+    std::vector<Ciphertext> NestedRandomizeBatch(const std::vector<Ciphertext>& cts, std::vector<Int>& as, std::vector<Int>& bs,
+                                                 const RandomSource& rnd = os_random) {
+        as = DrawUnits(cts.size(), rnd);
+        bs = DrawUnits(cts.size(), rnd);
+        return NestedRandomizeWithBatch(cts, as, bs);
     }
     // N x PublicKey.NestedRandomize (operations.go:96-118) with (a, b) supplied
     std::vector<Ciphertext> NestedRandomizeWithBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& as, const std::vector<Int>& bs) {
@@ -583,25 +718,72 @@ inline std::vector<bool> MillerRabinBatch(unsigned bits, const std::vector<Int>&
 class ThresholdPublicKey : public PublicKey {
 public:
     int TotalNumberOfDecryptionServers, Threshold;
+    Int VerificationKey;
+    std::vector<Int> VerificationKeys;
     ThresholdPublicKey(const Int& n, int l, int w, const Int& v, const std::vector<Int>& vi, int device = 0, int id = 0, const Int* share = nullptr)
-        : PublicKey(n, device), TotalNumberOfDecryptionServers(l), Threshold(w) {
+        : PublicKey(n, device), TotalNumberOfDecryptionServers(l), Threshold(w), VerificationKey(v), VerificationKeys(vi) {
         auto vk = detail::to_records(vi, w_n2);
         check(pgpu_ctx_set_threshold(ctx_, l, w, id, share ? share->data() : nullptr, share ? share->size() : 0, v.data(), v.size(),
                                      vi.empty() ? nullptr : vk.data()));
         check(pgpu_ctx_z_width(ctx_, &w_z));
     }
-    // N x PartialDecryptionZKP.VerifyProof (thresholdkey.go:278-291); one server per batch
+    // N x PartialDecryptionZKP.VerifyProof (thresholdkey.go:278-291); one server per batch.  A value wider than its record
+    // (E is a SHA-256 digest, Z < 2^(8 w_z) for every r < n^2, c and c_i residues mod n^2) cannot come from an honest
+    // prover: such a proof is answered false, as the reference's VerifyProof would, instead of failing the batch.
     std::vector<bool> VerifyProofBatch(const std::vector<PartialDecryptionZKP>& proofs) {
         if (proofs.empty()) return {};
         std::vector<Int> c, d, e, z;
+        std::vector<bool> fits;
         for (const auto& p : proofs) {
             if (p.ID != proofs[0].ID) throw Error(PGPU_ERR_ARG, "VerifyProofBatch: one server id per batch");
-            c.push_back(p.C); d.push_back(p.Decryption); e.push_back(p.E); z.push_back(p.Z);
+            const bool f = p.C.size() <= w_n2 && p.Decryption.size() <= w_n2 && p.E.size() <= 32 && p.Z.size() <= w_z;
+            fits.push_back(f);
+            c.push_back(f ? p.C : Int{}); d.push_back(f ? p.Decryption : Int{}); e.push_back(f ? p.E : Int{}); z.push_back(f ? p.Z : Int{});
         }
         auto rc = detail::to_records(c, w_n2), rd = detail::to_records(d, w_n2), re = detail::to_records(e, 32), rz = detail::to_records(z, w_z);
         std::vector<uint8_t> ok(proofs.size());
         check(pgpu_pdec_zkp_verify(ctx_, proofs.size(), proofs[0].ID, rc.data(), rd.data(), re.data(), rz.data(), ok.data()));
-        return std::vector<bool>(ok.begin(), ok.end());
+        std::vector<bool> out(proofs.size());
+        for (size_t i = 0; i < out.size(); ++i) out[i] = ok[i] != 0 && fits[i];
+        return out;
+    }
+    // N x CombinePartialDecryptionsZKP (thresholdkey.go:164-172): shares[j] = server j's batch, same ciphertext order.  As in
+    // the reference the proofs filter PER CIPHERTEXT: ciphertext i is combined from the servers whose proof for i verifies.
+    // Where fewer than Threshold remain the reference answers "Threshold not meet" for that ciphertext: with item_ok == nullptr
+    // the call throws Error(PGPU_ERR_THRESHOLD) if that happens to any of them; otherwise (*item_ok)[i] tells which plaintexts
+    // are valid (the others are empty).
+    std::vector<Int> CombinePartialDecryptionsZKPBatch(const std::vector<std::vector<PartialDecryptionZKP>>& shares,
+                                                       std::vector<bool>* item_ok = nullptr) {
+        if (shares.empty()) throw Error(PGPU_ERR_THRESHOLD, "Threshold not meet");
+        const size_t count = shares[0].size();
+        std::vector<int> ids;
+        std::vector<Int> flat;
+        std::vector<uint8_t> ok;
+        for (const auto& s : shares) {
+            if (s.size() != count) throw Error(PGPU_ERR_ARG, "CombinePartialDecryptionsZKPBatch: one proof per ciphertext and server");
+            ids.push_back(count ? s[0].ID : 0);
+            for (bool v : VerifyProofBatch(s)) ok.push_back(v ? 1 : 0);
+            for (const auto& p : s) flat.push_back(p.Decryption.size() <= w_n2 ? p.Decryption : Int{});
+        }
+        auto d = detail::to_records(flat, w_n2);
+        std::vector<uint8_t> m(count * w_n, 0), flags(count, 0);
+        const int rc = pgpu_combine_verified(ctx_, count, (int)ids.size(), ids.data(), d.empty() ? nullptr : d.data(), ok.empty() ? nullptr : ok.data(),
+                                             m.empty() ? nullptr : m.data(), flags.empty() ? nullptr : flags.data());
+        if (rc != PGPU_OK && !(rc == PGPU_ERR_THRESHOLD && item_ok)) check(rc);
+        if (item_ok) item_ok->assign(flags.begin(), flags.end());
+        return detail::from_records(m, w_n);
+    }
+    // N x ThresholdPublicKey.VerifyDecryption (thresholdkey.go:175-189): throws Error(PGPU_ERR_ARG) with the reference's
+    // error strings, or the combine's error when too few valid shares remain
+    void VerifyDecryptionBatch(const std::vector<Int>& encryptedMessages, const std::vector<Int>& decryptedMessages,
+                               const std::vector<std::vector<PartialDecryptionZKP>>& shares) {
+        for (const auto& s : shares) {
+            if (s.size() != encryptedMessages.size()) throw Error(PGPU_ERR_ARG, "The encrypted message is not the same than the one in the shares");
+            for (size_t i = 0; i < s.size(); ++i)
+                if (s[i].C != encryptedMessages[i]) throw Error(PGPU_ERR_ARG, "The encrypted message is not the same than the one in the shares");
+        }
+        if (CombinePartialDecryptionsZKPBatch(shares) != decryptedMessages)
+            throw Error(PGPU_ERR_ARG, "The decrypted message is not the same than the one in the shares");
     }
     // N x CombinePartialDecryptions (thresholdkey.go:149-161): shares[j] = server j's batch, same ciphertext order.
     // Throws Error(PGPU_ERR_THRESHOLD, "Threshold not meet" / duplicate server) like the reference's errors (:77-89).
@@ -626,7 +808,21 @@ class ThresholdSecretKey : public ThresholdPublicKey {
 public:
     int ID;
     ThresholdSecretKey(const Int& n, int l, int w, const Int& v, const std::vector<Int>& vi, int id, const Int& share, int device = 0)
-        : ThresholdPublicKey(n, l, w, v, vi, device, id, &share), ID(id) {}
+        : ThresholdPublicKey(n, l, w, v, vi, device, id, &share), ID(id), device_(device) {}
+    // ThresholdSecretKey.PublicKey (thresholdkey.go:213-222): the key without ID and Share, on a context of its own
+    std::unique_ptr<ThresholdPublicKey> GetPublicKey() const {
+        return std::make_unique<ThresholdPublicKey>(N, TotalNumberOfDecryptionServers, Threshold, VerificationKey, VerificationKeys, device_);
+    }
+    // ThresholdSecretKey.VerifyPartialDecryption (thresholdkey.go:258-275): encrypt a random m < n, prove its partial
+    // decryption (r < n^2, :233), verify the proof; `count` such checks run as one batch.  Throws Error(PGPU_ERR_ARG, "Invalid share").
+    void VerifyPartialDecryption(size_t count = 1, const RandomSource& rnd = os_random) {
+        const Int n2 = detail::mul(N, N);
+        std::vector<Int> ms, rs, cs;
+        for (size_t i = 0; i < count; ++i) { ms.push_back(random_below(N, rnd)); rs.push_back(random_below(n2, rnd)); }
+        for (auto& c : EncryptBatch(ms, rnd)) cs.push_back(std::move(c.C));
+        for (bool ok : VerifyProofBatch(PartialDecryptionWithZKPBatch(cs, rs)))
+            if (!ok) throw Error(PGPU_ERR_ARG, "Invalid share");
+    }
     // N x ThresholdSecretKey.PartialDecrypt (thresholdkey.go:192-201)
     std::vector<PartialDecryption> PartialDecryptBatch(const std::vector<Int>& cs) {
         auto c = detail::to_records(cs, w_n2);
@@ -646,6 +842,9 @@ public:
         for (size_t i = 0; i < cs.size(); ++i) out.push_back(PartialDecryptionZKP{ID, D[i], E[i], Z[i], cs[i]});
         return out;
     }
+
+private:
+    int device_ = 0;
 };
 
 }  // namespace paillier

@@ -266,14 +266,14 @@ class PublicKey:
         out = self.encrypt_with_rn_records(to_records(ms, self.w_n), to_records(rns, self.w_n2))
         return [Ciphertext(c, ENC_LEVEL_ONE, REGULAR) for c in from_records(out, self.w_n2)]
 
-    def EncryptBatch(self, ms: Sequence[int], rand=None) -> List[Ciphertext]:
-        """N x PublicKey.Encrypt (paillier.go:192, :258-269): draws r as GetRandomNumberInMultiplicativeGroup does
-        (utils.go:36-49: uniform below n, retry on 0 or gcd(n, r) != 1) -- the draws come from the host CSPRNG (`secrets`,
-        or `rand.randrange` if given), the unit test of the whole batch is one batched ModInverse mod n on the GPU."""
+    def _draw_units(self, count: int, rand=None) -> List[int]:
+        """count x GetRandomNumberInMultiplicativeGroup(n) (utils.go:36-49: uniform below n, redrawn on 0 or gcd(n, r) != 1).
+        The draws come from the host CSPRNG (`secrets`, or `rand.randrange` if given); the unit test of the whole batch is
+        one batched ModInverse mod n on the GPU, the host's gcd only names the culprits after a failure."""
         import secrets
         draw = (lambda: rand.randrange(self.N)) if rand is not None else (lambda: secrets.randbelow(self.N))
-        rs = [draw() for _ in ms]
-        while True:
+        rs = [draw() for _ in range(count)]
+        while count:
             bad = [i for i, r in enumerate(rs) if r == 0]
             if not bad:
                 try:
@@ -286,7 +286,41 @@ class PublicKey:
                     bad = [i for i, r in enumerate(rs) if gcd(r, self.N) != 1]
             for i in bad:
                 rs[i] = draw()
-        return self.EncryptWithRBatch(ms, rs)
+        return rs
+
+    def EncryptAtLevelBatch(self, ms: Sequence[int], level: int, rand=None) -> List[Ciphertext]:
+        """N x PublicKey.EncryptAtLevel (paillier.go:258-269): r drawn per item, then EncryptWithRAtLevel"""
+        return self.EncryptWithRAtLevelBatch(ms, self._draw_units(len(ms), rand), level)
+
+    def EncryptBatch(self, ms: Sequence[int], rand=None) -> List[Ciphertext]:
+        """N x PublicKey.Encrypt (paillier.go:192-194) = EncryptAtLevel(m, DefaultEncryptionLevel)"""
+        return self.EncryptAtLevelBatch(ms, ENC_LEVEL_ONE, rand)
+
+    def NestedEncryptBatch(self, ms: Sequence[int], rand=None) -> List[Ciphertext]:
+        """N x PublicKey.NestedEncrypt (paillier.go:200-203): a level-2 encryption of the level-1 ciphertext"""
+        inner = self.EncryptAtLevelBatch(ms, ENC_LEVEL_ONE, rand)
+        return self.EncryptAtLevelBatch([c.C for c in inner], ENC_LEVEL_TWO, rand)
+
+    def AltEncryptAtLevelBatch(self, ms: Sequence[int], level: int, rand=None) -> List[Ciphertext]:
+        """N x PublicKey.AltEncryptAtLevel (paillier.go:244-255): r drawn from Z*_n as there, reduced mod K by
+        AltEncryptWithRAtLevel"""
+        return self.AltEncryptWithRAtLevelBatch(ms, self._draw_units(len(ms), rand), level)
+
+    def EncryptZeroAtLevelBatch(self, count: int, level: int, rand=None) -> List[Ciphertext]:
+        """count x PublicKey.EncryptZeroAtLevel (paillier.go:282-284)"""
+        return self.EncryptAtLevelBatch([0] * count, level, rand)
+
+    def EncryptOneAtLevelBatch(self, count: int, level: int, rand=None) -> List[Ciphertext]:
+        """count x PublicKey.EncryptOneAtLevel (paillier.go:287-289)"""
+        return self.EncryptAtLevelBatch([1] * count, level, rand)
+
+    def EncryptZeroBatch(self, count: int, rand=None) -> List[Ciphertext]:
+        """count x PublicKey.EncryptZero (paillier.go:272-274)"""
+        return self.EncryptZeroAtLevelBatch(count, ENC_LEVEL_ONE, rand)
+
+    def EncryptOneBatch(self, count: int, rand=None) -> List[Ciphertext]:
+        """count x PublicKey.EncryptOne (paillier.go:277-279)"""
+        return self.EncryptOneAtLevelBatch(count, ENC_LEVEL_ONE, rand)
 
     # operations.go:11-64 take the modulus from the level of the (first) ciphertext: n^2 at level 1, n^3 at level 2
     def _level_modulus(self, level: int):
@@ -402,11 +436,49 @@ class PublicKey:
         return [Ciphertext(c, level, ALTERNATIVE) for c in from_records(out, wc)]
 
     def RandomizeWithRBatch(self, cts: Sequence[Ciphertext], rs: Sequence[int]) -> List[Ciphertext]:
-        """N x PublicKey.Randomize (operations.go:67-69) = Add(ct, EncryptWithR(0, r)) with r supplied"""
+        """N x PublicKey.Randomize (operations.go:67-69) = Add(ct, EncryptWithR(0, r)) with r supplied.  Add takes the modulus
+        from ct.Level (operations.go:13-15) while the fresh Encrypt(0) is always a level-1 ciphertext: a level-2 ct is
+        multiplied by r^n mod n^2 modulo n^3, as the reference does."""
+        if len(cts) != len(rs):
+            raise ValueError("one r per ciphertext")
+        level = self._one_level(cts, "RandomizeWithRBatch")
+        if level == ENC_LEVEL_TWO:
+            zeros = self.EncryptWithRBatch([0] * len(cts), rs)
+            modsel, width, mod = self._level_modulus(level)
+            vals = self.MulModBatch([c.C % mod for c in cts], [z.C for z in zeros], modsel)
+            return [Ciphertext(v, level, MIXED) for v in vals]
         cr, rr = to_records([c.C for c in cts], self.w_n2), to_records(rs, self.w_n)
         out = np.empty(len(cts) * self.w_n2, dtype=np.uint8)
         check(lib.pgpu_randomize_with_r(self._ctx, len(cts), _ptr(cr), _ptr(rr), _ptr(out)), self._ctx)
         return [Ciphertext(c, ENC_LEVEL_ONE, MIXED) for c in from_records(out, self.w_n2)]
+
+    def RandomizeBatch(self, cts: Sequence[Ciphertext], rand=None) -> List[Ciphertext]:
+        """N x PublicKey.Randomize (operations.go:67-69) with the r of each fresh Encrypt(0) drawn here"""
+        return self.RandomizeWithRBatch(cts, self._draw_units(len(cts), rand))
+
+    def NestedRandomizeBatch(self, cts: Sequence[Ciphertext], rand=None):
+        """N x PublicKey.NestedRandomize (operations.go:96-118) -> (randomized ciphertexts, a values, b values) with a, b drawn
+        from Z*_n as there (:105-106)"""
+        As, Bs = self._draw_units(len(cts), rand), self._draw_units(len(cts), rand)
+        return self.NestedRandomizeWithBatch(cts, As, Bs), As, Bs
+
+    def SubBatch(self, cts: Sequence[Ciphertext]) -> Ciphertext:
+        """PublicKey.Sub(cts...) (operations.go:32-55): cts[0] * prod_{i>0} cts[i]^-1 modulo n^(s+1) of cts[0].Level.  The
+        inverses of the reference's loop are taken once, of the product of cts[1:] (the same canonical residue); like there,
+        a single argument comes back unreduced.  Raises PgpuError(PGPU_ERR_NOT_INVERTIBLE) where ModInverse has no result."""
+        if not cts:
+            raise ValueError("Sub needs at least one ciphertext")                  # the reference indexes cts[0]
+        level = cts[0].Level
+        if len(cts) == 1:
+            return Ciphertext(cts[0].C, level, MIXED)
+        modsel, width, mod = self._level_modulus(level)
+        rest = to_records([c.C % mod for c in cts[1:]], width)
+        prod = np.empty(width, dtype=np.uint8)
+        check(lib.pgpu_add_reduce_at_level(self._ctx, level + 1, len(cts) - 1, _ptr(rest), _ptr(prod)), self._ctx)
+        inv = np.empty(width, dtype=np.uint8)
+        check(lib.pgpu_modinv(self._ctx, modsel, 1, _ptr(prod), _ptr(inv)), self._ctx)
+        out = self.modmul_records(modsel, to_records([cts[0].C % mod], width), inv, width)
+        return Ciphertext(from_records(out, width)[0], level, MIXED)
 
     def NestedRandomizeWithBatch(self, cts: Sequence[Ciphertext], As: Sequence[int], Bs: Sequence[int]) -> List[Ciphertext]:
         """N x PublicKey.NestedRandomize (operations.go:96-118) with the randomness (a, b) supplied"""
@@ -715,6 +787,21 @@ class ThresholdSecretKey(ThresholdPublicKey):
                          device, _id=ID, _share=Share)
         self.ID = ID
         self.Share = Share
+
+    def PublicKey(self) -> ThresholdPublicKey:
+        """ThresholdSecretKey.PublicKey (thresholdkey.go:213-222): the key without ID and Share, on a context of its own"""
+        return ThresholdPublicKey(self.N, self.TotalNumberOfDecryptionServers, self.Threshold, self.VerificationKey,
+                                  self.VerificationKeys, device=self.device)
+
+    def VerifyPartialDecryption(self, count: int = 1, rand=None) -> None:
+        """ThresholdSecretKey.VerifyPartialDecryption (thresholdkey.go:258-275): encrypt a random m < n, prove its partial
+        decryption, verify the proof; `count` such checks run as one batch.  Raises ValueError("Invalid share")."""
+        import secrets
+        below = (lambda b: rand.randrange(b)) if rand is not None else secrets.randbelow
+        cts = self.EncryptBatch([below(self.N) for _ in range(count)], rand)
+        proofs = self.PartialDecryptionWithZKPBatch([c.C for c in cts], [below(self.N ** 2) for _ in range(count)])
+        if not all(self.VerifyProofBatch(proofs)):
+            raise ValueError("Invalid share")
 
     def partial_decrypt_records(self, c) -> np.ndarray:
         c = np.ascontiguousarray(c).view(np.uint8).reshape(-1)

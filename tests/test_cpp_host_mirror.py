@@ -97,3 +97,38 @@ def test_cpp_gob_wire_format_matches_python_mirror():
     assert out[k:2 * k] == [f"{hex(c)} {l} {m}" for c, l, m in cases]
     assert out[2 * k] == "error no data provided"
     assert out[2 * k + 1].startswith("error ") and out[2 * k + 2].startswith("error ")
+
+
+CALLERS_EXE = os.path.join(ROOT, "tests", "cpp", "callers_test")
+
+
+def build_callers_test():
+    libdir = os.path.join(ROOT, "paillier_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "callers_test.cpp"),
+                    "-o", CALLERS_EXE, "-L", libdir, "-lpaillier_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    return CALLERS_EXE
+
+
+def test_cpp_host_helpers_of_the_drawing_callers():
+    """The host-only helpers behind the C++ mirror's randomness-drawing callers (no GPU): the byte-string product that gives
+    n^2 (range of a proof's r, thresholdkey.go:233) against Python ints, and random_below (crypto/rand.Int's rejection
+    sampling, utils.go:26-33) staying below its bound and covering it."""
+    import random
+    exe = build_callers_test()
+    rnd = random.Random(12)
+    pairs = [(0, 5), (1, 1), (255, 255), (2 ** 64 - 1, 2 ** 64 - 1), (2 ** 2048 - 1, 2 ** 2048 - 1), (2 ** 6144 - 1, 2 ** 6144 - 1)]
+    pairs += [(rnd.getrandbits(a), rnd.getrandbits(b)) for a, b in ((8, 4096), (1024, 1024), (2048, 2048), (3072, 3072), (4096, 17))]
+    bounds = [1, 2, 3, 255, 256, 257, 2 ** 64, rnd.getrandbits(2048) | 1 << 2047, 5 << 1000]
+    lines = [f"mul {a:x} {b:x}" for a, b in pairs] + [f"below {b:x}" for b in bounds]
+    r = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.split("\n")
+    assert [int(x, 16) for x in out[:len(pairs)]] == [a * b for a, b in pairs]
+    for b, line in zip(bounds, out[len(pairs):]):
+        draws = [int(x, 16) for x in line.split()]
+        assert len(draws) == 64 and all(0 <= d < b for d in draws)
+        if b >= 256:
+            assert len(set(draws)) > 32 and max(draws) >= b // 4          # spread over the range, top bits used
+        elif b > 1:
+            assert len(set(draws)) > 1
+    assert out[len(pairs) + len(bounds)] == "callers ok"
