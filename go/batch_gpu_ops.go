@@ -333,11 +333,21 @@ func (g *GPUContext) VerifyProofBatch(proofs []*PartialDecryptionZKP) ([]bool, e
 	}
 	id := proofs[0].ID
 	cs, ds, es, zs := make([]*gmp.Int, len(proofs)), make([]*gmp.Int, len(proofs)), make([]*gmp.Int, len(proofs)), make([]*gmp.Int, len(proofs))
+	fits := make([]bool, len(proofs))
+	zero := gmp.NewInt(0)
 	for i, p := range proofs {
 		if p.ID != id {
 			return nil, errors.New("one server id per batch")
 		}
-		cs[i], ds[i], es[i], zs[i] = p.C, p.Decryption, p.E, p.Z
+		// a value wider than its record cannot come from an honest prover (E is a SHA-256 digest, Z < 2^(8 wZ) for every
+		// r < n^2): the scalar VerifyProof answers false for it, so does the batch instead of failing as a whole
+		fits[i] = p.C.Sign() >= 0 && p.Decryption.Sign() >= 0 && p.E.Sign() >= 0 && p.Z.Sign() >= 0 &&
+			len(p.C.Bytes()) <= g.wN2 && len(p.Decryption.Bytes()) <= g.wN2 && len(p.E.Bytes()) <= 32 && len(p.Z.Bytes()) <= g.wZ
+		if fits[i] {
+			cs[i], ds[i], es[i], zs[i] = p.C, p.Decryption, p.E, p.Z
+		} else {
+			cs[i], ds[i], es[i], zs[i] = zero, zero, zero, zero
+		}
 	}
 	c, d, e, z := toRecords(cs, g.wN2), toRecords(ds, g.wN2), toRecords(es, 32), toRecords(zs, g.wZ)
 	ok := make([]byte, len(proofs))
@@ -347,7 +357,7 @@ func (g *GPUContext) VerifyProofBatch(proofs []*PartialDecryptionZKP) ([]bool, e
 	}
 	out := make([]bool, len(proofs))
 	for i, v := range ok {
-		out[i] = v == 1
+		out[i] = v == 1 && fits[i]
 	}
 	return out, nil
 }
