@@ -354,8 +354,45 @@ def config1_leg(local):
     return out
 
 
+def small_batch_leg(sk, m_np, r_np, n, lam, w_n, w_n2):
+    """Latency of ONE blocking host-buffer call at small batch sizes -- what a caller of the reference's scalar API sees when
+    it switches to the batch call with few items (paillier.go:185-187,292-303 are one item per call) -- beside one libgmp
+    thread doing the same items one after the other.  Pageable host memory (numpy), best of 5 calls after a warm-up call."""
+    import numpy as np
+    from oracle import gmp_ref as G
+    from paillier_b200._lib import check, lib
+    from paillier_b200.api import PublicKey
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rows = {}
+    for cnt in (1, 16, 256, 4096):
+        m = m_np[:cnt * w_n].copy(); r = r_np[:cnt * w_n].copy()            # copies: pageable memory, like a Go slice
+        c = np.empty(cnt * w_n2, dtype=np.uint8); d = np.empty(cnt * w_n, dtype=np.uint8)
+        be = bd = 1e9
+        for rep in range(6):
+            t0 = time.perf_counter(); check(lib.pgpu_encrypt_with_r(sk._ctx, cnt, ptr(m), ptr(r), ptr(c)), sk._ctx)
+            t1 = time.perf_counter(); check(lib.pgpu_decrypt(sk._ctx, cnt, ptr(c), ptr(d)), sk._ctx)
+            t2 = time.perf_counter()
+            if rep:
+                be, bd = min(be, t1 - t0), min(bd, t2 - t1)
+        assert np.array_equal(d, m), "small batch: Decrypt(Encrypt(m)) != m"
+        row = {"encrypt_ms_per_call": be * 1e3, "decrypt_ms_per_call": bd * 1e3, "encrypt_items_per_s": cnt / be, "decrypt_items_per_s": cnt / bd}
+        if cnt <= 256:
+            k = min(cnt, 16)
+            t0 = time.perf_counter(); cref = G.encrypt_with_r(n, m[:k * w_n], r[:k * w_n], w_n, threads=1)
+            t1 = time.perf_counter(); G.decrypt(n, lam, cref, w_n, threads=1)
+            t2 = time.perf_counter()
+            assert np.array_equal(cref, c[:k * w_n2]), "small batch: GPU ciphertexts differ from the libgmp oracle"
+            row["libgmp_1_thread_encrypt_ms_per_item"] = (t1 - t0) / k * 1e3
+            row["libgmp_1_thread_decrypt_ms_per_item"] = (t2 - t1) / k * 1e3
+        rows[str(cnt)] = row
+    return {"workload": "one blocking pgpu_encrypt_with_r / pgpu_decrypt call per batch, 2048-bit n, pageable host buffers", "batch": rows,
+            "note": "a single item occupies one lane group of one SM for a whole exponentiation: the GPU call pays that latency once per "
+                    "batch, libgmp pays its per-item time for every item"}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
+    ap.add_argument("--only-small-batch", action="store_true", help="run the small-batch latency leg alone and print it")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -410,6 +447,12 @@ def main() -> None:
     torch.cuda.set_stream(stream)
     check(lib.pgpu_ctx_set_stream(sk._ctx, C.c_void_p(stream.cuda_stream)), sk._ctx)
     count, w_n, w_n2 = args.count, sk.w_n, sk.w_n2
+    if args.only_small_batch:
+        k = 4096
+        print(json.dumps(small_batch_leg(sk, synth.plaintexts(k, n, w_n, synth.SEED), synth.randomness(k, n, w_n, synth.SEED), n, (p - 1) * (q - 1),
+                                         w_n, w_n2)), flush=True)
+        sk.close()
+        return
 
     # seeded synthetic inputs (different stream of the same generator per rank), pinned on the host
     seed = synth.SEED + rank
@@ -966,6 +1009,10 @@ def main() -> None:
             c_np = c_dev[:nd * w_n2].cpu().numpy()
             cpu_rows, ref_dot = cpu_baselines_leg(sk, n, p, q, w_n, w_n2, c_np, extras_keep, breakdown)
             config1 = config1_leg(local)
+            try:
+                breakdown["small_batch"] = small_batch_leg(sk, m_host.numpy(), r_host.numpy(), n, lam, w_n, w_n2)
+            except Exception as e:      # a report row, never a reason to lose the bench line
+                breakdown["small_batch"] = {"error": repr(e)}
             # the dot-product sample, recomputed on the GPU over the same terms, must equal the libgmp fold
             kd = torch.from_numpy(synth.scalars_u64(nd).view(np.int64).copy()).to(dev)
             dd = torch.empty(w_n2, dtype=torch.uint8, device=dev)

@@ -6,8 +6,8 @@
 //     lo = fma_rz(a, b, 2^104 + 2^52 - hi) -> 2^52 + (a*b mod 2^52)                 (exact: in [2^52, 2^53))
 // and the two results are accumulated as 64-bit INTEGERS on their bit patterns (IADD3 on the ALU pipe): the exponent
 // fields are constants, the mantissa fields add up like integers.  2704 bit^2 per 3 FP64-pipe slots against 1024 bit^2
-// per IMAD.WIDE slot: 1.64x the multiplier throughput of mont.cuh (measured 5.73 T limb products/s = 15.5 Pbit^2/s
-// against 9.47 Pbit^2/s, profiles/r02_dfma_peak.json).
+// per IMAD.WIDE slot on paper; measured, the carry adds do not hide behind the FP64 pipe and the two routes tie at
+// 9.1 vs 9.47 Pbit^2/s (profiles/r02_dfma_peak.json, r02_fp64_experiments.md): this kernel wins 3-17 % by shape, not 1.6x.
 //
 // Layout: a residue of S52 = TPI*L limbs of 52 bits, lane t of the group keeps limbs [t*L, t*L+L) as doubles (exact
 // integers < 2^52).  R = 2^(52*S52) > 4n, so values are kept lazily in [0, 2n) and no multiplication ends with a
