@@ -89,7 +89,8 @@ func (g *GPUContext) EncryptOneBatch(pk *PublicKey, count int) ([]*Ciphertext, e
 }
 
 // RandomizeBatch = N x PublicKey.Randomize (operations.go:67-69) with the r of each fresh Encrypt(0) drawn here.  Add takes
-// the modulus from ct.Level while Encrypt(0) is a level-1 ciphertext: a level-2 ct is multiplied by r^n mod n^2 modulo n^3.
+// the modulus from ct.Level while Encrypt(0) is a level-1 ciphertext: a level-2 ct is multiplied by r^n mod n^2 modulo n^3
+// (bit-exact with the scalar method; that product is not an encryption of the same plaintext -- use NestedRandomizeBatch).
 func (g *GPUContext) RandomizeBatch(pk *PublicKey, cts []*Ciphertext) ([]*Ciphertext, error) {
 	rs, err := drawUnits(pk.N, len(cts))
 	if err != nil {

@@ -448,7 +448,8 @@ public:
         return wrap(detail::from_records(c, cipher_width(level)), level, AlternativeEncryption);
     }
     // N x PublicKey.Randomize (operations.go:67-69) with the r of the fresh Encrypt(0) supplied.  Add takes the modulus from
-    // ct.Level while Encrypt(0) is always a level-1 ciphertext: a level-2 ct is multiplied by r^n mod n^2 modulo n^3.
+    // ct.Level while Encrypt(0) is always a level-1 ciphertext: a level-2 ct is multiplied by r^n mod n^2 modulo n^3 (bit-exact
+    // with the reference; that product is not an encryption of the same plaintext -- NestedRandomize is the level-2 form).
     std::vector<Ciphertext> RandomizeWithRBatch(const std::vector<Ciphertext>& cts, const std::vector<Int>& rs) {
         if (cts.size() != rs.size()) throw Error(PGPU_ERR_ARG, "one r per ciphertext");
         const int level = batch_level(cts, "RandomizeWithRBatch");

@@ -438,7 +438,8 @@ class PublicKey:
     def RandomizeWithRBatch(self, cts: Sequence[Ciphertext], rs: Sequence[int]) -> List[Ciphertext]:
         """N x PublicKey.Randomize (operations.go:67-69) = Add(ct, EncryptWithR(0, r)) with r supplied.  Add takes the modulus
         from ct.Level (operations.go:13-15) while the fresh Encrypt(0) is always a level-1 ciphertext: a level-2 ct is
-        multiplied by r^n mod n^2 modulo n^3, as the reference does."""
+        multiplied by r^n mod n^2 modulo n^3, as the reference does (bit-exact with it; that product is not an encryption of
+        the same plaintext -- the reference's Randomize is only meaningful at level 1, NestedRandomize is the level-2 form)."""
         if len(cts) != len(rs):
             raise ValueError("one r per ciphertext")
         level = self._one_level(cts, "RandomizeWithRBatch")

@@ -71,9 +71,14 @@ int main() {
                 auto nr = sk.NestedRandomizeBatch(nested, as, bs, rnd);
                 expect(as.size() == ms.size() && bs.size() == ms.size() && sk.NestedDecryptBatch(nr) == ms, "NestedRandomizeBatch keeps the plaintext");
                 expect(values(sk.NestedRandomizeWithBatch(nested, as, bs)) == values(nr), "NestedRandomizeBatch returns its (a, b)");
+                // at level 2 the reference's Randomize multiplies by a LEVEL-1 Encrypt(0) modulo n^3 (Add takes the modulus of
+                // ct.Level): bit-exact with that product, whatever it decrypts to
                 auto l2 = sk.EncryptAtLevelBatch(m2, EncLevelTwo, rnd);
-                auto l2r = sk.RandomizeBatch(l2, rnd);
-                expect(l2r[0].Level == EncLevelTwo && values(l2r) != values(l2) && sk.DecryptBatch(l2r) == m2, "RandomizeBatch at level 2");
+                auto rs2 = sk.DrawUnits(l2.size(), rnd);
+                auto l2r = sk.RandomizeWithRBatch(l2, rs2);
+                auto want = sk.AddPairs(l2, static_cast<PublicKey&>(sk).EncryptWithRBatch(std::vector<Int>(rs2.size()), rs2));
+                expect(l2r[0].Level == EncLevelTwo && values(l2r) != values(l2) && values(l2r) == values(want), "RandomizeWithRBatch at level 2");
+                expect(sk.RandomizeBatch(l2, rnd).size() == l2.size(), "RandomizeBatch at level 2");
             }
             const Int zero, one{1};
             expect(sk.DecryptBatch(sk.EncryptZeroBatch(3)) == std::vector<Int>(3, zero), "EncryptZeroBatch");
