@@ -17,8 +17,10 @@ semantics are mirrored where they differ from the obvious:
 Parity pinning: checked against every known-answer test the reference holds
 (tests/test_oracle_kats.py lists them with file:line).  The reference has no
 golden vectors at 1024-bit and above and cannot be built here (no Go toolchain,
-ncw/gmp absent), so large-size parity is pinned by cross-checking this module
-against libgmp (oracle/gmp_ref.c) on the same inputs -- see DESIGN.md.
+ncw/gmp absent): PARITY UNPINNED at >= 1024 bits against the reference itself.
+There it rests on three unrelated bignum implementations agreeing on the same
+inputs -- this module (CPython ints), libgmp (oracle/gmp_ref.c) and OpenSSL BN
+(oracle/ossl_ref.c) -- see DESIGN.md section 2.
 """
 from __future__ import annotations
 
