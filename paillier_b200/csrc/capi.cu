@@ -129,11 +129,13 @@ int pgpu_ctx_destroy(pgpu_ctx* ctx) {
     modctx_free(ctx->m_n); modctx_free(ctx->m_n2); modctx_free(ctx->m_n3); modctx_free(ctx->m_p2); modctx_free(ctx->m_q2);
     program_free(ctx->prog_enc); program_free(ctx->prog_dec_p); program_free(ctx->prog_dec_q); program_free(ctx->prog_pdec);
     program_free(ctx->prog_encq); program_free(ctx->prog_encp); program_free(ctx->prog_encf);
-    for (auto& kv : ctx->prog_cache) if (kv.second.d_ops) cudaFree(kv.second.d_ops);
+    for (auto& kv : ctx->prog_cache) { dev_scrub_free(kv.second.d_ops, kv.second.d_bytes); scrub(kv.second.ops); }
     protocols_free(ctx);
-    if (ctx->d_crt) cudaFree(ctx->d_crt);
-    if (ctx->d_table) cudaFree(ctx->d_table);
-    for (void* p : ctx->d_stage) if (p) cudaFree(p);
+    // key material and plaintext scratch do not go back to the allocator as they are (engine.hpp: dev_scrub_free)
+    dev_scrub_free(ctx->d_crt, ctx->d_crt_bytes);
+    dev_scrub_free(ctx->d_table, ctx->table_limbs * 4);
+    for (int i = 0; i < 16; ++i) dev_scrub_free(ctx->d_stage[i], ctx->stage_bytes[i]);
+    scrub(ctx->p); scrub(ctx->q); scrub(ctx->tk_share);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); }

@@ -84,9 +84,27 @@ int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N) {
     return PGPU_OK;
 }
 
+void dev_scrub_free(void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes) {
+        cudaDeviceSynchronize();
+        cudaMemset(p, 0, bytes);
+    }
+    cudaFree(p);
+}
+
+void scrub(std::vector<uint32_t>& v) {
+    volatile uint32_t* q = v.data();
+    for (size_t i = 0; i < v.size(); ++i) q[i] = 0;
+    v.clear();
+}
+
+void scrub(BigU& x) { scrub(x.v); }
+
 void modctx_free(ModCtx& m) {
-    if (m.d_mod) cudaFree(m.d_mod);
-    if (m.d_kconst) cudaFree(m.d_kconst);
+    dev_scrub_free(m.d_mod, (size_t)m.sh.S * 4);
+    dev_scrub_free(m.d_kconst, (size_t)K_SLOTS * m.sh.S * 4);
+    scrub(m.N); scrub(m.R1); scrub(m.R2); scrub(m.R3); scrub(m.W1);
     m = ModCtx();
 }
 
@@ -165,12 +183,14 @@ void emit_pow_items(Program& P, size_t exp_bits, uint32_t tb) {
 
 int program_upload(pgpu_ctx* ctx, Program& P) {
     P.ops.push_back(vm_op(OP_END, 0));
-    if (P.d_ops) cudaFree(P.d_ops);
+    dev_scrub_free(P.d_ops, P.d_bytes);
+    P.d_ops = nullptr; P.d_bytes = 0;
     CU(ctx, cudaMalloc(&P.d_ops, P.ops.size() * 4));
+    P.d_bytes = P.ops.size() * 4;
     return upload(ctx, P.d_ops, P.ops);
 }
 
-void program_free(Program& P) { if (P.d_ops) cudaFree(P.d_ops); P = Program(); }
+void program_free(Program& P) { dev_scrub_free(P.d_ops, P.d_bytes); scrub(P.ops); P = Program(); }
 
 // ------------------------------------------------------------- launching
 int ensure_table(pgpu_ctx* ctx, size_t limbs) {
@@ -371,9 +391,13 @@ int setup_crt(pgpu_ctx* ctx) {
     auto push = [&](const BigU& x) { auto l = x.limbs(h); K.insert(K.end(), l.begin(), l.end()); };
     push(p); push(q); push(pinv); push(qinv);
     push((hp * Rh) % p); push((hq * Rh) % q); push((qinv_p * Rh) % p);
-    if (ctx->d_crt) cudaFree(ctx->d_crt);
+    dev_scrub_free(ctx->d_crt, ctx->d_crt_bytes);
+    ctx->d_crt = nullptr; ctx->d_crt_bytes = 0;
     CU(ctx, cudaMalloc(&ctx->d_crt, K.size() * 4));
-    if ((rc = upload(ctx, ctx->d_crt, K))) return rc;
+    ctx->d_crt_bytes = K.size() * 4;
+    rc = upload(ctx, ctx->d_crt, K);
+    scrub(K);
+    if (rc) return rc;
     ctx->crt_np0_p = mont_np0(p.v[0]); ctx->crt_np0_q = mont_np0(q.v[0]);
     ctx->has_secret = true;
     if ((rc = setup_encrypt_crt(ctx))) return rc;

@@ -40,6 +40,7 @@ enum : uint32_t {
 struct Program {
     std::vector<uint32_t> ops;
     uint32_t* d_ops = nullptr;
+    size_t d_bytes = 0;             // size of d_ops (scrubbed before it is freed: the ops of a secret exponent spell it out)
     uint32_t n_sqr = 0, n_mul = 0, tbl_entries = 0;
     bool per_item = false;          // uses OP_WIN: table entries picked by per-item exponent bits
     void emit(uint32_t code, uint32_t arg) { ops.push_back(vm_op(code, arg)); if (code == OP_WIN) per_item = true; }
@@ -84,7 +85,7 @@ struct pgpu_ctx {
     // secret key
     bool has_secret = false;
     pgpu::BigU p, q;
-    uint32_t* d_crt = nullptr;
+    uint32_t* d_crt = nullptr; size_t d_crt_bytes = 0;
     uint32_t crt_np0_p = 0, crt_np0_q = 0;
     int crt_h = 0;
 
@@ -106,7 +107,7 @@ struct pgpu_ctx {
     pgpu::Program prog_dec2_p, prog_dec2_q;
     pgpu::Program prog_enc2q, prog_enc2p, prog_enc2f;   // secret-key EncryptWithRAtLevel(2) over p^3, q^3 (encrypt2_crt_dev)
     bool enc2_crt_ready = false;
-    uint32_t* d_crt2 = nullptr; size_t crt2_cq_off = 0, crt2_g_off = 0;
+    uint32_t* d_crt2 = nullptr; size_t d_crt2_bytes = 0, crt2_cq_off = 0, crt2_g_off = 0;
     uint32_t crt2_np0[4] = {0, 0, 0, 0};
     bool crt2_ready = false;
     bool has_alt = false;
@@ -203,6 +204,12 @@ size_t resident_groups(const pgpu_ctx* ctx, const ModCtx& m);
 
 bool pick_shape(size_t limbs, Shape& out);
 int upload(pgpu_ctx* ctx, uint32_t* dst, const std::vector<uint32_t>& v);
+// Device memory that held key material (CRT constants, Montgomery constants of p^2 / q^2, the window programs of secret
+// exponents) or plaintexts (staging, scratch tables) is zeroed before it goes back to the allocator; the same for the
+// context's long-lived host copies of p, q and the share.  Waits for the device first: a queued kernel may still read it.
+void dev_scrub_free(void* p, size_t bytes);
+void scrub(BigU& x);
+void scrub(std::vector<uint32_t>& v);
 int set_kconst(pgpu_ctx* ctx, ModCtx& m, uint32_t slot, const BigU& v);
 int modctx_init(pgpu_ctx* ctx, ModCtx& m, const BigU& N);
 void modctx_free(ModCtx& m);

@@ -104,7 +104,7 @@ void protocols_free(pgpu_ctx* ctx) {
     program_free(ctx->prog_enc2); program_free(ctx->prog_rand); program_free(ctx->prog_alt1); program_free(ctx->prog_alt2);
     fixed_table_free(ctx->fix_h1); fixed_table_free(ctx->fix_h2); fixed_table_free(ctx->fix_v);
     if (ctx->d_rec2) { cudaFree(ctx->d_rec2); ctx->d_rec2 = nullptr; }
-    if (ctx->d_crt2) { cudaFree(ctx->d_crt2); ctx->d_crt2 = nullptr; }
+    dev_scrub_free(ctx->d_crt2, ctx->d_crt2_bytes); ctx->d_crt2 = nullptr; ctx->d_crt2_bytes = 0;
     program_free(ctx->prog_dec2_p); program_free(ctx->prog_dec2_q);
     program_free(ctx->prog_enc2q); program_free(ctx->prog_enc2p); program_free(ctx->prog_enc2f);
     ctx->enc2_crt_ready = false;
@@ -309,8 +309,9 @@ int setup_level2_crt(pgpu_ctx* ctx) {
     BigU q2inv;
     if (!BigU::modinv(q2 % p2, p2, q2inv)) return fail(ctx, PGPU_ERR_ARG, "p and q are not coprime");
     for (const BigU& x : {(q2inv * (R % p2)) % p2, q2}) { auto l = x.limbs(H); K.insert(K.end(), l.begin(), l.end()); }
-    if (ctx->d_crt2) { cudaFree(ctx->d_crt2); ctx->d_crt2 = nullptr; }
+    dev_scrub_free(ctx->d_crt2, ctx->d_crt2_bytes); ctx->d_crt2 = nullptr; ctx->d_crt2_bytes = 0;
     CU(ctx, cudaMalloc(&ctx->d_crt2, K.size() * 4));
+    ctx->d_crt2_bytes = K.size() * 4;
     if ((rc = upload(ctx, ctx->d_crt2, K))) return rc;
     ctx->crt2_np0[0] = mont_np0(p.v[0]); ctx->crt2_np0[1] = mont_np0(p2.v[0]);
     ctx->crt2_np0[2] = mont_np0(q.v[0]); ctx->crt2_np0[3] = mont_np0(q2.v[0]);
