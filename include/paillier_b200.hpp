@@ -15,6 +15,9 @@
 //   paillier::ThresholdPublicKey::VerifyProofBatch / CombinePartialDecryptionsBatch / CombinePartialDecryptionsZKPBatch /
 //     VerifyDecryptionBatch                                                             <- thresholdkey.go:149-189,278-311
 //   paillier::ThresholdSecretKey::GetPublicKey / VerifyPartialDecryption                <- thresholdkey.go:213-222,258-275
+//   paillier::DeviceBuffer / PinnedBytes, PublicKey::EncryptWithRDev / ConstMultDev / AddPairsDev / AddReduceDev / Sync,
+//     SecretKey::DecryptDev, ThresholdSecretKey::PartialDecryptDev  <- ciphertexts kept on the GPU between operations.go calls
+//   paillier::ThresholdGroup  <- one share-holder per GPU: thresholdkey.go:149-172,192-311 with one NCCL all-gather
 //   the callers that draw their own randomness (paillier::RandomSource, default the OS CSPRNG) or take an argument list:
 //   PublicKey::EncryptBatch / EncryptAtLevelBatch / NestedEncryptBatch / AltEncryptAtLevelBatch / EncryptZero*Batch /
 //     EncryptOne*Batch / RandomizeBatch / NestedRandomizeBatch / SubBatch  <- paillier.go:192-203,244-289, operations.go:32-55,67-118
@@ -305,6 +308,55 @@ inline std::vector<uint8_t> Ciphertext::Bytes() const { return gob::encode(*this
 // PublicKey.NewCiphertextFromBytes (paillier.go:374-390); like the reference it needs no key material and does not range-check C
 inline Ciphertext NewCiphertextFromBytes(const std::vector<uint8_t>& data) { return gob::decode(data.data(), data.size()); }
 
+// Device memory on a key's device (pgpu_buf_*): what the *Dev methods below take, so that ciphertexts stay on the GPU between
+// Encrypt / ConstMult / Add / Decrypt calls (the callers of operations.go:11-64).  Made by PublicKey::NewDeviceBuffer; free it
+// (destructor) before the key it came from.
+class DeviceBuffer {
+public:
+    DeviceBuffer(pgpu_ctx* ctx, size_t bytes) {
+        const int rc = pgpu_buf_alloc(ctx, bytes, &buf_);
+        if (rc != PGPU_OK) throw Error(rc, pgpu_last_error(ctx));
+    }
+    ~DeviceBuffer() { if (buf_) pgpu_buf_free(buf_); }
+    DeviceBuffer(DeviceBuffer&& o) noexcept : buf_(o.buf_) { o.buf_ = nullptr; }
+    DeviceBuffer& operator=(DeviceBuffer&& o) noexcept { if (this != &o) { if (buf_) pgpu_buf_free(buf_); buf_ = o.buf_; o.buf_ = nullptr; } return *this; }
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    void* ptr() const { return pgpu_buf_ptr(buf_); }
+    size_t size() const { return pgpu_buf_size(buf_); }
+    // blocking copies of whole records at byte offset `off`
+    void Upload(size_t off, const std::vector<uint8_t>& records) {
+        const int rc = pgpu_buf_upload(buf_, off, records.data(), records.size());
+        if (rc != PGPU_OK) throw Error(rc, pgpu_last_error(nullptr));
+    }
+    std::vector<uint8_t> Download(size_t off, size_t bytes) const {
+        std::vector<uint8_t> out(bytes);
+        const int rc = pgpu_buf_download(buf_, off, out.data(), bytes);
+        if (rc != PGPU_OK) throw Error(rc, pgpu_last_error(nullptr));
+        return out;
+    }
+private:
+    pgpu_buf* buf_ = nullptr;
+};
+
+// Page-locked host memory (pgpu_host_alloc): the host-buffer entry points copy from / to it at the full PCIe rate and overlap
+// the copies of one chunk with the kernels of the next (pageable memory works too, several times slower).
+class PinnedBytes {
+public:
+    explicit PinnedBytes(size_t bytes) : size_(bytes) {
+        const int rc = pgpu_host_alloc(bytes, &p_);
+        if (rc != PGPU_OK) throw Error(rc, pgpu_last_error(nullptr));
+    }
+    ~PinnedBytes() { if (p_) pgpu_host_free(p_); }
+    PinnedBytes(const PinnedBytes&) = delete;
+    PinnedBytes& operator=(const PinnedBytes&) = delete;
+    uint8_t* data() const { return static_cast<uint8_t*>(p_); }
+    size_t size() const { return size_; }
+private:
+    void* p_ = nullptr;
+    size_t size_ = 0;
+};
+
 // PublicKey{N} with g = n+1 (paillier.go:46-56,147); owns one engine context on `device`.
 class PublicKey {
 public:
@@ -556,9 +608,38 @@ public:
         return out;
     }
 
+    // ---- device-resident batches: work is enqueued on the context's stream and NOT synchronised; Sync() waits for it ------
+    DeviceBuffer NewDeviceBuffer(size_t bytes) { return DeviceBuffer(ctx_, bytes); }
+    void Sync() { check(pgpu_ctx_sync(ctx_)); }
+    // c[i] = EncryptWithR(m[i], r[i]) (paillier.go:185-187): n-width m and r, n2-width c
+    void EncryptWithRDev(size_t count, const DeviceBuffer& m, const DeviceBuffer& r, DeviceBuffer& c) {
+        need(m, count * w_n); need(r, count * w_n); need(c, count * w_n2);
+        check(pgpu_encrypt_with_r_dev(ctx_, count, m.ptr(), r.ptr(), c.ptr()));
+    }
+    // out[i] = ConstMult(c[i], k[i]) (operations.go:58-64): k = k_bytes-wide little-endian unsigned scalars (multiple of 4)
+    void ConstMultDev(size_t count, const DeviceBuffer& c, const DeviceBuffer& k, size_t k_bytes, DeviceBuffer& out) {
+        need(c, count * w_n2); need(k, count * k_bytes); need(out, count * w_n2);
+        check(pgpu_const_mult_dev(ctx_, count, c.ptr(), k.ptr(), k_bytes, out.ptr()));
+    }
+    // out[i] = Add(a[i], b[i]) (operations.go:11-29); out may be a or b
+    void AddPairsDev(size_t count, const DeviceBuffer& a, const DeviceBuffer& b, DeviceBuffer& out) {
+        need(a, count * w_n2); need(b, count * w_n2); need(out, count * w_n2);
+        check(pgpu_add_pairs_dev(ctx_, count, a.ptr(), b.ptr(), out.ptr()));
+    }
+    // out = Add(c[0], ..., c[count-1]) as one tree reduction
+    void AddReduceDev(size_t count, const DeviceBuffer& c, DeviceBuffer& out) {
+        need(c, count * w_n2); need(out, w_n2);
+        check(pgpu_add_reduce_dev(ctx_, count, c.ptr(), out.ptr()));
+    }
+    // the C ABI handle of this key's context (pgpu.h), for entry points this header does not wrap
+    pgpu_ctx* Handle() const { return ctx_; }
+
     size_t w_n = 0, w_n2 = 0, w_n3 = 0;
 
 protected:
+    static void need(const DeviceBuffer& b, size_t bytes) {
+        if (b.size() < bytes) throw Error(PGPU_ERR_ARG, "device buffer smaller than the batch");
+    }
     pgpu_ctx* ctx_ = nullptr;
     unsigned k_bits_ = 0;
     size_t plain_width(int level) const {
@@ -623,6 +704,11 @@ public:
         std::vector<Int> zeros(rs.size()), out;
         for (auto& c : EncryptWithRBatch(zeros, rs)) out.push_back(std::move(c.C));
         return out;
+    }
+    // m[i] = Decrypt(c[i]) (paillier.go:292-303, CRT over p^2, q^2) on device buffers: n2-width c, n-width m; enqueued, see Sync()
+    void DecryptDev(size_t count, const DeviceBuffer& c, DeviceBuffer& m) {
+        need(c, count * w_n2); need(m, count * w_n);
+        check(pgpu_decrypt_dev(ctx_, count, c.ptr(), m.ptr()));
     }
     // N x SecretKey.Decrypt (paillier.go:292-340); one encryption level per batch
     std::vector<Int> DecryptBatch(const std::vector<Ciphertext>& cts) {
@@ -824,6 +910,11 @@ public:
         for (bool ok : VerifyProofBatch(PartialDecryptionWithZKPBatch(cs, rs)))
             if (!ok) throw Error(PGPU_ERR_ARG, "Invalid share");
     }
+    // out[i] = PartialDecrypt(c[i]) (thresholdkey.go:192-201) on device buffers of n2-width records; enqueued, see Sync()
+    void PartialDecryptDev(size_t count, const DeviceBuffer& c, DeviceBuffer& out) {
+        need(c, count * w_n2); need(out, count * w_n2);
+        check(pgpu_partial_decrypt_dev(ctx_, count, c.ptr(), out.ptr()));
+    }
     // N x ThresholdSecretKey.PartialDecrypt (thresholdkey.go:192-201)
     std::vector<PartialDecryption> PartialDecryptBatch(const std::vector<Int>& cs) {
         auto c = detail::to_records(cs, w_n2);
@@ -846,6 +937,58 @@ public:
 
 private:
     int device_ = 0;
+};
+
+// Threshold decryption with one share-holder per GPU of this process (pgpu_multi_*, BASELINE config 4): PartialDecrypt (+ proofs)
+// of every ciphertext on every device, one NCCL all-gather, proof verification and Combine of a ciphertext slice per device
+// (thresholdkey.go:149-172,192-311).  Takes one ThresholdSecretKey per device, all shares of the same key; the keys must
+// outlive the group.
+class ThresholdGroup {
+public:
+    explicit ThresholdGroup(const std::vector<ThresholdSecretKey*>& keys) : keys_(keys) {
+        if (keys.empty()) throw Error(PGPU_ERR_ARG, "ThresholdGroup: at least one share-holder");
+        std::vector<pgpu_ctx*> raw;
+        for (auto* k : keys) raw.push_back(k->Handle());
+        const int rc = pgpu_multi_create(&m_, raw.data(), (int)raw.size());
+        if (rc != PGPU_OK) throw Error(rc, pgpu_multi_last_error(nullptr));
+    }
+    ~ThresholdGroup() { if (m_) pgpu_multi_destroy(m_); }
+    ThresholdGroup(const ThresholdGroup&) = delete;
+    ThresholdGroup& operator=(const ThresholdGroup&) = delete;
+    int Size() const { return pgpu_multi_size(m_); }
+    // Plaintexts of cs.  zkp_rs is empty (PartialDecrypt + CombinePartialDecryptions) or holds, per share-holder, one r in
+    // [0, n^2) per ciphertext (PartialDecryptionWithZKP + CombinePartialDecryptionsZKP; the reference draws r at
+    // thresholdkey.go:233).  Where too few proofs verify the reference answers "Threshold not meet" for that ciphertext: with
+    // item_ok == nullptr the call throws Error(PGPU_ERR_THRESHOLD) if that happens to any; otherwise (*item_ok)[i] tells which
+    // plaintexts are valid.
+    std::vector<Int> Decrypt(const std::vector<Int>& cs, const std::vector<std::vector<Int>>& zkp_rs = {}, std::vector<bool>* item_ok = nullptr) {
+        const size_t w_n = keys_[0]->w_n, w_n2 = keys_[0]->w_n2, count = cs.size();
+        auto c = detail::to_records(cs, w_n2);
+        std::vector<std::vector<uint8_t>> rrec;
+        std::vector<const void*> rp;
+        if (!zkp_rs.empty()) {
+            if (zkp_rs.size() != keys_.size()) throw Error(PGPU_ERR_ARG, "one vector of randomness per share-holder");
+            for (const auto& rs : zkp_rs) {
+                if (rs.size() != count) throw Error(PGPU_ERR_ARG, "one r per ciphertext and share-holder");
+                rrec.push_back(detail::to_records(rs, w_n2));
+            }
+            for (const auto& r : rrec) rp.push_back(r.data());
+        }
+        std::vector<uint8_t> m(count * w_n, 0), flags(count, 0);
+        const int rc = pgpu_multi_threshold_round(m_, count, c.data(), rp.empty() ? nullptr : rp.data(), m.data(), flags.data());
+        if (rc != PGPU_OK && !(rc == PGPU_ERR_THRESHOLD && item_ok)) throw Error(rc, pgpu_multi_last_error(m_));
+        if (item_ok) item_ok->assign(flags.begin(), flags.end());
+        return detail::from_records(m, w_n);
+    }
+    // device milliseconds of the last Decrypt per phase (max over the devices): PartialDecrypt, proofs, all-gather, VerifyProof, Combine
+    std::vector<float> PhasesMs() const {
+        std::vector<float> out(5, 0.f);
+        pgpu_multi_last_phases_ms(m_, out.data());
+        return out;
+    }
+private:
+    std::vector<ThresholdSecretKey*> keys_;
+    pgpu_multi* m_ = nullptr;
 };
 
 }  // namespace paillier

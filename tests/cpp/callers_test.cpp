@@ -6,6 +6,8 @@
 //   below bound             -> prints 64 draws of random_below(bound) from the deterministic source below
 //   paillier N lambda H k_bits
 //   threshold N l w V (vi) x l (id share) x l
+//   device N lambda
+//   group N V v1 share          (a 1-of-1 threshold key)
 #include <algorithm>
 #include <iostream>
 #include <string>
@@ -143,6 +145,62 @@ int main() {
             ThresholdSecretKey bad(N, l, w, V, vi, 1, share_bad);
             try { bad.VerifyPartialDecryption(1, test_random); expect(false, "Invalid share must throw"); }
             catch (const Error& e) { expect(std::string(e.what()) == "Invalid share", "Invalid share"); }
+        } else if (kind == "device") {
+            // Encrypt -> ConstMult -> Add -> Decrypt with the ciphertexts staying on the GPU (DeviceBuffer), against the host-buffer batch calls
+            Int N = rd(), lambda = rd();
+            SecretKey sk(N, lambda);
+            const size_t count = 6, kb = 8;
+            std::vector<Int> ms, ks;
+            for (size_t i = 0; i < count; ++i) { ms.push_back(random_below(N, test_random)); ks.push_back(random_below(from_hex("0xffffffffffffffff"), test_random)); }
+            auto rs = sk.DrawUnits(count, test_random);
+            auto cts = sk.EncryptWithRBatch(ms, rs);
+            auto sum = sk.AddBatch(sk.ConstMultBatch(cts, ks));
+            auto plain = sk.DecryptBatch({sum});
+            auto m = sk.NewDeviceBuffer(count * sk.w_n), r = sk.NewDeviceBuffer(count * sk.w_n), k = sk.NewDeviceBuffer(count * kb);
+            auto c = sk.NewDeviceBuffer(count * sk.w_n2), c2 = sk.NewDeviceBuffer(count * sk.w_n2), total = sk.NewDeviceBuffer(sk.w_n2), out = sk.NewDeviceBuffer(sk.w_n);
+            expect(m.size() == count * sk.w_n && m.ptr() != nullptr, "DeviceBuffer size / ptr");
+            m.Upload(0, detail::to_records(ms, sk.w_n)); r.Upload(0, detail::to_records(rs, sk.w_n)); k.Upload(0, detail::to_records(ks, kb));
+            sk.EncryptWithRDev(count, m, r, c);
+            sk.ConstMultDev(count, c, k, kb, c2);
+            sk.AddReduceDev(count, c2, total);
+            sk.DecryptDev(1, total, out);
+            sk.Sync();
+            std::vector<Int> cvals;
+            for (auto& ct : cts) cvals.push_back(ct.C);
+            expect(detail::from_records(c.Download(0, count * sk.w_n2), sk.w_n2) == cvals, "EncryptWithRDev == EncryptWithRBatch");
+            expect(detail::from_records(total.Download(0, sk.w_n2), sk.w_n2)[0] == sum.C, "ConstMultDev + AddReduceDev == AddBatch(ConstMultBatch)");
+            expect(detail::from_records(out.Download(0, sk.w_n), sk.w_n) == plain, "DecryptDev == DecryptBatch");
+            sk.AddPairsDev(count, c, c2, c2);
+            sk.Sync();
+            auto pairs = sk.AddPairs(cts, sk.ConstMultBatch(cts, ks));
+            std::vector<Int> pvals;
+            for (auto& ct : pairs) pvals.push_back(ct.C);
+            expect(detail::from_records(c2.Download(0, count * sk.w_n2), sk.w_n2) == pvals, "AddPairsDev in place == AddPairs");
+            try { sk.EncryptWithRDev(count + 1, m, r, c); expect(false, "a batch larger than its buffers must throw"); }
+            catch (const Error& e) { expect(e.code == PGPU_ERR_ARG, "device buffer smaller than the batch"); }
+            DeviceBuffer moved = std::move(total);
+            expect(moved.size() == sk.w_n2, "DeviceBuffer is movable");
+            PinnedBytes pin(1 << 16);
+            expect(pin.data() != nullptr && pin.size() == (1 << 16), "PinnedBytes");
+            auto recs = detail::to_records(ms, sk.w_n);
+            std::copy(recs.begin(), recs.end(), pin.data());
+            m.Upload(0, std::vector<uint8_t>(pin.data(), pin.data() + recs.size()));
+        } else if (kind == "group") {
+            // one share-holder per device of this process (pgpu_multi_*): here a 1-of-1 key on device 0, a one-rank communicator
+            Int N = rd(), V = rd(), v1 = rd(), share = rd();
+            ThresholdSecretKey tsk(N, 1, 1, V, {v1}, 1, share);
+            ThresholdGroup grp({&tsk});
+            expect(grp.Size() == 1, "ThresholdGroup size");
+            const Int n2 = detail::mul(N, N);
+            std::vector<Int> ms, cs, rs;
+            for (int i = 0; i < 5; ++i) { ms.push_back(random_below(N, test_random)); rs.push_back(random_below(n2, test_random)); }
+            for (auto& c : tsk.EncryptBatch(ms, test_random)) cs.push_back(c.C);
+            expect(grp.Decrypt(cs) == ms, "ThresholdGroup::Decrypt without proofs");
+            std::vector<bool> item_ok;
+            expect(grp.Decrypt(cs, {rs}, &item_ok) == ms && item_ok == std::vector<bool>(5, true), "ThresholdGroup::Decrypt with proofs");
+            expect(grp.PhasesMs().size() == 5, "PhasesMs");
+            try { grp.Decrypt(cs, {rs, rs}); expect(false, "one vector of randomness per share-holder"); }
+            catch (const Error& e) { expect(e.code == PGPU_ERR_ARG, "one vector of randomness per share-holder"); }
         } else {
             std::cerr << "unknown section " << kind << "\n";
             return 2;

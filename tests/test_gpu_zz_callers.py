@@ -140,6 +140,11 @@ def test_cpp_mirror_callers():
     lines += ["threshold", hex(I(t["p"]) * I(t["q"])), str(t["l"]), str(t["w"]), t["V"]] + t["vi"]
     for i in range(t["l"]):
         lines += [str(i + 1), t["shares"][i]]
+    # device-resident chaining (DeviceBuffer, *Dev methods) on the 64-bit key; a 1-of-1 threshold key for ThresholdGroup
+    lines += ["device", hex(p * q), hex((p - 1) * (q - 1))]
+    one = ThresholdKeyGenerator(512, 1, 1, rng=random.Random(5)).with_safe_primes(I(t["p"]), I(t["q"])).GenerateKeys()[0]
+    lines += ["group", hex(one.N), hex(one.VerificationKey), hex(one.VerificationKeys[0]), hex(one.Share)]
+    one.close()
     r = subprocess.run([build_callers_test()], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "callers ok" in r.stdout
