@@ -27,14 +27,17 @@
 // arithmetic on batch items happens in libpaillier_b200.so on the GPU.  Errors: paillier::Error carries the PGPU_ERR_*
 // code; the reference's error strings ("Threshold not meet", ...) are the message.
 #pragma once
+#include <cerrno>
 #include <cstdint>
-#include <cstdio>
 #include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include <sys/random.h>
+#include <sys/types.h>
 
 #include "pgpu.h"
 
@@ -139,10 +142,14 @@ inline Int mul(const Int& a, const Int& b) {
 // utils.go:26-49): fills `len` bytes.  The default reads the operating system's CSPRNG.
 using RandomSource = std::function<void(uint8_t*, size_t)>;
 inline void os_random(uint8_t* out, size_t len) {
-    std::FILE* f = std::fopen("/dev/urandom", "rb");
-    const size_t got = f ? std::fread(out, 1, len, f) : 0;
-    if (f) std::fclose(f);
-    if (got != len) throw Error(PGPU_ERR_STATE, "cannot read /dev/urandom");
+    while (len) {                                   // getrandom(2): the kernel's CSPRNG, no descriptor, no user-space buffer
+        const ssize_t got = getrandom(out, len, 0);
+        if (got < 0) {
+            if (errno == EINTR) continue;
+            throw Error(PGPU_ERR_STATE, "getrandom failed");
+        }
+        out += got; len -= (size_t)got;
+    }
 }
 // uniform in [0, bound) by rejection, as crypto/rand.Int does (utils.go:26-33)
 inline Int random_below(const Int& bound, const RandomSource& rnd) {

@@ -4,6 +4,7 @@
 // and tests/test_gpu_zz_callers.py (GPU).  Input: whitespace-separated tokens, integers in hex.
 //   mul a b                 -> prints a*b
 //   below bound             -> prints 64 draws of random_below(bound) from the deterministic source below
+//   osrandom bound          -> the same from os_random
 //   paillier N lambda H k_bits
 //   threshold N l w V (vi) x l (id share) x l
 //   device N lambda
@@ -46,6 +47,9 @@ int main() {
                 expect(detail::less(r, bound), "random_below < bound");
                 std::cout << to_hex(r) << (i == 63 ? "\n" : " ");
             }
+        } else if (kind == "osrandom") {                      // the default source: the operating system's CSPRNG
+            Int bound = rd();
+            for (int i = 0; i < 64; ++i) std::cout << to_hex(random_below(bound, os_random)) << (i == 63 ? "\n" : " ");
         } else if (kind == "paillier") {
             Int N = rd(), lambda = rd(), H = rd();
             unsigned k_bits; std::cin >> k_bits;

@@ -119,7 +119,7 @@ def test_cpp_host_helpers_of_the_drawing_callers():
     pairs = [(0, 5), (1, 1), (255, 255), (2 ** 64 - 1, 2 ** 64 - 1), (2 ** 2048 - 1, 2 ** 2048 - 1), (2 ** 6144 - 1, 2 ** 6144 - 1)]
     pairs += [(rnd.getrandbits(a), rnd.getrandbits(b)) for a, b in ((8, 4096), (1024, 1024), (2048, 2048), (3072, 3072), (4096, 17))]
     bounds = [1, 2, 3, 255, 256, 257, 2 ** 64, rnd.getrandbits(2048) | 1 << 2047, 5 << 1000]
-    lines = [f"mul {a:x} {b:x}" for a, b in pairs] + [f"below {b:x}" for b in bounds]
+    lines = [f"mul {a:x} {b:x}" for a, b in pairs] + [f"below {b:x}" for b in bounds] + [f"osrandom {1 << 128:x}"] * 2
     r = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     out = r.stdout.split("\n")
@@ -131,4 +131,6 @@ def test_cpp_host_helpers_of_the_drawing_callers():
             assert len(set(draws)) > 32 and max(draws) >= b // 4          # spread over the range, top bits used
         elif b > 1:
             assert len(set(draws)) > 1
-    assert out[len(pairs) + len(bounds)] == "callers ok"
+    a, b = ([int(x, 16) for x in out[len(pairs) + len(bounds) + i].split()] for i in (0, 1))
+    assert len(set(a + b)) == 128 and all(0 <= v < 1 << 128 for v in a + b) and max(a + b) >> 120      # getrandom(2): no repeats, full range
+    assert out[len(pairs) + len(bounds) + 2] == "callers ok"
