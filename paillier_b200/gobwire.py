@@ -82,7 +82,8 @@ class _Reader:
         return ~(u >> 1) if u & 1 else u >> 1
 
     def string(self) -> str:
-        return self.take(self.uint()).decode()
+        # a Go string is arbitrary bytes (gob does not validate UTF-8): a name that is not UTF-8 is just a name that matches nothing
+        return self.take(self.uint()).decode("utf-8", "surrogateescape")
 
 
 # ---- gmp.Int (ncw/gmp Int.GobEncode / GobDecode) -------------------------------------------------------------------
