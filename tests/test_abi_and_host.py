@@ -122,3 +122,30 @@ def test_host_bignum_against_python():
     for a, b in [((1 << 128) - 1, (1 << 64) + 1), ((1 << 96), (1 << 64) - 1), (0x7fffffff800000010000000000000000, 0x800000008000000200000005),
                  ((1 << 4096) - 1, (1 << 2048) - 1), (3 * ((1 << 64) - 1) ** 2, (1 << 64) - 1)]:
         assert _bn(1, a, b) == a // b and _bn(2, a, b) == a % b
+
+
+def test_every_export_survives_null_and_zero_arguments():
+    """No abort across the ABI (SURVEY.md 8b "Errors"): every exported function called with a null context, null pointers and
+    zero counts returns (an error code where it has one) instead of crashing.  Runs in a child process so that a crash is a
+    test failure, not the end of the test session."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from paillier_b200 import _lib as L
+ints = (C.c_int, C.c_uint, C.c_size_t, C.c_uint32, C.c_uint64)
+for name, (res, args) in L.SIGNATURES.items():
+    rc = getattr(L.lib, name)(*[0 if a in ints else None for a in args])
+    print(name, rc, flush=True)
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    lines = dict(l.split(" ", 1) for l in r.stdout.strip().split("\n"))
+    assert r.returncode == 0, f"crashed after {list(lines)[-1] if lines else 'start'}: {r.stderr[-500:]}"
+    L = _lib()
+    assert set(lines) == set(L.SIGNATURES)
+    ok_with_nulls = {"pgpu_version", "pgpu_ctx_destroy", "pgpu_buf_free", "pgpu_host_free", "pgpu_multi_destroy",     # destroy(NULL) is a no-op
+                     "pgpu_buf_size", "pgpu_multi_size", "pgpu_buf_ptr", "pgpu_last_error", "pgpu_primes_last_error", "pgpu_multi_last_error"}
+    for name, rc in lines.items():
+        if name not in ok_with_nulls:
+            assert rc not in ("0", "None"), f"{name} accepted null arguments"
