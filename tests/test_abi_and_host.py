@@ -149,3 +149,42 @@ for name, (res, args) in L.SIGNATURES.items():
     for name, rc in lines.items():
         if name not in ok_with_nulls:
             assert rc not in ("0", "None"), f"{name} accepted null arguments"
+
+
+def test_host_bignum_structured_operands():
+    """bn_host.hpp on operands built to hit carries, borrows and normalisation: all-ones, single bits, 2^k - small, limbs drawn
+    from {0, 0xffffffff, 0x80000000, 1, random}, widths around the 32-bit and 64-bit limb boundaries up to 8191 bits."""
+    import math
+    rnd = random.Random(4242)
+
+    def rv():
+        bits = rnd.choice([0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 255, 256, 1000, 2048, 4096, 6144, 8191])
+        if bits == 0:
+            return 0
+        k = rnd.randrange(8)
+        if k == 0:
+            return (1 << bits) - 1
+        if k == 1:
+            return 1 << (bits - 1)
+        if k == 2:
+            return max(0, (1 << bits) - rnd.randrange(1, 4))
+        if k == 3:
+            v = 0
+            for i in range(0, bits, 32):
+                v |= rnd.choice([0, 0xffffffff, 0x80000000, 1, rnd.getrandbits(32)]) << i
+            return v & ((1 << bits) - 1)
+        return rnd.getrandbits(bits)
+
+    for it in range(400):
+        a, b = rv(), rv()
+        assert _bn(0, a, b) == a * b
+        if b:
+            assert _bn(1, a, b) == a // b and _bn(2, a, b) == a % b
+        m = rv() | 1
+        if m > 1:
+            want = pow(a, -1, m) if math.gcd(a, m) == 1 else None
+            assert _bn(3, a, 0, m) == want
+            if it % 7 == 0:
+                e = rnd.getrandbits(rnd.choice([1, 8, 64, 130]))
+                assert _bn(4, a, e, m) == pow(a, e, m)
+        assert _bn(5, a) == math.isqrt(a)
