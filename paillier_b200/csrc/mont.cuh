@@ -30,6 +30,7 @@ namespace pgpu {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+#ifndef PGPU_HOST_EMULATION
 // ---- single-instruction carry-chain primitives (CC flag lives across them) --
 __device__ __forceinline__ void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) {
     asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -58,6 +59,26 @@ __device__ __forceinline__ void subc_cc(uint32_t& d, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void subc(uint32_t& d, uint32_t a, uint32_t b) {
     asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
 }
+#else
+// ---- the same primitives for tests/cpp/mont_host_test.cpp, which runs THIS header on CPU threads (one per lane of an
+// emulated warp, tests/cpp/cuda_host_shim.h): the CC.CF flag of a thread is a thread-local variable.
+inline thread_local uint32_t pgpu_cc = 0;
+inline void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) {
+    const uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c; d = (uint32_t)s; pgpu_cc = (uint32_t)(s >> 32);
+}
+inline void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) {
+    const uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + c + pgpu_cc; d = (uint32_t)s; pgpu_cc = (uint32_t)(s >> 32);
+}
+inline void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) {
+    const uint64_t s = (((uint64_t)a * b) >> 32) + c + pgpu_cc; d = (uint32_t)s; pgpu_cc = (uint32_t)(s >> 32);
+}
+inline void add_cc(uint32_t& d, uint32_t a, uint32_t b) { const uint64_t s = (uint64_t)a + b; d = (uint32_t)s; pgpu_cc = (uint32_t)(s >> 32); }
+inline void addc_cc(uint32_t& d, uint32_t a, uint32_t b) { const uint64_t s = (uint64_t)a + b + pgpu_cc; d = (uint32_t)s; pgpu_cc = (uint32_t)(s >> 32); }
+inline void addc(uint32_t& d, uint32_t a, uint32_t b) { d = a + b + pgpu_cc; }
+inline void sub_cc(uint32_t& d, uint32_t a, uint32_t b) { const uint32_t bw = a < b; d = a - b; pgpu_cc = bw; }
+inline void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { const uint32_t bw = (uint64_t)a < (uint64_t)b + pgpu_cc; d = a - b - pgpu_cc; pgpu_cc = bw; }
+inline void subc(uint32_t& d, uint32_t a, uint32_t b) { d = a - b - pgpu_cc; }
+#endif
 
 // Carry look-ahead over a group: g = lanes that generate a carry, p = lanes
 // that propagate one (mutually exclusive).  Returns the mask of lanes that
@@ -73,12 +94,16 @@ __device__ __forceinline__ uint64_t lookahead(uint32_t g, uint32_t p) {
 // loop (half the multiplies per row, same per-row bookkeeping) 73 % -- so mul(a, a) stays faster there.
 template <int TPI_, int L_> struct SqrShape { static constexpr bool value = (TPI_ == 4) && (L_ % 8 == 0) && (L_ <= 16); };
 
+#ifndef PGPU_HOST_EMULATION
 __device__ __forceinline__ uint4 lds_v4_volatile(const uint4* p) {
     uint4 v;
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
+#else
+inline uint4 lds_v4_volatile(const uint4* p) { return *p; }
+#endif
 
 // NSM: the modulus limbs are kept in shared memory and fetched at every use instead of occupying L registers
 // for the whole kernel (needed by the dedicated squaring, whose product phase has no use for them).

@@ -1,0 +1,124 @@
+// Runs the multiplier SOURCES of the kernels -- paillier_b200/csrc/mont.cuh (32-bit limbs, integer pipe, incl. the dedicated
+// squaring with its shared-memory exchange) and mont52.cuh (52-bit limbs as doubles, FP64 pipe) -- on the CPU, one thread per
+// lane of an emulated warp (cuda_host_shim.h), and prints the results for tests/test_mont_host_emulation.py to compare with
+// Python integers.  Built with -fsanitize=thread it is the race check of the squaring's exchange protocol (tools/host_sanitize.sh).
+// stdin, whitespace separated, integers in hex:
+//   m32 TPI L NSM  n  G  (a b) x G      -> G lines "mul sqr add sub"      (R = 2^(32*TPI*L); a, b < n; one (a, b) per lane group)
+//   m52 TPI L S32  n  G  (a b) x G      -> G lines "mul add sub"          (R = 2^(52*TPI*L); records of S32 limbs)
+#include "cuda_host_shim.h"
+
+#include <iostream>
+#include <string>
+
+#include "../../paillier_b200/csrc/mont.cuh"
+#include "../../paillier_b200/csrc/mont52.cuh"
+
+using Limbs = std::vector<uint32_t>;
+
+static Limbs parse_hex(std::string h, size_t limbs) {
+    if (h.rfind("0x", 0) == 0) h = h.substr(2);
+    Limbs v(limbs, 0);
+    size_t nib = 0;
+    for (size_t i = h.size(); i-- > 0; ++nib) {
+        const char c = h[i];
+        const uint32_t d = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        if (nib / 8 >= limbs) { if (d) { std::cerr << "value wider than " << limbs << " limbs\n"; std::exit(2); } continue; }
+        v[nib / 8] |= d << (4 * (nib % 8));
+    }
+    return v;
+}
+static std::string to_hex(const Limbs& v) {
+    static const char* d = "0123456789abcdef";
+    std::string s;
+    for (size_t i = v.size(); i-- > 0;)
+        for (int k = 7; k >= 0; --k) s += d[(v[i] >> (4 * k)) & 15];
+    const size_t nz = s.find_first_not_of('0');
+    return "0x" + (nz == std::string::npos ? std::string("0") : s.substr(nz));
+}
+static uint32_t neg_inv32(uint32_t n0) {
+    uint32_t inv = n0;                                   // Newton: 3 correct bits, doubled four times
+    for (int i = 0; i < 5; ++i) inv *= 2u - n0 * inv;
+    return 0u - inv;
+}
+
+template <int TPI, int L, bool NSM>
+static void run32(const Limbs& n, const std::vector<Limbs>& A, const std::vector<Limbs>& B) {
+    using M = pgpu::Mont<TPI, L, NSM>;
+    constexpr int S = TPI * L, G = 32 / TPI;
+    std::vector<uint4> smem((size_t)M::SQR_ROWS * 32 + 1);
+    std::vector<Limbs> mul(G, Limbs(S)), sqr(G, Limbs(S)), add(G, Limbs(S)), sub(G, Limbs(S));
+    const uint32_t np0 = neg_inv32(n[0]);
+    hostwarp::run_warp([&](int lane) {
+        M m;
+        m.init(n.data(), np0);
+        if constexpr (M::HAS_SQR) m.init_sqr(smem.data());
+        const int g = lane / TPI, t = lane % TPI;
+        uint32_t a[L], b[L], r[L];
+        for (int k = 0; k < L; ++k) { a[k] = A[g % A.size()][t * L + k]; b[k] = B[g % B.size()][t * L + k]; }
+        m.mul(r, a, b);
+        for (int k = 0; k < L; ++k) mul[g][t * L + k] = r[k];
+        m.sqr(r, a);
+        for (int k = 0; k < L; ++k) sqr[g][t * L + k] = r[k];
+        m.add(r, a, b);
+        for (int k = 0; k < L; ++k) add[g][t * L + k] = r[k];
+        m.sub(r, a, b);
+        for (int k = 0; k < L; ++k) sub[g][t * L + k] = r[k];
+    });
+    for (size_t g = 0; g < A.size() && g < (size_t)G; ++g)
+        std::cout << to_hex(mul[g]) << " " << to_hex(sqr[g]) << " " << to_hex(add[g]) << " " << to_hex(sub[g]) << "\n";
+}
+
+template <int TPI, int L, int S32>
+static void run52(const Limbs& n, const std::vector<Limbs>& A, const std::vector<Limbs>& B) {
+    using M = pgpu::Mont52<TPI, L, S32>;
+    constexpr int G = 32 / TPI;
+    std::vector<Limbs> mul(G, Limbs(S32)), add(G, Limbs(S32)), sub(G, Limbs(S32));
+    const uint32_t np0 = neg_inv32(n[0]);
+    hostwarp::run_warp([&](int lane) {
+        M m;
+        m.init(n.data(), np0);
+        const int g = lane / TPI;
+        double x[L], y[L], r[L];
+        m.load_rec(x, A[g % A.size()].data(), S32);
+        m.load_rec(y, B[g % B.size()].data(), S32);
+        m.mul(r, x, y);
+        m.store_rec(mul[g].data(), r, S32);
+        m.add(r, x, y);
+        m.store_rec(add[g].data(), r, S32);
+        m.sub(r, x, y);
+        m.store_rec(sub[g].data(), r, S32);
+    });
+    for (size_t g = 0; g < A.size() && g < (size_t)G; ++g)
+        std::cout << to_hex(mul[g]) << " " << to_hex(add[g]) << " " << to_hex(sub[g]) << "\n";
+}
+
+// the shapes powm.cu builds (PGPU_FOR_EACH_SHAPE with NSM = SqrShape<TPI, L>::value, PGPU_FOR_EACH_SHAPE52)
+#define SHAPES32(X) X(2, 16, false) X(4, 8, true) X(4, 16, true) X(8, 8, false) X(8, 12, false) X(4, 24, false) X(8, 16, false) \
+                    X(16, 8, false) X(4, 32, false) X(32, 4, false) X(8, 24, false) X(16, 12, false) X(32, 6, false)
+#define SHAPES52(X) X(4, 5, 32) X(4, 10, 64) X(8, 5, 64) X(4, 15, 96) X(8, 8, 96) X(8, 10, 128) X(8, 15, 192) X(16, 8, 192)
+
+int main() {
+    std::string kind;
+    while (std::cin >> kind) {
+        int tpi, l, third;
+        std::string nh;
+        size_t groups;
+        std::cin >> tpi >> l >> third >> nh >> groups;
+        const size_t limbs = kind == "m32" ? (size_t)tpi * l : (size_t)third;
+        const Limbs n = parse_hex(nh, limbs);
+        std::vector<Limbs> A, B;
+        for (size_t g = 0; g < groups; ++g) { std::string a, b; std::cin >> a >> b; A.push_back(parse_hex(a, limbs)); B.push_back(parse_hex(b, limbs)); }
+        bool done = false;
+        if (kind == "m32") {
+#define X(T, LL, NSM) if (!done && tpi == T && l == LL && (third != 0) == NSM) { static_assert(pgpu::SqrShape<T, LL>::value == NSM, "NSM follows SqrShape"); run32<T, LL, NSM>(n, A, B); done = true; }
+            SHAPES32(X)
+#undef X
+        } else if (kind == "m52") {
+#define X(T, LL, SS) if (!done && tpi == T && l == LL && third == SS) { run52<T, LL, SS>(n, A, B); done = true; }
+            SHAPES52(X)
+#undef X
+        }
+        if (!done) { std::cerr << "shape not built: " << kind << " " << tpi << " " << l << " " << third << "\n"; return 2; }
+    }
+    return 0;
+}

@@ -38,3 +38,49 @@ r = subprocess.run([sys.argv[1]], input="\n".join("dec " + c.hex() for c in case
 print("gob decoder under ASan/UBSan: rc", r.returncode, "stderr bytes", len(r.stderr), "lines", len(r.stdout.split("\n")) - 1)
 sys.exit(r.returncode or (1 if r.stderr else 0))
 PY
+
+# ---- the multiplier sources under ThreadSanitizer: one thread per lane of an emulated warp (tests/cpp/cuda_host_shim.h), so a
+# missing __syncwarp() in the dedicated squaring's shared-memory exchange (csrc/mont.cuh: Mont::sqr) is a real data race
+g++ -std=c++20 -O1 -g -frounding-math -pthread -fsanitize=thread -Wno-unknown-pragmas tests/cpp/mont_host_test.cpp -o "$W/mont_host_tsan"
+unset LD_PRELOAD
+python - "$W/mont_host_tsan" "$W" <<'PY'
+import random, re, subprocess, sys
+exe, W = sys.argv[1], sys.argv[2]
+rnd = random.Random(7)
+src = open("paillier_b200/csrc/powm.cu").read()
+s32 = re.findall(r"X\((\d+),\s*(\d+)\)", src[src.index("#define PGPU_FOR_EACH_SHAPE(X)"):src.index("// FP64-pipe shapes")])
+s52 = re.findall(r"X\((\d+),\s*(\d+),\s*(\d+)\)", src[src.index("#define PGPU_FOR_EACH_SHAPE52(X)"):src.index("cudaError_t vm_launch")])
+lines = []
+for t, l in s32:
+    t, l = int(t), int(l)
+    bits, g = 32 * t * l, 32 // t
+    n = rnd.getrandbits(bits) | 1 | 1 << (bits - 1)
+    lines.append(f"m32 {t} {l} {int(t == 4 and l % 8 == 0 and l <= 16)} {n:x} {g} " + " ".join(f"{rnd.randrange(n):x} {rnd.randrange(n):x}" for _ in range(g)))
+for t, l, s in s52:
+    t, l, s = int(t), int(l), int(s)
+    n = rnd.getrandbits(32 * s) | 1 | 1 << (32 * s - 1)
+    lines.append(f"m52 {t} {l} {s} {n:x} {32 // t} " + " ".join(f"{rnd.randrange(n):x} {rnd.randrange(n):x}" for _ in range(32 // t)))
+inp = "\n".join(lines) + "\n"
+r = subprocess.run([exe], input=inp, capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0"})
+races = r.stderr.count("WARNING: ThreadSanitizer")
+print(f"multiplier sources under ThreadSanitizer ({len(s32)} integer + {len(s52)} FP64 shapes, mul/sqr/add/sub on every lane group): rc {r.returncode}, {races} reports")
+# negative control: the same harness against a copy of mont.cuh with ONE __syncwarp() of the squaring removed must be reported
+import os, shutil
+neg = os.path.join(W, "neg")
+shutil.rmtree(neg, ignore_errors=True)
+os.makedirs(os.path.join(neg, "paillier_b200", "csrc")); os.makedirs(os.path.join(neg, "tests", "cpp"))
+for f in ("mont.cuh", "mont52.cuh"): shutil.copy(os.path.join("paillier_b200", "csrc", f), os.path.join(neg, "paillier_b200", "csrc", f))
+for f in ("cuda_host_shim.h", "mont_host_test.cpp"): shutil.copy(os.path.join("tests", "cpp", f), os.path.join(neg, "tests", "cpp", f))
+p = os.path.join(neg, "paillier_b200", "csrc", "mont.cuh")
+s = open(p).read()
+old = "block_product_to_smem<L>(a, sa, round == 0 ? gb + ((t + 1) & 3) : wl, 0);\n                __syncwarp();\n"
+assert old in s
+open(p, "w").write(s.replace(old, old.replace("                __syncwarp();\n", ""), 1))
+subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-frounding-math", "-pthread", "-fsanitize=thread", "-Wno-unknown-pragmas",
+                os.path.join(neg, "tests", "cpp", "mont_host_test.cpp"), "-o", os.path.join(W, "mont_host_tsan_neg")], check=True)
+r2 = subprocess.run([os.path.join(W, "mont_host_tsan_neg")], input=inp, capture_output=True, text=True, env={"TSAN_OPTIONS": "halt_on_error=0"})
+neg_races = r2.stderr.count("WARNING: ThreadSanitizer")
+first = re.search(r"Read of size.*?\n\s+#0 (.*?) \(", r2.stderr, re.S)
+print(f"negative control (one __syncwarp of Mont::sqr removed): rc {r2.returncode}, {neg_races} reports; first: {first.group(1)[:160] if first else None}")
+sys.exit(1 if (r.returncode or races or not neg_races) else 0)
+PY
