@@ -5,6 +5,7 @@
 // stdin, whitespace separated, integers in hex:
 //   m32 TPI L NSM  n  G  (a b) x G      -> G lines "mul sqr add sub"      (R = 2^(32*TPI*L); a, b < n; one (a, b) per lane group)
 //   m52 TPI L S32  n  G  (a b) x G      -> G lines "mul add sub"          (R = 2^(52*TPI*L); records of S32 limbs)
+//   m52s TPI L S32 lim  n  G  (a b) x G -> G lines "mul"                  (a read from, the product stored to, records of lim limbs)
 #include "cuda_host_shim.h"
 
 #include <iostream>
@@ -92,6 +93,31 @@ static void run52(const Limbs& n, const std::vector<Limbs>& A, const std::vector
         std::cout << to_hex(mul[g]) << " " << to_hex(add[g]) << " " << to_hex(sub[g]) << "\n";
 }
 
+// short records: a is loaded from a record of `lim` limbs (EncryptWithR reads n-width m and r into the n^2 shape), the product is
+// stored as a record of `lim` limbs (what an n-width output gets); the caller picks b so that the product fits
+template <int TPI, int L, int S32>
+static void run52_short(const Limbs& n, uint32_t lim, const std::vector<Limbs>& A, const std::vector<Limbs>& B) {
+    using M = pgpu::Mont52<TPI, L, S32>;
+    constexpr int G = 32 / TPI;
+    std::vector<Limbs> mul(G, Limbs(S32, 0xdeadbeefu));
+    const uint32_t np0 = neg_inv32(n[0]);
+    hostwarp::run_warp([&](int lane) {
+        M m;
+        m.init(n.data(), np0);
+        const int g = lane / TPI;
+        double x[L], y[L], r[L];
+        m.load_rec(x, A[g % A.size()].data(), lim);
+        m.load_rec(y, B[g % B.size()].data(), S32);
+        m.mul(r, x, y);
+        m.store_rec(mul[g].data(), r, lim);
+    });
+    for (size_t g = 0; g < A.size() && g < (size_t)G; ++g) {
+        for (uint32_t k = lim; k < (uint32_t)S32; ++k)
+            if (mul[g][k] != 0xdeadbeefu) { std::cerr << "store_rec wrote past its " << lim << " limbs\n"; std::exit(3); }
+        std::cout << to_hex(Limbs(mul[g].begin(), mul[g].begin() + lim)) << "\n";
+    }
+}
+
 // the shapes powm.cu builds (PGPU_FOR_EACH_SHAPE with NSM = SqrShape<TPI, L>::value, PGPU_FOR_EACH_SHAPE52)
 #define SHAPES32(X) X(2, 16, false) X(4, 8, true) X(4, 16, true) X(8, 8, false) X(8, 12, false) X(4, 24, false) X(8, 16, false) \
                     X(16, 8, false) X(4, 32, false) X(32, 4, false) X(8, 24, false) X(16, 12, false) X(32, 6, false)
@@ -101,13 +127,22 @@ int main() {
     std::string kind;
     while (std::cin >> kind) {
         int tpi, l, third;
+        uint32_t lim = 0;
         std::string nh;
         size_t groups;
-        std::cin >> tpi >> l >> third >> nh >> groups;
+        std::cin >> tpi >> l >> third;
+        if (kind == "m52s") std::cin >> lim;
+        std::cin >> nh >> groups;
         const size_t limbs = kind == "m32" ? (size_t)tpi * l : (size_t)third;
         const Limbs n = parse_hex(nh, limbs);
         std::vector<Limbs> A, B;
-        for (size_t g = 0; g < groups; ++g) { std::string a, b; std::cin >> a >> b; A.push_back(parse_hex(a, limbs)); B.push_back(parse_hex(b, limbs)); }
+        for (size_t g = 0; g < groups; ++g) {
+            std::string a, b; std::cin >> a >> b;
+            A.push_back(parse_hex(a, limbs));
+            B.push_back(parse_hex(b, limbs));
+            if (kind == "m52s")                      // what lies behind a short record (the next item's record) must not be read
+                for (size_t k = lim; k < limbs; ++k) A.back()[k] = 0xa5a5a5a5u;
+        }
         bool done = false;
         if (kind == "m32") {
 #define X(T, LL, NSM) if (!done && tpi == T && l == LL && (third != 0) == NSM) { static_assert(pgpu::SqrShape<T, LL>::value == NSM, "NSM follows SqrShape"); run32<T, LL, NSM>(n, A, B); done = true; }
@@ -115,6 +150,10 @@ int main() {
 #undef X
         } else if (kind == "m52") {
 #define X(T, LL, SS) if (!done && tpi == T && l == LL && third == SS) { run52<T, LL, SS>(n, A, B); done = true; }
+            SHAPES52(X)
+#undef X
+        } else if (kind == "m52s") {
+#define X(T, LL, SS) if (!done && tpi == T && l == LL && third == SS) { run52_short<T, LL, SS>(n, lim, A, B); done = true; }
             SHAPES52(X)
 #undef X
         }

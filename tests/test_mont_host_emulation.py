@@ -100,3 +100,23 @@ def test_fp64_pipe_multiplier_source_on_emulated_warps(exe):
     assert len(out) == len(want)
     for got, exp in zip(out, want):
         assert all(e is None or g == e for g, e in zip(got, exp)), (got, exp)
+
+
+def test_fp64_pipe_short_records(exe):
+    """Mont52::load_rec / store_rec with records narrower than the modulus: EncryptWithR reads n-width m and r into the n^2 shape
+    (OP_LDI with in_limbs < S), n-width results are stored from it (out_limbs < S).  b = R mod n makes the product equal a."""
+    _, i52 = _shapes()
+    rnd = random.Random(53)
+    lines, want = [], []
+    for tpi, l, s32 in i52:
+        groups = 32 // tpi
+        R = 1 << (52 * tpi * l)
+        n = rnd.getrandbits(32 * s32) | 1 | (1 << (32 * s32 - 1))
+        for lim in (s32 // 2, 1, s32 - 1, s32 // 2 + 3):
+            pairs = [(rnd.getrandbits(32 * lim), R % n) for _ in range(groups)]
+            pairs[0] = ((1 << (32 * lim)) - 1, R % n)
+            lines.append(f"m52s {tpi} {l} {s32} {lim} {n:x} {groups} " + " ".join(f"{a:x} {b:x}" for a, b in pairs))
+            want += [a for a, _ in pairs]
+    r = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert [int(x, 16) for x in r.stdout.split()] == want
