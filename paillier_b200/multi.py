@@ -14,7 +14,7 @@
   earliest accepted candidate in stream order -- the same (p, q) a single device returns for that stream.
 
 The compute steps are injected as callables so that the plumbing can be exercised with the gloo backend on
-CPU tensors in tests (tests/test_multi_gloo.py); `gpu_threshold_round` binds them to the CUDA engine.
+CPU tensors in tests (tests/test_multi_gloo.py); `gpu_threshold_round_shares` is the same round on the CUDA engine.
 """
 from __future__ import annotations
 
@@ -42,9 +42,11 @@ def threshold_round(dist, rank: int, world: int, count: int, record_width: int,
     partial_decrypt() -> uint8 tensor [count * record_width]: this rank's share applied to every ciphertext.
     combine(gathered, ids, lo, hi) -> plaintext records of ciphertexts [lo, hi) from the gathered
         [world][count][record_width] buffer using the shares `ids` (server ids, rank r holds id r+1).
-    verify(gathered, r) (optional) -> whether rank r's partials are to be used (CombinePartialDecryptionsZKP,
-        thresholdkey.go:164-172 drops shares whose proof fails).
+    verify(gathered, r) (optional) -> whether rank r's partials are to be used at all.
     verify_all(gathered) (optional) -> one verdict per rank, all shares checked in one batch (takes precedence).
+    These two hooks drop a share as a whole: they exist for the plumbing tests on CPU tensors.  The CUDA drivers below do not use
+    them -- they filter per ciphertext, as CombinePartialDecryptionsZKP does (thresholdkey.go:164-172), inside
+    `gpu_threshold_round_shares` (pgpu_combine_verified_dev).
     Returns (plaintext slice tensor, (lo, hi))."""
     import torch
     mine = partial_decrypt()
@@ -128,87 +130,13 @@ def gpu_safe_prime_search(dist, rank: int, world: int, bit_len: int, random_read
 
 
 def gpu_threshold_round(dist, tsk, c_dev, count: int, world: int, rank: int, with_zkp_r=None):
-    """BASELINE config 4 on the CUDA engine: tsk = this rank's ThresholdSecretKey (share id rank+1),
-    c_dev = device tensor of `count` n2-width ciphertext records (the same on every rank).
-    with_zkp_r: optional device tensor of count n2-width r values -> proofs are produced, all-gathered and
-    verified on the combining rank before its slice is combined."""
-    import torch
-    from ._lib import check, lib
-    w2, wn = tsk.w_n2, tsk.w_n
-    vp = lambda t: C.c_void_p(t.data_ptr())
-    proofs = {}
-    # the engine enqueues on a torch-owned side stream so that NCCL (which orders against torch's current
-    # stream) sees its results; stream 0 would mean "the context's private stream" to pgpu_ctx_set_stream
-    stream = torch.cuda.Stream(c_dev.device)
-    stream.wait_stream(torch.cuda.current_stream(c_dev.device))
-    check(lib.pgpu_ctx_set_stream(tsk._ctx, C.c_void_p(stream.cuda_stream)), tsk._ctx)
-
-    def partial_decrypt():
-        out = torch.empty(count * w2, dtype=torch.uint8, device=c_dev.device)
-        if with_zkp_r is None:
-            check(lib.pgpu_partial_decrypt_dev(tsk._ctx, count, vp(c_dev), vp(out)), tsk._ctx)
-        else:
-            e = torch.empty(count * 32, dtype=torch.uint8, device=c_dev.device)
-            z = torch.empty(count * tsk.w_z, dtype=torch.uint8, device=c_dev.device)
-            check(lib.pgpu_pdec_zkp_prove_dev(tsk._ctx, count, vp(c_dev), vp(with_zkp_r), vp(out), vp(e), vp(z)), tsk._ctx)
-            ge = torch.empty(world * e.numel(), dtype=torch.uint8, device=c_dev.device)
-            gz = torch.empty(world * z.numel(), dtype=torch.uint8, device=c_dev.device)
-            if world > 1:
-                stream.synchronize()
-                dist.all_gather_into_tensor(ge, e)
-                dist.all_gather_into_tensor(gz, z)
-            else:
-                ge.copy_(e); gz.copy_(z)
-            proofs["e"], proofs["z"] = ge, gz
-        stream.synchronize()
-        return out
-
-    lo, hi = shard_range(count, world, rank)
-
-    def verify(gathered, r):
-        if with_zkp_r is None:
-            return True
-        n = hi - lo
-        ok = torch.zeros(max(n, 1), dtype=torch.uint8, device=c_dev.device)
-        dec = gathered[(r * count + lo) * w2:(r * count + hi) * w2]
-        e = proofs["e"][(r * count + lo) * 32:(r * count + hi) * 32]
-        z = proofs["z"][(r * count + lo) * tsk.w_z:(r * count + hi) * tsk.w_z]
-        check(lib.pgpu_pdec_zkp_verify_dev(tsk._ctx, n, r + 1, vp(c_dev[lo * w2:hi * w2]), vp(dec), vp(e), vp(z), vp(ok)), tsk._ctx)
-        stream.synchronize()
-        return bool(ok[:n].all().item()) if n else True
-
-    def verify_all(gathered):
-        n = hi - lo
-        if n == 0:
-            return [True] * world
-        rows = lambda buf, w: torch.cat([buf[(r * count + lo) * w:(r * count + hi) * w] for r in range(world)])
-        dec, e, z = rows(gathered, w2), rows(proofs["e"], 32), rows(proofs["z"], tsk.w_z)
-        c_rep = c_dev[lo * w2:hi * w2].repeat(world)
-        ok = torch.zeros(world * n, dtype=torch.uint8, device=c_dev.device)
-        idarr = (C.c_int * world)(*range(1, world + 1))
-        check(lib.pgpu_pdec_zkp_verify_multi_dev(tsk._ctx, n, world, idarr, vp(c_rep), vp(dec), vp(e), vp(z), vp(ok)), tsk._ctx)
-        stream.synchronize()
-        return [bool(v) for v in ok.view(world, n).all(dim=1).cpu()]
-
-    def combine(gathered, ids, lo, hi):
-        n = hi - lo
-        out = torch.empty(max(n, 1) * wn, dtype=torch.uint8, device=c_dev.device)
-        # shares are rows of the gathered buffer: pick the rows of `ids`; a full set is used in place
-        if ids == list(range(1, world + 1)):
-            base, stride = gathered[lo * w2:], count
-        else:
-            rows = [gathered[((i - 1) * count + lo) * w2:((i - 1) * count + hi) * w2] for i in ids]
-            base, stride = torch.cat(rows) if rows else gathered[:0], n
-        idarr = (C.c_int * max(len(ids), 1))(*ids)
-        check(lib.pgpu_combine_strided_dev(tsk._ctx, n, len(ids), idarr, vp(base), max(stride, n), vp(out)), tsk._ctx)
-        stream.synchronize()
-        return out[:n * wn]
-
-    with torch.cuda.stream(stream):
-        res = threshold_round(dist, rank, world, count, w2, partial_decrypt, combine, None, verify_all if with_zkp_r is not None else None)
-    stream.synchronize()
-    check(lib.pgpu_ctx_set_stream(tsk._ctx, None), tsk._ctx)
-    return res
+    """BASELINE config 4 with ONE share-holder per rank: tsk = this rank's ThresholdSecretKey (share id rank+1), c_dev = device
+    tensor of `count` n2-width ciphertext records (the same on every rank), with_zkp_r = optional device tensor of count
+    n2-width r values (proofs are produced, all-gathered and verified before the slice is combined).  It is
+    `gpu_threshold_round_shares` with a single local share, so the proofs filter PER CIPHERTEXT like the reference's
+    CombinePartialDecryptionsZKP (thresholdkey.go:164-172).  Returns (plaintext slice tensor, (lo, hi))."""
+    out, span, _ = gpu_threshold_round_shares(dist, [tsk], c_dev, count, world, rank, None if with_zkp_r is None else [with_zkp_r])
+    return out, span
 
 
 def gpu_threshold_round_shares(dist, tsks, c_dev, count: int, world: int, rank: int, zkp_r=None, keep=None):
