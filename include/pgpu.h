@@ -323,6 +323,11 @@ int pgpu_selftest_program(int kind, const uint8_t* mod_be, size_t mod_len, const
                           const uint8_t* shared_exp_be, size_t shared_len, const uint32_t* item_exps, uint32_t exp_limbs, uint32_t k, uint32_t pre,
                           uint8_t* out, size_t out_cap, uint32_t* n_out, uint32_t* n_sqr, uint32_t* n_mul);
 
+/* the micro-program (csrc/vm.h ops, OP_END included) pgpu_selftest_program compiled last on the calling thread and the number of
+ * table entries it uses: tests/test_mont_host_emulation.py runs it through the interpreter's SOURCE (csrc/vm_run.cuh) on an
+ * emulated warp of CPU threads.  *n_ops is set even when the buffer is too small.  Test hook only. */
+int pgpu_selftest_last_program(uint32_t* ops, size_t cap, size_t* n_ops, uint32_t* tbl_entries);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,7 @@ SIGNATURES = {
     "pgpu_selftest_program": (C.c_int, [C.c_int, _u8p, _sz, _u8p, _sz, _u8p, _sz, _p, C.c_uint32, C.c_uint32, C.c_uint32, _p, _sz,
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pgpu_selftest_bn": (C.c_int, [C.c_int, _u8p, _sz, _u8p, _sz, _u8p, _sz, C.c_char_p, C.POINTER(_sz)]),
+    "pgpu_selftest_last_program": (C.c_int, [_p, _sz, C.POINTER(_sz), C.POINTER(C.c_uint32)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

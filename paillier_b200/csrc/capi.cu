@@ -60,6 +60,13 @@ int host_vm_run(const Program& P, const BigU& N, const BigU& in0, const uint32_t
 }  // namespace
 
 
+namespace {
+// the program pgpu_selftest_program compiled last on this thread (pgpu_selftest_last_program hands it to the CPU test that runs
+// the interpreter's source on an emulated warp)
+std::vector<uint32_t>& selftest_last_ops() { static thread_local std::vector<uint32_t> v; return v; }
+uint32_t& selftest_last_tbl() { static thread_local uint32_t t = 0; return t; }
+}  // namespace
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -1142,6 +1149,8 @@ int pgpu_selftest_program(int kind, const uint8_t* mod_be, size_t mod_len, const
         default: return fail(nullptr, PGPU_ERR_ARG, "bad program kind");
     }
     P.ops.push_back(vm_op(OP_END, 0));
+    selftest_last_ops() = P.ops;
+    selftest_last_tbl() = P.tbl_entries;
     std::vector<BigU> outs;
     const int rc = host_vm_run(P, N, base, item_exps, exp_limbs, kind == 2 ? exp_limbs : 0u, outs);
     if (rc) return fail(nullptr, rc, "host interpreter: op not supported");
@@ -1155,6 +1164,17 @@ int pgpu_selftest_program(int kind, const uint8_t* mod_be, size_t mod_len, const
     if (n_mul) *n_mul = P.n_mul;
     return PGPU_OK;
     GUARD_END(nullptr)
+}
+
+int pgpu_selftest_last_program(uint32_t* ops, size_t cap, size_t* n_ops, uint32_t* tbl_entries) {
+    if (!n_ops) return fail(nullptr, PGPU_ERR_ARG, "null argument");
+    const std::vector<uint32_t>& v = selftest_last_ops();
+    *n_ops = v.size();
+    if (tbl_entries) *tbl_entries = selftest_last_tbl();
+    if (v.empty()) return fail(nullptr, PGPU_ERR_STATE, "no program compiled by pgpu_selftest_program on this thread yet");
+    if (!ops || cap < v.size()) return fail(nullptr, PGPU_ERR_ARG, "ops buffer too small");
+    std::copy(v.begin(), v.end(), ops);
+    return PGPU_OK;
 }
 
 }  // extern "C"

@@ -22,11 +22,14 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct uint2 { uint32_t x, y; };
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 struct HostDim3 { unsigned x = 0, y = 0, z = 0; };
-inline thread_local HostDim3 threadIdx;
+inline thread_local HostDim3 threadIdx, blockIdx;          // one emulated block = one warp: blockIdx.x = 0
+inline const HostDim3 blockDim{32, 1, 1};
 
 namespace hostwarp {
 struct Warp {
@@ -35,6 +38,7 @@ struct Warp {
 };
 inline thread_local Warp* warp = nullptr;
 inline thread_local int lane = 0;
+inline uint4* shared_mem = nullptr;                        // the block's dynamic shared memory (vm_run.cuh: vm_smem)
 
 // every lane deposits `raw`, all meet, every lane reads the slot it wants, all meet again (so that the next collective
 // cannot overwrite a slot somebody has not read yet)

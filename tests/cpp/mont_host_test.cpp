@@ -13,6 +13,7 @@
 
 #include "../../paillier_b200/csrc/mont.cuh"
 #include "../../paillier_b200/csrc/mont52.cuh"
+#include "../../paillier_b200/csrc/vm_run.cuh"
 
 using Limbs = std::vector<uint32_t>;
 
@@ -118,14 +119,88 @@ static void run52_short(const Limbs& n, uint32_t lim, const std::vector<Limbs>& 
     }
 }
 
+// ---- the interpreter itself (vm_run.cuh: what powm_vm / powm_vm52 wrap) on one emulated block of one warp: 32 / TPI resident
+// groups, group g takes items g, g + n_groups, ...; a program the LIBRARY compiled (pgpu_selftest_last_program) is run for every
+// item with the table, dump and constant buffers laid out as engine.cu's run_vm lays them out
+struct VmJob {
+    Limbs n, kconst, ops, in0, exps, out0, out1;
+    uint32_t n_items = 0, in_limbs = 0, exp_stride = 0, exp_bits = 0, exp_sub = 0, out0_per_item = 1, tbl_entries = 1, flags = 0;
+};
+template <class B>
+static void run_vm_job(VmJob& J) {
+    constexpr int S = B::S32, TPI = B::TPI_, G = 32 / TPI, TS = TPI * B::TBL;
+    J.out0.assign((size_t)J.n_items * J.out0_per_item * S, 0);
+    J.out1.assign((size_t)J.n_items * S, 0);
+    Limbs table((size_t)std::max<uint32_t>(J.tbl_entries, 1) * G * TS + 4, 0), dump((size_t)G * S, 0);
+    std::vector<uint4> smem((size_t)pgpu::Mont<4, 8, true>::SQR_ROWS * 32 * 8 + 1);     // more than any shape's SQR_ROWS * 32
+    hostwarp::shared_mem = smem.data();
+    pgpu::VmParams P{};
+    P.prog = J.ops.data(); P.n_items = J.n_items; P.mod = J.n.data(); P.np0 = neg_inv32(J.n[0]); P.kconst = J.kconst.data();
+    for (int i = 0; i < pgpu::VM_MAX_IN; ++i) P.in_div[i] = 1;
+    P.in[0] = J.in0.data(); P.in_stride[0] = J.in_limbs; P.in_limbs[0] = J.in_limbs;
+    P.out[0] = J.out0.data(); P.out_stride[0] = J.out0_per_item * S; P.out_limbs[0] = S;
+    P.out[1] = J.out1.data(); P.out_stride[1] = S; P.out_limbs[1] = S;
+    P.exp = J.exps.data(); P.exp_stride = J.exp_stride; P.exp_bits = J.exp_bits; P.exp_sub = J.exp_sub;
+    P.table = table.data(); P.n_groups = G; P.flags = J.flags; P.dump = dump.data();
+    hostwarp::run_warp([&](int) { pgpu::vm_run<B>(P); });
+}
+
 // the shapes powm.cu builds (PGPU_FOR_EACH_SHAPE with NSM = SqrShape<TPI, L>::value, PGPU_FOR_EACH_SHAPE52)
 #define SHAPES32(X) X(2, 16, false) X(4, 8, true) X(4, 16, true) X(8, 8, false) X(8, 12, false) X(4, 24, false) X(8, 16, false) \
                     X(16, 8, false) X(4, 32, false) X(32, 4, false) X(8, 24, false) X(16, 12, false) X(32, 6, false)
 #define SHAPES52(X) X(4, 5, 32) X(4, 10, 64) X(8, 5, 64) X(4, 15, 96) X(8, 8, 96) X(8, 10, 128) X(8, 15, 192) X(16, 8, 192)
+// the interpreter is instantiated for a subset (compile time): both squaring shapes, the widest integer shape, two FP64 shapes
+// incl. the one that serves 4096-bit moduli
+#define VM_SHAPES32(X) X(4, 8, true) X(4, 16, true) X(8, 8, false) X(4, 32, false)
+#define VM_SHAPES52(X) X(4, 5, 32) X(8, 10, 128)
 
 int main() {
     std::string kind;
     while (std::cin >> kind) {
+        if (kind == "vm32" || kind == "vm52") {
+            // vm32 TPI L | vm52 TPI L S32 ; flags n_items in_limbs exp_stride exp_bits exp_sub out0_per_item tbl_entries ; n ; R1 R2 ;
+            // n_ops ops... ; per item: base exps(one number of exp_stride limbs)   ->  per item: out0 records..., out1
+            int tpi, l, s32 = 0;
+            std::cin >> tpi >> l;
+            if (kind == "vm52") std::cin >> s32; else s32 = tpi * l;
+            VmJob J;
+            size_t n_ops;
+            std::string nh, r1, r2;
+            std::cin >> J.flags >> J.n_items >> J.in_limbs >> J.exp_stride >> J.exp_bits >> J.exp_sub >> J.out0_per_item >> J.tbl_entries >> nh >> r1 >> r2 >> n_ops;
+            J.n = parse_hex(nh, s32);
+            J.kconst.assign((size_t)16 * s32, 0);                                   // engine.hpp: K_R2 = 0, K_R1 = 1, K_ONE = 2 of K_SLOTS = 16
+            const Limbs R2 = parse_hex(r2, s32), R1 = parse_hex(r1, s32);
+            std::copy(R2.begin(), R2.end(), J.kconst.begin());
+            std::copy(R1.begin(), R1.end(), J.kconst.begin() + s32);
+            J.kconst[2 * (size_t)s32] = 1;
+            for (size_t i = 0; i < n_ops; ++i) { std::string o; std::cin >> o; J.ops.push_back((uint32_t)std::stoul(o, nullptr, 16)); }
+            for (uint32_t i = 0; i < J.n_items; ++i) {
+                std::string b, e; std::cin >> b >> e;
+                const Limbs bl = parse_hex(b, J.in_limbs), el = parse_hex(e, std::max<uint32_t>(J.exp_stride, 1));
+                J.in0.insert(J.in0.end(), bl.begin(), bl.end());
+                J.exps.insert(J.exps.end(), el.begin(), el.begin() + J.exp_stride);
+            }
+            J.in0.resize(J.in0.size() + 8, 0); J.exps.resize(J.exps.size() + 8, 0);
+            bool done = false;
+            if (kind == "vm32") {
+#define X(T, LL, NSM) if (!done && tpi == T && l == LL) { run_vm_job<pgpu::Vm32<T, LL>>(J); done = true; }
+                VM_SHAPES32(X)
+#undef X
+            } else {
+#define X(T, LL, SS) if (!done && tpi == T && l == LL && s32 == SS) { run_vm_job<pgpu::Vm52<T, LL, SS>>(J); done = true; }
+                VM_SHAPES52(X)
+#undef X
+            }
+            if (!done) { std::cerr << "shape not built: " << kind << " " << tpi << " " << l << "\n"; return 2; }
+            for (uint32_t i = 0; i < J.n_items; ++i) {
+                for (uint32_t j = 0; j < J.out0_per_item; ++j) {
+                    const size_t o = ((size_t)i * J.out0_per_item + j) * s32;
+                    std::cout << to_hex(Limbs(J.out0.begin() + o, J.out0.begin() + o + s32)) << " ";
+                }
+                std::cout << to_hex(Limbs(J.out1.begin() + (size_t)i * s32, J.out1.begin() + (size_t)(i + 1) * s32)) << "\n";
+            }
+            continue;
+        }
         int tpi, l, third;
         uint32_t lim = 0;
         std::string nh;

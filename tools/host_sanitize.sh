@@ -84,3 +84,7 @@ first = re.search(r"Read of size.*?\n\s+#0 (.*?) \(", r2.stderr, re.S)
 print(f"negative control (one __syncwarp of Mont::sqr removed): rc {r2.returncode}, {neg_races} reports; first: {first.group(1)[:160] if first else None}")
 sys.exit(1 if (r.returncode or races or not neg_races) else 0)
 PY
+# the whole emulation test file under ThreadSanitizer: the multipliers as above plus the INTERPRETER's source (csrc/vm_run.cuh)
+# running library-compiled programs -- table, dump and output accesses of the resident groups
+PGPU_EMU_CXXFLAGS="-fsanitize=thread -g" TSAN_OPTIONS="halt_on_error=0" python -m pytest tests/test_mont_host_emulation.py -q
+g++ -std=c++20 -O1 -frounding-math -pthread -Wno-unknown-pragmas tests/cpp/mont_host_test.cpp -o tests/cpp/mont_host_test   # leave the plain build behind
