@@ -103,6 +103,51 @@ class DDLEQProof:
     Instances: List[DDLEQProofInstance]
 
 
+class DeviceBuffer:
+    """Device memory on a key's device (pgpu_buf_*): what the *Dev methods take, so that ciphertexts stay on the GPU between
+    Encrypt / ConstMult / Add / Decrypt calls (the callers of operations.go:11-64).  Made by `key.NewDeviceBuffer(nbytes)`;
+    free it (or let it be collected) before the key it came from is closed.  The same type as Go's DeviceBuffer and
+    paillier::DeviceBuffer of the C++ mirror."""
+
+    def __init__(self, ctx, nbytes: int):
+        self._h = C.c_void_p()
+        check(lib.pgpu_buf_alloc(ctx, nbytes, C.byref(self._h)), ctx)
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return C.c_void_p(lib.pgpu_buf_ptr(self._h))
+
+    def __len__(self) -> int:
+        return lib.pgpu_buf_size(self._h)
+
+    def Upload(self, records, offset: int = 0) -> "DeviceBuffer":
+        a = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+        check(lib.pgpu_buf_upload(self._h, offset, _ptr(a), a.size))
+        return self
+
+    def Download(self, nbytes: Optional[int] = None, offset: int = 0) -> np.ndarray:
+        out = np.empty(len(self) - offset if nbytes is None else nbytes, dtype=np.uint8)
+        check(lib.pgpu_buf_download(self._h, offset, _ptr(out), out.size))
+        return out
+
+    def Free(self) -> None:
+        if self._h is not None and self._h.value:
+            check(lib.pgpu_buf_free(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Free()
+        except Exception:
+            pass
+
+
+def _need(buf: DeviceBuffer, nbytes: int) -> C.c_void_p:
+    if len(buf) < nbytes:
+        raise ValueError("device buffer smaller than the batch")
+    return buf.ptr
+
+
 class PublicKey:
     """paillier.go:46-56 with g = n+1 (paillier.go:147); owns one engine context on `device`.
     H and K (alternative encryption, paillier.go:151,158-166) are optional."""
@@ -531,6 +576,32 @@ class PublicKey:
                                     _ptr(ok)), self._ctx)
         return ok
 
+    # -- device-resident batches: enqueued on the context's stream, NOT synchronised; Sync() waits for them ---------------
+    def NewDeviceBuffer(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self._ctx, nbytes)
+
+    def Sync(self) -> None:
+        check(lib.pgpu_ctx_sync(self._ctx), self._ctx)
+
+    def EncryptWithRDev(self, count: int, m: DeviceBuffer, r: DeviceBuffer, c: DeviceBuffer) -> None:
+        """c[i] = EncryptWithR(m[i], r[i]) (paillier.go:185-187): n-width m and r, n2-width c"""
+        check(lib.pgpu_encrypt_with_r_dev(self._ctx, count, _need(m, count * self.w_n), _need(r, count * self.w_n), _need(c, count * self.w_n2)),
+              self._ctx)
+
+    def ConstMultDev(self, count: int, c: DeviceBuffer, k: DeviceBuffer, k_bytes: int, out: DeviceBuffer) -> None:
+        """out[i] = ConstMult(c[i], k[i]) (operations.go:58-64): k = k_bytes-wide little-endian unsigned scalars (multiple of 4)"""
+        check(lib.pgpu_const_mult_dev(self._ctx, count, _need(c, count * self.w_n2), _need(k, count * k_bytes), k_bytes,
+                                      _need(out, count * self.w_n2)), self._ctx)
+
+    def AddPairsDev(self, count: int, a: DeviceBuffer, b: DeviceBuffer, out: DeviceBuffer) -> None:
+        """out[i] = Add(a[i], b[i]) (operations.go:11-29); out may be a or b"""
+        check(lib.pgpu_add_pairs_dev(self._ctx, count, _need(a, count * self.w_n2), _need(b, count * self.w_n2), _need(out, count * self.w_n2)),
+              self._ctx)
+
+    def AddReduceDev(self, count: int, c: DeviceBuffer, out: DeviceBuffer) -> None:
+        """out = Add(c[0], ..., c[count-1]) as one tree reduction"""
+        check(lib.pgpu_add_reduce_dev(self._ctx, count, _need(c, count * self.w_n2), _need(out, self.w_n2)), self._ctx)
+
     # -- introspection -------------------------------------------------------
     def launch_count(self) -> int:
         v = C.c_uint64()
@@ -592,6 +663,10 @@ class SecretKey(PublicKey):
         out = np.empty(count * self.w_n, dtype=np.uint8)
         check(lib.pgpu_decrypt(self._ctx, count, _ptr(c), _ptr(out)), self._ctx)
         return out
+
+    def DecryptDev(self, count: int, c: DeviceBuffer, m: DeviceBuffer) -> None:
+        """m[i] = Decrypt(c[i]) (paillier.go:292-303, CRT over p^2, q^2) on device buffers; enqueued, see Sync()"""
+        check(lib.pgpu_decrypt_dev(self._ctx, count, _need(c, count * self.w_n2), _need(m, count * self.w_n)), self._ctx)
 
     def DecryptBatch(self, cts: Sequence[Ciphertext]) -> List[int]:
         """N x SecretKey.Decrypt (paillier.go:292-303); one level per batch"""
@@ -826,6 +901,10 @@ class ThresholdSecretKey(ThresholdPublicKey):
         dec, e, z = self.zkp_prove_records(to_records(cs, self.w_n2), to_records(rs, self.w_n2))
         return [PartialDecryptionZKP(self.ID, d, ee, zz, c) for d, ee, zz, c in
                 zip(from_records(dec, self.w_n2), from_records(e, 32), from_records(z, self.w_z), cs)]
+
+    def PartialDecryptDev(self, count: int, c: DeviceBuffer, out: DeviceBuffer) -> None:
+        """out[i] = PartialDecrypt(c[i]) (thresholdkey.go:192-201) on device buffers of n2-width records; enqueued, see Sync()"""
+        check(lib.pgpu_partial_decrypt_dev(self._ctx, count, _need(c, count * self.w_n2), _need(out, count * self.w_n2)), self._ctx)
 
     def PartialDecryptBatch(self, cs: Sequence[int]) -> List[PartialDecryption]:
         """N x ThresholdSecretKey.PartialDecrypt (thresholdkey.go:192-201)"""

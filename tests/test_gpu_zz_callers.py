@@ -148,3 +148,38 @@ def test_cpp_mirror_callers():
     r = subprocess.run([build_callers_test()], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "callers ok" in r.stdout
+
+
+def test_python_device_buffers_chain():
+    """DeviceBuffer and the *Dev methods of the Python mirror (the same objects the Go binding and the C++ mirror have):
+    Encrypt -> ConstMult -> AddPairs -> AddReduce -> Decrypt without leaving the GPU, against the host-buffer batch methods"""
+    import numpy as np
+    from paillier_b200 import synth
+    from paillier_b200.api import SecretKey, from_records, to_records
+    p, q = synth.load_key("paillier_2048")
+    n = p * q
+    sk = SecretKey(n, p=p, q=q)
+    count = 40
+    rnd = random.Random(61)
+    ms = [rnd.randrange(n) for _ in range(count)]
+    rs = sk._draw_units(count, rnd)
+    ks = [rnd.getrandbits(64) | 1 for _ in range(count)]
+    bm, br = sk.NewDeviceBuffer(count * sk.w_n).Upload(to_records(ms, sk.w_n)), sk.NewDeviceBuffer(count * sk.w_n).Upload(to_records(rs, sk.w_n))
+    bk = sk.NewDeviceBuffer(count * 8).Upload(np.array(ks, dtype=np.uint64))
+    bc, bc2, bt, bo = sk.NewDeviceBuffer(count * sk.w_n2), sk.NewDeviceBuffer(count * sk.w_n2), sk.NewDeviceBuffer(sk.w_n2), sk.NewDeviceBuffer(sk.w_n)
+    assert len(bc) == count * sk.w_n2
+    sk.EncryptWithRDev(count, bm, br, bc)
+    sk.ConstMultDev(count, bc, bk, 8, bc2)          # k_i * m_i
+    sk.AddPairsDev(count, bc2, bc, bc2)             # + m_i
+    sk.AddReduceDev(count, bc2, bt)
+    sk.DecryptDev(1, bt, bo)
+    sk.Sync()
+    cts = sk.EncryptWithRBatch(ms, rs)
+    assert from_records(bc.Download(), sk.w_n2) == [c.C for c in cts]
+    assert from_records(bo.Download(), sk.w_n) == [sum((k + 1) * m for k, m in zip(ks, ms)) % n]
+    assert from_records(bc.Download(sk.w_n2, offset=3 * sk.w_n2), sk.w_n2) == [cts[3].C]
+    with pytest.raises(ValueError):
+        sk.EncryptWithRDev(count + 1, bm, br, bc)   # a batch larger than its buffers
+    for b in (bm, br, bk, bc, bc2, bt, bo):
+        b.Free()
+    sk.close()
